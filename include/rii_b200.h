@@ -1,0 +1,121 @@
+/* rii_b200.h -- C ABI of librii_b200.so: the B200 (sm_100a) implementation of Rii's ADC hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one member of the reference's pybind11 class
+ * `main.RiiCpp` (matsui528/rii v0.2.12, src/main.cpp:12-54; implementation src/rii.h) and is what a
+ * maintainer's FFI stub (ctypes / pybind11 / cgo) binds -- see INTEGRATION.md.  Plain pointers and sizes
+ * only; no C++/torch types cross the boundary.  All functions return 0 (or a non-negative count) on
+ * success and a negative code on failure, with the message available from rii_last_error(); nothing
+ * throws and nothing aborts (the reference asserts/terminates, src/rii.h:166-170).
+ *
+ * Pointers named `h_*`/unprefixed are HOST pointers; `d_*` are DEVICE pointers on the index's GPU.
+ * Results use the total order (distance ascending, id ascending); ids are global 64-bit ids.
+ */
+#ifndef RII_B200_H
+#define RII_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rii_index rii_index_t;
+
+#define RII_OK 0
+#define RII_ERR_ARG (-1)      /* invalid argument (the reference would assert) */
+#define RII_ERR_STATE (-2)    /* call not valid in this state (e.g. update without coarse centers) */
+#define RII_ERR_CUDA (-3)     /* CUDA runtime error */
+#define RII_ERR_LIMIT (-4)    /* shape outside the implemented range */
+
+#define RII_METHOD_LINEAR 0
+#define RII_METHOD_IVF 1
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *rii_last_error(void);
+/* "0.2.12+b200.<n>": tracks main.__version__ (src/main.cpp:56-60). */
+const char *rii_version(void);
+/* Number of kernels this library launched on behalf of the calling process (bench.py gpu_launches). */
+int64_t rii_launch_count(void);
+
+/* RiiCpp(codewords, verbose)  src/main.cpp:14, src/rii.h:86-106.
+ * codewords: float32 (M, Ks, Ds) row-major, copied.  Ks <= 256 (rii/rii.py:35).  device: CUDA ordinal.
+ * l2_variant: accumulator width of the reference build whose fvec_L2sqr rounding is reproduced
+ * (src/distance.h:113,172,219): 16 = AVX-512, 8 = AVX, 4 = SSE, 0 = pick from this host's CPU flags.
+ * (The variants differ only when Ds >= 16.) */
+int rii_create(const float *codewords, int M, int Ks, int Ds, int verbose, int device, int l2_variant,
+               rii_index_t **out);
+int rii_destroy(rii_index_t *h);
+
+/* RiiCpp::add_codes(codes, update_flag)  src/main.cpp:16, src/rii.h:158-193.  codes: uint8 (n, M). */
+int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag);
+/* RiiCpp::reconfigure(nlist, iter)  src/main.cpp:15, src/rii.h:108-156 (+ PQk-means src/pqkmeans.cpp). */
+int rii_reconfigure(rii_index_t *h, int nlist, int iter);
+/* RiiCpp::clear()  src/main.cpp:28, src/rii.h:328-333. */
+int rii_clear(rii_index_t *h);
+
+/* RiiCpp::query_linear(query, topk, target_ids)  src/main.cpp:17-21, src/rii.h:195-242.
+ * query: float32 (M*Ds); target_ids: int64 (S) or NULL/S=0 for all.  Writes <= topk results, returns the
+ * count (== topk) or a negative error. */
+int64_t rii_query_linear(rii_index_t *h, const float *query, int topk, const int64_t *target_ids, int64_t S,
+                         int64_t *out_ids, float *out_dists);
+/* RiiCpp::query_ivf(query, topk, target_ids, L)  src/main.cpp:22-27, src/rii.h:244-326.
+ * target_ids must be sorted ascending (src/rii.h:294).  Returns 0 for the reference's empty result
+ * (src/rii.h:325). */
+int64_t rii_query_ivf(rii_index_t *h, const float *query, int topk, const int64_t *target_ids, int64_t S, int64_t L,
+                      int64_t *out_ids, float *out_dists);
+/* Batch entry (new: the reference takes one query per call, rii/rii.py:251).  queries: float32 (B, M*Ds);
+ * one shared target_ids set; method RII_METHOD_*; L ignored for linear.  out_ids/out_dists: (B, topk),
+ * out_counts: (B) results per query. */
+int rii_query_batch(rii_index_t *h, const float *queries, int B, int topk, const int64_t *target_ids, int64_t S,
+                    int64_t L, int method, int64_t *out_ids, float *out_dists, int32_t *out_counts);
+/* Same with DEVICE buffers, enqueued on `stream` (a cudaStream_t, 0 = the index's own stream) and not
+ * synchronised unless the rare full-ranking re-run (walk beyond w) is needed.
+ * d_target_ids: device int64 (S) or NULL. */
+int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids,
+                        int64_t S, int64_t L, int method, int64_t *d_out_ids, float *d_out_dists,
+                        int32_t *d_out_counts, void *stream);
+
+/* Properties  src/main.cpp:29-34. */
+int64_t rii_get_N(const rii_index_t *h);
+int rii_get_nlist(const rii_index_t *h);
+int rii_get_verbose(const rii_index_t *h);
+int rii_set_verbose(rii_index_t *h, int verbose);
+int rii_get_dims(const rii_index_t *h, int *M, int *Ks, int *Ds);
+/* flattened_codes -> (N, M) uint8; coarse_centers -> (nlist, M) uint8; posting_lists -> CSR
+ * (offsets int64 (nlist+1), ids int32 (N)).  Caller allocates. */
+int rii_copy_codes(const rii_index_t *h, uint8_t *out);
+int rii_copy_coarse_centers(const rii_index_t *h, uint8_t *out);
+int rii_copy_posting_lists(const rii_index_t *h, int64_t *offsets, int32_t *ids);
+/* __setstate__  src/main.cpp:39-53: replace codes / coarse centers / posting lists wholesale. */
+int rii_set_state(rii_index_t *h, const uint8_t *coarse_centers, int nlist, const uint8_t *codes, int64_t N,
+                  const int64_t *offsets, const int32_t *ids);
+
+/* ---- building blocks of the path, exposed for parity tests and multi-GPU orchestration ---------- */
+/* K1: distance tables of B queries -> out (B, M, Ks) float32 (host).  src/rii.h:361-373. */
+int rii_dtable(rii_index_t *h, const float *queries, int B, float *out);
+/* ADC distance of every stored code to one query -> out (N) float32 (host).  src/rii.h:386-394. */
+int rii_adist_all(rii_index_t *h, const float *query, float *out);
+/* K6: nearest coarse center (symmetric distance, first minimum wins) of n codes against K centers.
+ * src/pqkmeans.cpp:193-218.  out_assign int32 (n), out_dist float32 (n) or NULL. */
+int rii_assign(rii_index_t *h, const uint8_t *codes, int64_t n, const uint8_t *centers, int K, int32_t *out_assign,
+               float *out_dist);
+/* Codeword distance matrices (M, Ks, Ks) float32.  src/pqkmeans.cpp:23-34. */
+int rii_sym_matrices(rii_index_t *h, float *out);
+
+/* ---- id-range sharding (one index object per GPU) -------------------------- */
+/* This shard holds global ids [id_base, id_base + N_local) of an index of N_total codes. */
+int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total);
+/* Replace coarse centers and assign every local code (UpdatePostingLists(0, N), src/rii.h:335-359). */
+int rii_set_coarse_centers(rii_index_t *h, const uint8_t *centers, int nlist);
+/* PQk-means on a given sample (src/pqkmeans.cpp:46-133): sample uint8 (ns, M) already in the reference's
+ * shuffled order -> centers_out (nlist, M). */
+int rii_fit_coarse(rii_index_t *h, const uint8_t *sample, int64_t ns, int nlist, int iter, uint8_t *centers_out);
+/* Local list lengths (nlist) int32. */
+int rii_copy_list_lengths(const rii_index_t *h, int32_t *out);
+/* Global list lengths and the lengths held by lower ranks (both (nlist) int32), from the all-gather. */
+int rii_set_global_lengths(rii_index_t *h, const int32_t *glob_len, const int32_t *pre_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RII_B200_H */

@@ -1,0 +1,759 @@
+// sm_100a kernels of the ADC hot path.  Reference semantics are cited per kernel (file:line into
+// matsui528/rii v0.2.12); arithmetic is fp32 with explicit round-to-nearest sub/mul/add intrinsics so that
+// nvcc never contracts to FMA and never reassociates: results are bit-identical to the reference code as
+// written (oracle/_ref/strict_*, oracle/rii_oracle.cpp).
+#pragma once
+#include "topk.cuh"
+
+#define RII_THREADS 256
+#define RII_ROWS_PER_THREAD 4
+
+// ---------------------------------------------------------------------------------------------------
+// K1  distance table.  src/rii.h:361-373 (DTable) + src/distance.h:117-252 (fvec_L2sqr).
+// `variant` = accumulator width of the reference build being mirrored: 16 (AVX-512), 8 (AVX), 4 (SSE).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqdiff(float a, float b)
+{
+    float t = __fsub_rn(a, b);
+    return __fmul_rn(t, t);
+}
+
+__device__ float l2sqr_lanes(const float *__restrict__ x, const float *__restrict__ y, int d, int variant)
+{
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d >= 8) {
+        float a8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a8[i] = 0.f;
+        if (variant == 16) {
+            float a16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a16[i] = 0.f;
+            while (d >= 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a16[i] = __fadd_rn(a16[i], sqdiff(x[i], y[i]));
+                x += 16; y += 16; d -= 16;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a8[i] = __fadd_rn(a16[8 + i], a16[i]);
+        }
+        if (variant >= 8) {
+            while (d >= 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a8[i] = __fadd_rn(a8[i], sqdiff(x[i], y[i]));
+                x += 8; y += 8; d -= 8;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a4[i] = __fadd_rn(a8[4 + i], a8[i]);
+        } else {
+            while (d >= 8) {  // SSE build: 4-lane accumulator over every 4-block
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a4[i] = __fadd_rn(a4[i], sqdiff(x[i], y[i]));
+                x += 4; y += 4; d -= 4;
+            }
+        }
+    }
+    if (d >= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a4[i] = __fadd_rn(a4[i], sqdiff(x[i], y[i]));
+        x += 4; y += 4; d -= 4;
+    }
+    // masked tail (src/distance.h:44-65): absent lanes contribute (0-0)^2 = +0, and a + 0 == a
+    if (d > 0) a4[0] = __fadd_rn(a4[0], sqdiff(x[0], y[0]));
+    if (d > 1) a4[1] = __fadd_rn(a4[1], sqdiff(x[1], y[1]));
+    if (d > 2) a4[2] = __fadd_rn(a4[2], sqdiff(x[2], y[2]));
+    return __fadd_rn(__fadd_rn(a4[0], a4[1]), __fadd_rn(a4[2], a4[3]));
+}
+
+// grid (ceil(M*Ks/256), B).  Q: (B, M*Ds), cw: (M, Ks, Ds), T: (B, M*Ks)
+__global__ void __launch_bounds__(RII_THREADS) k_dtable(const float *__restrict__ Q, const float *__restrict__ cw,
+                                                        float *__restrict__ T, int M, int Ks, int Ds, int variant)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * Ks) return;
+    int m = e / Ks;
+    size_t b = blockIdx.y;
+    T[b * (size_t)(M * Ks) + e] = l2sqr_lanes(Q + b * (size_t)(M * Ds) + (size_t)m * Ds, cw + (size_t)e * Ds, Ds, variant);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ADC of one code row.  src/rii.h:375-394 (ADist): dist = 0; for m: dist += T[m][code[m]] -- sequential
+// fp32 adds in m order.  0 + x == x exactly for x >= +0, so the chain starts at the first lookup.
+// Row loads: a 32-byte row is one LDG.256 (sm_100a); rows that are multiples of 16/4 bytes use
+// 128-/32-bit loads; anything else falls back to byte loads.
+// ---------------------------------------------------------------------------------------------------
+template <int M, bool STREAM>
+__device__ __forceinline__ void load_row(const uint8_t *__restrict__ p, uint32_t (&w)[(M + 3) / 4])
+{
+    if constexpr (M % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < M / 32; ++i) {
+            if constexpr (STREAM)
+                asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[8 * i]), "=r"(w[8 * i + 1]), "=r"(w[8 * i + 2]), "=r"(w[8 * i + 3]),
+                               "=r"(w[8 * i + 4]), "=r"(w[8 * i + 5]), "=r"(w[8 * i + 6]), "=r"(w[8 * i + 7])
+                             : "l"(p + 32 * i));
+            else
+                asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[8 * i]), "=r"(w[8 * i + 1]), "=r"(w[8 * i + 2]), "=r"(w[8 * i + 3]),
+                               "=r"(w[8 * i + 4]), "=r"(w[8 * i + 5]), "=r"(w[8 * i + 6]), "=r"(w[8 * i + 7])
+                             : "l"(p + 32 * i));
+        }
+    } else if constexpr (M % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < M / 16; ++i) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    } else if constexpr (M % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < M / 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t *>(p) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < (M + 3) / 4; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * i + j < M) v |= (uint32_t)__ldg(p + 4 * i + j) << (8 * j);
+            w[i] = v;
+        }
+    }
+}
+
+template <int M>
+__device__ __forceinline__ float adc_regs(const float *lut, int Ks, const uint32_t (&w)[(M + 3) / 4])
+{
+    float acc = lut[w[0] & 0xff];
+#pragma unroll
+    for (int m = 1; m < M; ++m) acc = __fadd_rn(acc, lut[m * Ks + ((w[m >> 2] >> (8 * (m & 3))) & 0xff)]);
+    return acc;
+}
+
+// runtime-M fallback (byte loads)
+__device__ __forceinline__ float adc_bytes(const float *lut, int Ks, int M, const uint8_t *__restrict__ row)
+{
+    float acc = lut[__ldg(row)];
+    for (int m = 1; m < M; ++m) acc = __fadd_rn(acc, lut[m * Ks + __ldg(row + m)]);
+    return acc;
+}
+
+template <int M_T, bool STREAM>
+__device__ __forceinline__ float adc_row(const float *lut, int Ks, int M, const uint8_t *__restrict__ row)
+{
+    if constexpr (M_T > 0) {
+        uint32_t w[(M_T + 3) / 4];
+        load_row<M_T, STREAM>(row, w);
+        return adc_regs<M_T>(lut, Ks, w);
+    } else {
+        return adc_bytes(lut, Ks, M, row);
+    }
+}
+
+__device__ __forceinline__ void load_lut(float *lut, const float *__restrict__ T, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) lut[i] = __ldg(T + i);
+}
+
+// Dynamic shared memory layout shared by the scan kernels:
+//   float lut[M*Ks] | u64 keys[cap] | int count | u64 thr | (kernel specific tail)
+struct ScanSmem {
+    float *lut;
+    BlockTopk tk;
+    unsigned char *tail;
+};
+__device__ __forceinline__ ScanSmem carve_smem(unsigned char *base, int lut_floats, int cap, int k)
+{
+    ScanSmem s;
+    s.lut = reinterpret_cast<float *>(base);
+    size_t off = ((size_t)lut_floats * 4 + 15) & ~(size_t)15;
+    s.tk.keys = reinterpret_cast<u64 *>(base + off);
+    off += (size_t)cap * 8;
+    s.tk.thr = reinterpret_cast<u64 *>(base + off);
+    off += 8;
+    s.tk.count = reinterpret_cast<int *>(base + off);
+    off += 8;
+    s.tk.cap = cap;
+    s.tk.k = k;
+    s.tail = base + off;
+    return s;
+}
+static inline size_t scan_smem_bytes(int lut_floats, int cap, size_t tail)
+{
+    return (((size_t)lut_floats * 4 + 15) & ~(size_t)15) + (size_t)cap * 8 + 16 + tail;
+}
+
+// Emit the CTA's sorted top-k: either final (ids/dists/count) or a partial key list for k_merge.
+struct TopkOut {
+    u64 *partial;        // (B, parts, k) keys, RII_KEY_MAX padded   (when !final)
+    long long *out_ids;  // (B, k) global ids                         (when final)
+    float *out_dists;    // (B, k)
+    int *out_counts;     // (B)
+    long long id_base;
+    int final;
+};
+__device__ __forceinline__ void emit_topk(BlockTopk &tk, const TopkOut &o, int b, int part, int parts)
+{
+    tk.compact();
+    int n = *tk.count;
+    int k = tk.k;
+    if (o.final) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 key = tk.keys[i];
+            o.out_ids[(size_t)b * k + i] = o.id_base + (long long)key_id(key);
+            o.out_dists[(size_t)b * k + i] = key_dist(key);
+        }
+        if (threadIdx.x == 0) o.out_counts[b] = n;
+    } else {
+        u64 *dst = o.partial + ((size_t)b * parts + part) * k;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = i < n ? tk.keys[i] : RII_KEY_MAX;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2/K3  linear scan + top-k.  src/rii.h:195-242 (QueryLinear): all rows (S == 0) or exactly the given
+// target ids in the given order (S != 0), then top-k.  grid (parts, B).
+// ---------------------------------------------------------------------------------------------------
+struct LinearArgs {
+    const float *T;            // (B, M*Ks) distance tables
+    const uint8_t *codes;      // (N, M) local shard
+    const long long *tids;     // (S) global ids or null
+    long long S;
+    long long N;               // local rows
+    long long id_base;         // global id of local row 0
+    int M, Ks, k, cap;
+    TopkOut out;
+};
+
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_scan_linear(LinearArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.k);
+    const int b = blockIdx.y;
+    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    s.tk.init();
+
+    const long long ncand = a.S ? a.S : a.N;
+    long long chunk = (ncand + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + RII_THREADS - 1) / RII_THREADS * RII_THREADS;
+    long long pos = (long long)blockIdx.x * chunk;
+    long long end = pos + chunk < ncand ? pos + chunk : ncand;
+    bool first = true;
+    while (pos < end) {
+        const int R = first ? 1 : RII_ROWS_PER_THREAD;  // small first round: cheap first threshold
+        first = false;
+        s.tk.reserve(R * RII_THREADS);
+        const uint32_t thr_hi = s.tk.thr_hi();
+        const u64 thr_key = s.tk.thr_key();
+        long long row[RII_ROWS_PER_THREAD];
+#pragma unroll
+        for (int r = 0; r < RII_ROWS_PER_THREAD; ++r) {
+            row[r] = -1;
+            long long idx = pos + (long long)r * RII_THREADS + threadIdx.x;
+            if (r < R && idx < end) {
+                long long rr = a.S ? (a.tids[idx] - a.id_base) : idx;
+                if (rr >= 0 && rr < a.N) row[r] = rr;
+            }
+        }
+        float d[RII_ROWS_PER_THREAD];
+        if constexpr (M_T > 0) {
+            uint32_t w[RII_ROWS_PER_THREAD][(M_T + 3) / 4];
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) {
+                    if (a.S) load_row<M_T, false>(a.codes + row[r] * M_T, w[r]);
+                    else load_row<M_T, true>(a.codes + row[r] * M_T, w[r]);
+                }
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) d[r] = adc_regs<M_T>(s.lut, a.Ks, w[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) d[r] = adc_bytes(s.lut, a.Ks, a.M, a.codes + row[r] * a.M);
+        }
+#pragma unroll
+        for (int r = 0; r < RII_ROWS_PER_THREAD; ++r) {
+            if (row[r] >= 0 && __float_as_uint(d[r]) <= thr_hi) {
+                u64 key = pack_key(d[r], (uint32_t)row[r]);
+                if (key < thr_key) s.tk.push(key);
+            }
+        }
+        pos += (long long)R * RII_THREADS;
+    }
+    emit_topk(s.tk, a.out, b, blockIdx.x, gridDim.x);
+}
+
+// Merge `parts` partial key lists per query into the final top-k.  grid (B).
+__global__ void __launch_bounds__(RII_THREADS) k_merge(const u64 *__restrict__ partial, int parts, int k, int cap,
+                                                       TopkOut out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem s = carve_smem(smem_raw, 0, cap, k);
+    s.tk.init();
+    const int b = blockIdx.x;
+    const u64 *src = partial + (size_t)b * parts * k;
+    const long long n = (long long)parts * k;
+    for (long long pos = 0; pos < n; pos += RII_THREADS) {
+        s.tk.reserve(RII_THREADS);
+        u64 thr_key = s.tk.thr_key();
+        long long i = pos + threadIdx.x;
+        if (i < n) {
+            u64 key = src[i];
+            if (key != RII_KEY_MAX && key < thr_key) s.tk.push(key);
+        }
+    }
+    TopkOut o = out;
+    o.final = 1;
+    emit_topk(s.tk, o, b, 0, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4  coarse ranking + candidate plan.  src/rii.h:259-280: ADist to every coarse center, w = number of
+// lists to consider, partial_sort of the first w.  We rank by (coarse dist, list id).  grid (B).
+// The plan (prefix-sum form) turns the reference's sequential posting-list walk
+// (src/rii.h:286-322) into per-list take counts.
+// ---------------------------------------------------------------------------------------------------
+struct PlanArgs {
+    // inputs
+    const int *glob_len;   // (nlist) global (all-shard) list lengths       [no subset]
+    const int *pre_len;    // (nlist) sum of lengths on lower ranks, or null (single shard)
+    const int *loc_len;    // (nlist) local list lengths
+    const int *filt_cnt;   // (B, w_eff) filtered counts per ranked list, or null  [subset]
+    long long L;
+    int topk;
+    int w;                 // the reference's w (src/rii.h:267-277)
+    int w_eff;             // ranked lists available (== w, or nlist on the full re-run)
+    int nlist;
+    // outputs
+    int *ranked;           // (B, w_eff) list ids in rank order
+    int *cum;              // (B, w_eff) inclusive prefix of local take counts
+    int *take_last;        // (B) global take count from the last segment (subset truncation)
+    int *J;                // (B) number of segments
+    int *flags;            // (B) bit0: needs full ranking (walk beyond w), bit1: empty result
+};
+
+__device__ void make_plan(const PlanArgs &p, int b)
+{
+    // single thread; w is small (tens) on every BASELINE config
+    const int *ranked = p.ranked + (size_t)b * p.w_eff;
+    int *cum = p.cum + (size_t)b * p.w_eff;
+    long long P = 0;
+    int J = 0, flag = 0, local = 0;
+    bool done = false;
+    int take_last = 0;
+    for (int j = 0; j < p.w_eff; ++j) {
+        int no = ranked[j];
+        long long f = p.filt_cnt ? p.filt_cnt[(size_t)b * p.w_eff + j] : p.glob_len[no];
+        long long take = f;
+        if (P + f >= p.L) { take = p.L - P; done = true; }            // src/rii.h:302-304
+        P += take;
+        long long lt;
+        if (p.filt_cnt) lt = take;  // subset: counted in filtered ids (single shard)
+        else {
+            long long pre = p.pre_len ? p.pre_len[no] : 0;
+            lt = take - pre;
+            if (lt < 0) lt = 0;
+            if (lt > p.loc_len[no]) lt = p.loc_len[no];
+        }
+        local += (int)lt;
+        cum[j] = local;
+        take_last = (int)take;
+        J = j + 1;
+        if (done) break;
+        if (j == p.w - 1 && P >= p.topk) { done = true; break; }       // src/rii.h:309
+    }
+    if (!done) {
+        if (p.w_eff >= p.nlist) flag |= 2;   // src/rii.h:325: nothing (enough) found -> empty result
+        else flag |= 1;                      // walk continues beyond w: host re-runs with the full ranking
+    }
+    p.J[b] = J;
+    p.take_last[b] = take_last;
+    p.flags[b] = flag;
+}
+
+struct CoarseArgs {
+    const float *T;          // (B, M*Ks)
+    const uint8_t *centers;  // (nlist, M)
+    int M, Ks, nlist, cap;
+    int do_plan;
+    PlanArgs plan;
+};
+
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_coarse_rank(CoarseArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.plan.w_eff);
+    const int b = blockIdx.x;
+    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    s.tk.init();
+    for (int pos = 0; pos < a.nlist; pos += RII_THREADS) {
+        s.tk.reserve(RII_THREADS);
+        const uint32_t thr_hi = s.tk.thr_hi();
+        const u64 thr_key = s.tk.thr_key();
+        int no = pos + threadIdx.x;
+        if (no < a.nlist) {
+            float d = adc_row<M_T, false>(s.lut, a.Ks, a.M, a.centers + (size_t)no * a.M);
+            if (__float_as_uint(d) <= thr_hi) {
+                u64 key = pack_key(d, (uint32_t)no);
+                if (key < thr_key) s.tk.push(key);
+            }
+        }
+    }
+    s.tk.compact();
+    int *ranked = a.plan.ranked + (size_t)b * a.plan.w_eff;
+    for (int i = threadIdx.x; i < a.plan.w_eff; i += blockDim.x) ranked[i] = (int)key_id(s.tk.keys[i]);
+    __syncthreads();
+    if (a.do_plan && threadIdx.x == 0) make_plan(a.plan, b);
+}
+
+__global__ void k_plan(PlanArgs p, int B)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) make_plan(p, b);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5  posting-list scan.  src/rii.h:283-320: walk the ranked lists, ADist every visited id, top-k.
+// No subset: the candidate set is the concatenation of the first cum[j]-cum[j-1] ids of each planned
+// segment; grid (parts, B), each CTA takes a contiguous slice of the flattened candidate space.
+// ---------------------------------------------------------------------------------------------------
+struct IvfArgs {
+    const float *T;
+    const uint8_t *codes;
+    const long long *offsets;  // (nlist+1) CSR of local posting lists
+    const int *ids;            // local ids, ascending per list
+    const int *ranked;         // (B, w_eff)
+    const int *cum;            // (B, w_eff)
+    const int *J;              // (B)
+    const int *flags;          // (B)
+    const int *take_last;      // (B)
+    const uint32_t *bitmap;    // subset membership (bit per local id) or null
+    int w_eff;
+    int M, Ks, k, cap;
+    TopkOut out;
+};
+
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_scan_ivf(IvfArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.k);
+    const int b = blockIdx.y;
+    const int J = (a.flags[b] != 0) ? 0 : a.J[b];
+    int *s_cum = reinterpret_cast<int *>(s.tail);
+    int *s_list = s_cum + a.w_eff;
+    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
+        s_list[j] = a.ranked[(size_t)b * a.w_eff + j];
+    }
+    s.tk.init();
+    const int total = J ? s_cum[J - 1] : 0;
+    int chunk = (total + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + RII_THREADS - 1) / RII_THREADS * RII_THREADS;
+    int pos = blockIdx.x * chunk;
+    int end = pos + chunk < total ? pos + chunk : total;
+    bool first = true;
+    while (pos < end) {
+        const int R = first ? 1 : RII_ROWS_PER_THREAD;
+        first = false;
+        s.tk.reserve(R * RII_THREADS);
+        const uint32_t thr_hi = s.tk.thr_hi();
+        const u64 thr_key = s.tk.thr_key();
+        int row[RII_ROWS_PER_THREAD];
+#pragma unroll
+        for (int r = 0; r < RII_ROWS_PER_THREAD; ++r) {
+            row[r] = -1;
+            if (r >= R) continue;
+            int idx = pos + r * RII_THREADS + threadIdx.x;
+            if (idx < end) {
+                int lo = 0, hi = J - 1;  // first segment with cum > idx
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (s_cum[mid] > idx) hi = mid; else lo = mid + 1;
+                }
+                int p = idx - (lo ? s_cum[lo - 1] : 0);
+                row[r] = __ldg(a.ids + a.offsets[s_list[lo]] + p);
+            }
+        }
+        float d[RII_ROWS_PER_THREAD];
+        if constexpr (M_T > 0) {
+            uint32_t w[RII_ROWS_PER_THREAD][(M_T + 3) / 4];
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) load_row<M_T, false>(a.codes + (size_t)row[r] * M_T, w[r]);
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) d[r] = adc_regs<M_T>(s.lut, a.Ks, w[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RII_ROWS_PER_THREAD; ++r)
+                if (row[r] >= 0) d[r] = adc_bytes(s.lut, a.Ks, a.M, a.codes + (size_t)row[r] * a.M);
+        }
+#pragma unroll
+        for (int r = 0; r < RII_ROWS_PER_THREAD; ++r) {
+            if (row[r] >= 0 && __float_as_uint(d[r]) <= thr_hi) {
+                u64 key = pack_key(d[r], (uint32_t)row[r]);
+                if (key < thr_key) s.tk.push(key);
+            }
+        }
+        pos += R * RII_THREADS;
+    }
+    emit_topk(s.tk, a.out, b, blockIdx.x, gridDim.x);
+}
+
+// Subset variant (src/rii.h:294 binary_search filter): membership comes from a bitmap over local ids.
+// One CTA walks whole segments (segment j -> CTA j % parts) in stored order; the last segment is cut
+// after its first take_last[b] *member* ids, which needs the in-order rank of every member.
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_scan_ivf_subset(IvfArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.k);
+    const int b = blockIdx.y;
+    const int J = (a.flags[b] != 0) ? 0 : a.J[b];
+    int *s_warp = reinterpret_cast<int *>(s.tail);  // 8 warp counts + running base
+    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    s.tk.init();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j = blockIdx.x; j < J; j += gridDim.x) {
+        const int no = a.ranked[(size_t)b * a.w_eff + j];
+        const long long beg = a.offsets[no];
+        const int len = (int)(a.offsets[no + 1] - beg);
+        const int limit = (j == J - 1) ? a.take_last[b] : 0x7fffffff;
+        int base = 0;  // members seen so far in this list (uniform across the CTA)
+        for (int pos = 0; pos < len && base < limit; pos += RII_THREADS) {
+            s.tk.reserve(RII_THREADS);
+            const uint32_t thr_hi = s.tk.thr_hi();
+            const u64 thr_key = s.tk.thr_key();
+            int i = pos + threadIdx.x;
+            int id = -1;
+            bool member = false;
+            if (i < len) {
+                id = __ldg(a.ids + beg + i);
+                member = (__ldg(a.bitmap + (id >> 5)) >> (id & 31)) & 1u;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, member);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            __syncthreads();
+            int before = base + __popc(bal & ((1u << lane) - 1));
+            int tot = 0;
+            for (int w2 = 0; w2 < RII_THREADS / 32; ++w2) {
+                int c = s_warp[w2];
+                if (w2 < wid) before += c;
+                tot += c;
+            }
+            if (member && before < limit) {
+                float d = adc_row<M_T, false>(s.lut, a.Ks, a.M, a.codes + (size_t)id * a.M);
+                if (__float_as_uint(d) <= thr_hi) {
+                    u64 key = pack_key(d, (uint32_t)id);
+                    if (key < thr_key) s.tk.push(key);
+                }
+            }
+            base += tot;
+            __syncthreads();  // s_warp reused next iteration
+        }
+    }
+    emit_topk(s.tk, a.out, b, blockIdx.x, gridDim.x);
+}
+
+// membership bitmap over local ids from (sorted or unsorted) global target ids
+__global__ void k_bitmap_set(const long long *__restrict__ tids, long long S, long long id_base, long long N,
+                             uint32_t *bitmap)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    long long id = tids[i] - id_base;
+    if (id >= 0 && id < N) atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+}
+
+// filtered length of every ranked list.  grid (w_eff, B)
+__global__ void __launch_bounds__(RII_THREADS) k_count_members(const long long *__restrict__ offsets,
+                                                               const int *__restrict__ ids,
+                                                               const int *__restrict__ ranked, int w_eff,
+                                                               const uint32_t *__restrict__ bitmap, int *filt_cnt)
+{
+    const int b = blockIdx.y, j = blockIdx.x;
+    const int no = ranked[(size_t)b * w_eff + j];
+    const long long beg = offsets[no];
+    const int len = (int)(offsets[no + 1] - beg);
+    int c = 0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        int id = __ldg(ids + beg + i);
+        c += (__ldg(bitmap + (id >> 5)) >> (id & 31)) & 1u;
+    }
+    __shared__ int red[RII_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < RII_THREADS / 32; ++i) t += red[i];
+        filt_cnt[(size_t)b * w_eff + j] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6  symmetric-distance assignment.  src/pqkmeans.cpp:23-34,164-173 (codeword distance matrices),
+// :152-162 (SymmetricDistance), :193-218 (FindNearetCenterLinear, first minimum wins), called from
+// src/rii.h:350-354 and src/pqkmeans.cpp:88-94.
+// ---------------------------------------------------------------------------------------------------
+// Dm[m][k1][k2] = sum_i (c1[i]-c2[i])^2, scalar, sequential in i.  grid (ceil(Ks*Ks/256), M)
+__global__ void __launch_bounds__(RII_THREADS) k_symmat(const float *__restrict__ cw, float *__restrict__ Dm, int Ks,
+                                                        int Ds)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Ks * Ks) return;
+    int m = blockIdx.y, k1 = e / Ks, k2 = e % Ks;
+    const float *a = cw + ((size_t)m * Ks + k1) * Ds, *bb = cw + ((size_t)m * Ks + k2) * Ds;
+    float dist = 0.f;
+    for (int i = 0; i < Ds; ++i) dist = __fadd_rn(dist, sqdiff(a[i], bb[i]));
+    Dm[(size_t)m * Ks * Ks + e] = dist;
+}
+
+// Each CTA owns a tile of TILE codes (staged once in shared memory) and sweeps all K centers in groups
+// of G; the group's tables T_g[m][a] = Dm[m][center_g[m]][a] (Dm is bit-symmetric) are packed G-wide so
+// one LDS.(32*G) serves G centers.  Running (min dist, argmin) per code lives in registers; centers are
+// visited in ascending order with strict '<', i.e. the first minimum wins exactly as in the reference.
+template <int G, int CPT>
+__global__ void __launch_bounds__(RII_THREADS) k_assign(const float *__restrict__ Dm, const uint8_t *__restrict__ codes,
+                                                        long long N, const uint8_t *__restrict__ centers, int K, int M,
+                                                        int Ks, int *__restrict__ assign, float *__restrict__ best_dist)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lut = reinterpret_cast<float *>(smem_raw);                     // [M][Ks][G]
+    uint8_t *tile = smem_raw + (size_t)M * Ks * G * sizeof(float);        // [TILE][M]
+    const int TILE = RII_THREADS * CPT;
+    const long long row0 = (long long)blockIdx.x * TILE;
+    const long long rows = (N - row0) < TILE ? (N - row0) : TILE;
+    {   // stage the code tile (bytes are contiguous in global memory)
+        const uint8_t *src = codes + row0 * M;
+        const long long nbytes = rows * M;
+        for (long long i = threadIdx.x; i < nbytes; i += blockDim.x) tile[i] = __ldg(src + i);
+    }
+    float best[CPT];
+    int arg[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) { best[c] = 3.402823466e+38f; arg[c] = -1; }
+
+    for (int k0 = 0; k0 < K; k0 += G) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < M * Ks; e += blockDim.x) {
+            int m = e / Ks, a = e % Ks;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                int k = k0 + g < K ? k0 + g : K - 1;
+                lut[(size_t)e * G + g] = __ldg(Dm + ((size_t)m * Ks + centers[(size_t)k * M + m]) * Ks + a);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            int r = c * RII_THREADS + threadIdx.x;
+            if (r >= rows) continue;
+            const uint8_t *code = tile + (size_t)r * M;
+            float acc[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g] = 0.f;
+            for (int m = 0; m < M; ++m) {
+                const float *e = lut + ((size_t)m * Ks + code[m]) * G;
+                if constexpr (G == 4) {
+                    float4 v = *reinterpret_cast<const float4 *>(e);
+                    acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
+                    acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
+                } else if constexpr (G == 2) {
+                    float2 v = *reinterpret_cast<const float2 *>(e);
+                    acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
+                } else {
+                    acc[0] = __fadd_rn(acc[0], e[0]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (k0 + g < K && acc[g] < best[c]) { best[c] = acc[g]; arg[c] = k0 + g; }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        int r = c * RII_THREADS + threadIdx.x;
+        if (r < rows) {
+            assign[row0 + r] = arg[c];
+            if (best_dist) best_dist[row0 + r] = best[c];
+        }
+    }
+}
+
+// gather rows by id (sampling for PQk-means, src/rii.h:126-132)
+__global__ void k_gather_rows(const uint8_t *__restrict__ codes, const long long *__restrict__ pick, long long n, int M,
+                              uint8_t *__restrict__ out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * M) return;
+    long long r = i / M;
+    int m = (int)(i % M);
+    out[i] = codes[pick[r] * M + m];
+}
+
+// histogram of code bytes per (cluster, subspace): hist[k][m][ks].  src/pqkmeans.cpp:229-233
+__global__ void k_vote_hist(const uint8_t *__restrict__ codes, const int *__restrict__ assign, long long n, int M,
+                            int Ks, int *hist)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * M) return;
+    long long r = i / M;
+    int m = (int)(i % M);
+    atomicAdd(hist + ((size_t)assign[r] * M + m) * Ks + codes[i], 1);
+}
+
+// sparse voting, src/pqkmeans.cpp:235-258: vote[k2] = sum over k1 (ascending, freq != 0) of
+// (float)freq * Dm[m][k1][k2] (mul then add), argmin with strict '<' from FLT_MAX.
+// grid (M, K), Ks <= 256 threads.  Empty clusters keep their center (src/pqkmeans.cpp:115-120).
+__global__ void __launch_bounds__(256) k_vote_centers(const float *__restrict__ Dm, const int *__restrict__ hist,
+                                                      int M, int Ks, uint8_t *centers)
+{
+    const int m = blockIdx.x, k = blockIdx.y, k2 = threadIdx.x;
+    __shared__ int s_hist[256];
+    __shared__ float s_vote[256];
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    int h = 0;
+    if (k2 < Ks) h = hist[((size_t)k * M + m) * Ks + k2];
+    s_hist[k2] = h;
+    if (h) atomicAdd(&s_total, h);
+    __syncthreads();
+    if (s_total == 0) return;
+    float vote = 0.f;
+    if (k2 < Ks) {
+        for (int k1 = 0; k1 < Ks; ++k1) {
+            int freq = s_hist[k1];
+            if (freq == 0) continue;
+            vote = __fadd_rn(vote, __fmul_rn((float)freq, __ldg(Dm + ((size_t)m * Ks + k1) * Ks + k2)));
+        }
+    }
+    s_vote[k2] = vote;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float min_dist = 3.402823466e+38f;
+        int min_ks = -1;
+        for (int ks = 0; ks < Ks; ++ks)
+            if (s_vote[ks] < min_dist) { min_ks = ks; min_dist = s_vote[ks]; }
+        centers[(size_t)k * M + m] = (uint8_t)min_ks;
+    }
+}
+
+// all ADC distances of a row range (diagnostics / K-parity tests): out[b][n]
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict__ T, const uint8_t *__restrict__ codes,
+                                                         long long N, int M, int Ks, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    const int b = blockIdx.y;
+    load_lut(lut, T + (size_t)b * M * Ks, M * Ks);
+    __syncthreads();
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x)
+        out[(size_t)b * N + n] = adc_row<M_T, true>(lut, Ks, M, codes + n * M);
+}

@@ -1,0 +1,915 @@
+// librii_b200.so -- host side of the B200 ADC path + the C ABI declared in include/rii_b200.h.
+//
+// Mirrors the state and the entry points of the reference's `RiiCpp` (src/rii.h:39-83, src/main.cpp:12-54)
+// with the data resident in HBM:
+//   codes      (N, M)  uint8, row-major, rows M bytes apart (32-byte rows for M=32 -> one LDG.256 / sector)
+//   codewords  (M, Ks, Ds) float32             coarse centers (nlist, M) uint8
+//   posting lists as CSR: offsets int64 (nlist+1), ids int32 (N)   (the reference stores ids only, too)
+//   Dm         (M, Ks, Ks) float32 codeword distance matrices (built on first use)
+// The host keeps only what the reference's host glue needs (posting lists / centers mirrors and the two
+// libstdc++ shuffles that define the reconfigure sampling, src/rii.h:120-124, src/pqkmeans.cpp:177-191).
+#include "../../include/rii_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(RII_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ +  \
+                                          ":" + std::to_string(__LINE__) + ")");                             \
+    } while (0)
+#define CKR(call)                     \
+    do {                              \
+        int r_ = (call);              \
+        if (r_ < 0) return r_;        \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+const size_t SMEM_MAX = 227 * 1024;  // opt-in shared memory per CTA on sm_100
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(RII_ERR_CUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+int host_l2_variant()
+{
+    FILE *f = fopen("/proc/cpuinfo", "r");
+    if (!f) return 16;
+    std::string s;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0 && s.size() < (1u << 20)) s.append(buf, n);
+    fclose(f);
+    if (s.find(" avx512f") != std::string::npos) return 16;
+    if (s.find(" avx ") != std::string::npos || s.find(" avx2") != std::string::npos) return 8;
+    return 4;
+}
+
+}  // namespace
+
+struct rii_index {
+    int M = 0, Ks = 0, Ds = 0, variant = 16, verbose = 0, device = 0;
+    long long N = 0, cap_rows = 0;      // local rows
+    long long id_base = 0, N_total = -1;  // sharding (N_total < 0: single shard, N_total = N)
+    int nlist = 0;
+    cudaStream_t stream = nullptr;
+
+    float *d_cw = nullptr;
+    float *d_Dm = nullptr;
+    uint8_t *d_codes = nullptr;
+    DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
+    bool has_global = false;
+
+    std::vector<uint8_t> h_centers;      // (nlist, M)
+    std::vector<long long> h_offsets;    // (nlist+1)
+    std::vector<int> h_ids;              // (N) local ids grouped by list
+    std::vector<long long> len_sorted_prefix;  // prefix sums of ascending *global* list lengths
+
+    // scratch (grow only)
+    DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
+        tmp2, tmp3;
+
+    long long n_total() const { return N_total >= 0 ? N_total : N; }
+};
+
+namespace {
+
+template <class F> int set_smem(F *kernel, size_t bytes)
+{
+    if (bytes > SMEM_MAX) return fail(RII_ERR_LIMIT, "shape needs " + std::to_string(bytes) + " B of shared memory per CTA (> 227 KB)");
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// ---- per-M dispatch (register-resident rows for the common sizes, byte loads otherwise) -------------
+#define DISPATCH_M(M, ...)                                  \
+    switch (M) {                                            \
+    case 4: { constexpr int MT = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int MT = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int MT = 16; __VA_ARGS__; } break; \
+    case 32: { constexpr int MT = 32; __VA_ARGS__; } break; \
+    case 64: { constexpr int MT = 64; __VA_ARGS__; } break; \
+    default: { constexpr int MT = 0; __VA_ARGS__; } break;  \
+    }
+
+int ensure_Dm(rii_index *h)
+{
+    if (h->d_Dm) return 0;
+    CK(cudaMalloc(&h->d_Dm, (size_t)h->M * h->Ks * h->Ks * sizeof(float)));
+    dim3 grid((h->Ks * h->Ks + RII_THREADS - 1) / RII_THREADS, h->M);
+    k_symmat<<<grid, RII_THREADS, 0, h->stream>>>(h->d_cw, h->d_Dm, h->Ks, h->Ds);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// K6 launcher: d_codes (n, M) device, d_centers (K, M) device -> d_assign (n) [, d_dist (n)]
+int launch_assign(rii_index *h, const uint8_t *d_codes, long long n, const uint8_t *d_centers, int K, int *d_assign,
+                  float *d_dist)
+{
+    if (n == 0) return 0;
+    CKR(ensure_Dm(h));
+    const size_t lut1 = (size_t)h->M * h->Ks * sizeof(float);
+    int G = 0, CPT = 4;
+    for (int g : {4, 2, 1}) {
+        if (lut1 * g + (size_t)RII_THREADS * 4 * h->M <= 200 * 1024) { G = g; CPT = 4; break; }
+    }
+    if (!G) {
+        if (lut1 + (size_t)RII_THREADS * h->M <= 220 * 1024) { G = 1; CPT = 1; }
+        else return fail(RII_ERR_LIMIT, "assignment kernel: M*Ks too large for shared memory");
+    }
+    const int tile = RII_THREADS * CPT;
+    const size_t smem = lut1 * G + (size_t)tile * h->M;
+    const unsigned grid = (unsigned)((n + tile - 1) / tile);
+#define LAUNCH_ASSIGN(GG, CC)                                                                                        \
+    do {                                                                                                             \
+        CKR(set_smem(k_assign<GG, CC>, smem));                                                                       \
+        k_assign<GG, CC><<<grid, RII_THREADS, smem, h->stream>>>(h->d_Dm, d_codes, n, d_centers, K, h->M, h->Ks,    \
+                                                                  d_assign, d_dist);                                 \
+    } while (0)
+    if (G == 4) LAUNCH_ASSIGN(4, 4);
+    else if (G == 2) LAUNCH_ASSIGN(2, 4);
+    else if (CPT == 4) LAUNCH_ASSIGN(1, 4);
+    else LAUNCH_ASSIGN(1, 1);
+#undef LAUNCH_ASSIGN
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int upload_lists(rii_index *h)
+{
+    const int nlist = h->nlist;
+    CKR(h->offsets.ensure((size_t)(nlist + 1) * 8));
+    CKR(h->ids.ensure(std::max<size_t>(4, h->h_ids.size() * 4)));
+    CKR(h->loc_len.ensure((size_t)std::max(1, nlist) * 4));
+    CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (!h->h_ids.empty())
+        CK(cudaMemcpyAsync(h->ids.p, h->h_ids.data(), h->h_ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    std::vector<int> len(nlist);
+    for (int i = 0; i < nlist; ++i) len[i] = (int)(h->h_offsets[i + 1] - h->h_offsets[i]);
+    if (nlist) CK(cudaMemcpyAsync(h->loc_len.p, len.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!h->has_global) {
+        std::sort(len.begin(), len.end());
+        h->len_sorted_prefix.assign(nlist + 1, 0);
+        for (int i = 0; i < nlist; ++i) h->len_sorted_prefix[i + 1] = h->len_sorted_prefix[i] + len[i];
+    }
+    return 0;
+}
+
+// src/rii.h:335-359 UpdatePostingLists(start, num): assign on the GPU, append ids in ascending order.
+int update_posting_lists(rii_index *h, long long start, long long num)
+{
+    if (num <= 0) return upload_lists(h);
+    CKR(h->tmp0.ensure((size_t)num * 4));
+    CKR(launch_assign(h, h->d_codes + start * h->M, num, h->centers.as<uint8_t>(), h->nlist, h->tmp0.as<int>(), nullptr));
+    std::vector<int> assign(num);
+    CK(cudaMemcpyAsync(assign.data(), h->tmp0.p, (size_t)num * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int nlist = h->nlist;
+    std::vector<long long> add(nlist, 0);
+    for (long long n = 0; n < num; ++n) {
+        if (assign[n] < 0 || assign[n] >= nlist) return fail(RII_ERR_CUDA, "assignment kernel produced an invalid list id");
+        add[assign[n]]++;
+    }
+    std::vector<long long> noff(nlist + 1, 0);
+    for (int i = 0; i < nlist; ++i) noff[i + 1] = noff[i] + (h->h_offsets[i + 1] - h->h_offsets[i]) + add[i];
+    std::vector<int> nids((size_t)noff[nlist]);
+    std::vector<long long> cur(nlist);
+    for (int i = 0; i < nlist; ++i) {
+        long long len = h->h_offsets[i + 1] - h->h_offsets[i];
+        if (len) std::memcpy(&nids[noff[i]], &h->h_ids[h->h_offsets[i]], (size_t)len * 4);
+        cur[i] = noff[i] + len;
+    }
+    for (long long n = 0; n < num; ++n) nids[cur[assign[n]]++] = (int)(start + n);
+    h->h_offsets.swap(noff);
+    h->h_ids.swap(nids);
+    return upload_lists(h);
+}
+
+int set_centers(rii_index *h, const uint8_t *centers_host, int nlist)
+{
+    h->nlist = nlist;
+    h->h_centers.assign(centers_host, centers_host + (size_t)nlist * h->M);
+    CKR(h->centers.ensure((size_t)nlist * h->M));
+    CK(cudaMemcpyAsync(h->centers.p, h->h_centers.data(), (size_t)nlist * h->M, cudaMemcpyHostToDevice, h->stream));
+    h->h_offsets.assign(nlist + 1, 0);
+    h->h_ids.clear();
+    h->has_global = false;
+    return 0;
+}
+
+// src/pqkmeans.cpp:46-133 on a device-resident sample (already in the reference's shuffled order).
+// Leaves the final centers in tmp2 (device) and copies them to centers_out (host).
+int fit_coarse(rii_index *h, const uint8_t *d_sample, long long ns, int nlist, int iter, uint8_t *centers_out)
+{
+    const int M = h->M, Ks = h->Ks;
+    if (nlist <= 0 || (long long)nlist > ns) return fail(RII_ERR_ARG, "fit_coarse: need 0 < nlist <= number of sample codes");
+    CKR(ensure_Dm(h));
+    // InitializeCentersByRandomPicking, src/pqkmeans.cpp:177-191
+    std::vector<int> ids((size_t)ns);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::mt19937 random_engine(0);
+    std::shuffle(ids.begin(), ids.end(), random_engine);
+    std::vector<long long> pick(nlist);
+    for (int k = 0; k < nlist; ++k) pick[k] = ids[k];
+    CKR(h->tmp1.ensure((size_t)nlist * 8));
+    CKR(h->tmp2.ensure((size_t)nlist * M));       // centers_new
+    CKR(h->tmp3.ensure((size_t)nlist * M));       // centers_old
+    CK(cudaMemcpyAsync(h->tmp1.p, pick.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice, h->stream));
+    {
+        long long tot = (long long)nlist * M;
+        k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(d_sample, h->tmp1.as<long long>(), nlist, M,
+                                                                          h->tmp2.as<uint8_t>());
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    DevBuf assign, hist;
+    int rc = 0;
+    do {
+        if ((rc = assign.ensure((size_t)ns * 4)) < 0) break;
+        if (iter > 1 && (rc = hist.ensure((size_t)nlist * M * Ks * 4)) < 0) break;
+        for (int itr = 0; itr < iter; ++itr) {
+            if (h->verbose) printf("Iteration start: %d / %d\n", itr, iter);
+            cudaMemcpyAsync(h->tmp3.p, h->tmp2.p, (size_t)nlist * M, cudaMemcpyDeviceToDevice, h->stream);
+            if ((rc = launch_assign(h, d_sample, ns, h->tmp3.as<uint8_t>(), nlist, assign.as<int>(), nullptr)) < 0) break;
+            if (itr != iter - 1) {  // src/pqkmeans.cpp:110
+                cudaMemsetAsync(hist.p, 0, (size_t)nlist * M * Ks * 4, h->stream);
+                long long tot = ns * M;
+                k_vote_hist<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(d_sample, assign.as<int>(), ns, M, Ks,
+                                                                                hist.as<int>());
+                LAUNCHED();
+                k_vote_centers<<<dim3(M, nlist), 256, 0, h->stream>>>(h->d_Dm, hist.as<int>(), M, Ks, h->tmp2.as<uint8_t>());
+                LAUNCHED();
+            }
+        }
+        if (rc < 0) break;
+        cudaError_t e = cudaMemcpyAsync(centers_out, h->tmp2.p, (size_t)nlist * M, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(RII_ERR_CUDA, std::string("fit_coarse: ") + cudaGetErrorString(e));
+    } while (0);
+    assign.release();
+    hist.release();
+    return rc;
+}
+
+int grow_codes(rii_index *h, long long rows)
+{
+    if (rows <= h->cap_rows) return 0;
+    long long ncap = std::max(rows, h->cap_rows + h->cap_rows / 2);
+    uint8_t *nb = nullptr;
+    CK(cudaMalloc(&nb, (size_t)ncap * h->M + 64));
+    if (h->N) CK(cudaMemcpyAsync(nb, h->d_codes, (size_t)h->N * h->M, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_codes) cudaFree(h->d_codes);
+    h->d_codes = nb;
+    h->cap_rows = ncap;
+    return 0;
+}
+
+// ---- the query pipeline on device buffers -----------------------------------------------------------
+struct QueryCfg {
+    int topk;
+    long long S, L;
+    int method;
+};
+
+int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const long long *d_tids, long long *d_out_ids,
+              float *d_out_dists, int *d_out_counts, cudaStream_t st, int w, int w_eff, bool *checked_flags)
+{
+    const int M = h->M, Ks = h->Ks, lutf = M * Ks;
+    // K1
+    CKR(h->T.ensure((size_t)B * lutf * 4));
+    {
+        dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
+        k_dtable<<<grid, RII_THREADS, 0, st>>>(d_Q, h->d_cw, h->T.as<float>(), M, Ks, h->Ds, h->variant);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    const int round = RII_THREADS * RII_ROWS_PER_THREAD;
+    const int cap = next_pow2(c.topk + round);
+    TopkOut out{};
+    out.out_ids = d_out_ids;
+    out.out_dists = d_out_dists;
+    out.out_counts = d_out_counts;
+    out.id_base = h->id_base;
+    const int max_parts = std::max(1, 592 / B);
+    const long long per_cta = B >= 148 ? 8192 : 1024;
+
+    if (c.method == RII_METHOD_LINEAR) {
+        const long long ncand = c.S ? c.S : h->N;
+        int parts = (int)std::min<long long>(max_parts, std::max<long long>(1, (ncand + per_cta - 1) / per_cta));
+        out.final = parts == 1;
+        if (!out.final) {
+            CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
+            out.partial = h->partial.as<u64>();
+        }
+        LinearArgs a{};
+        a.T = h->T.as<float>();
+        a.codes = h->d_codes;
+        a.tids = c.S ? d_tids : nullptr;
+        a.S = c.S;
+        a.N = h->N;
+        a.id_base = h->id_base;
+        a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
+        a.out = out;
+        const size_t smem = scan_smem_bytes(lutf, cap, 0);
+        DISPATCH_M(M, {
+            CKR(set_smem(k_scan_linear<MT>, smem));
+            k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+        });
+        LAUNCHED();
+        CK(cudaGetLastError());
+        if (!out.final) {
+            const int mcap = next_pow2(c.topk + RII_THREADS);
+            const size_t msmem = scan_smem_bytes(0, mcap, 0);
+            CKR(set_smem(k_merge, msmem));
+            k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
+            LAUNCHED();
+            CK(cudaGetLastError());
+        }
+        return 0;
+    }
+
+    // ---- IVF ----
+    const bool subset = c.S != 0;
+    CKR(h->ranked.ensure((size_t)B * w_eff * 4));
+    CKR(h->cum.ensure((size_t)B * w_eff * 4));
+    CKR(h->take_last.ensure((size_t)B * 4));
+    CKR(h->J.ensure((size_t)B * 4));
+    CKR(h->flags.ensure((size_t)B * 4));
+    PlanArgs p{};
+    p.glob_len = h->has_global ? h->glob_len.as<int>() : h->loc_len.as<int>();
+    p.pre_len = h->has_global ? h->pre_len.as<int>() : nullptr;
+    p.loc_len = h->loc_len.as<int>();
+    p.filt_cnt = nullptr;
+    p.L = c.L;
+    p.topk = c.topk;
+    p.w = w;
+    p.w_eff = w_eff;
+    p.nlist = h->nlist;
+    p.ranked = h->ranked.as<int>();
+    p.cum = h->cum.as<int>();
+    p.take_last = h->take_last.as<int>();
+    p.J = h->J.as<int>();
+    p.flags = h->flags.as<int>();
+    if (subset) {
+        const size_t words = (size_t)(h->N + 31) / 32 + 1;
+        CKR(h->bitmap.ensure(words * 4));
+        CK(cudaMemsetAsync(h->bitmap.p, 0, words * 4, st));
+        k_bitmap_set<<<(unsigned)((c.S + 255) / 256), 256, 0, st>>>(d_tids, c.S, h->id_base, h->N, h->bitmap.as<uint32_t>());
+        LAUNCHED();
+        CKR(h->filt.ensure((size_t)B * w_eff * 4));
+    }
+    {
+        CoarseArgs a{};
+        a.T = h->T.as<float>();
+        a.centers = h->centers.as<uint8_t>();
+        a.M = M; a.Ks = Ks; a.nlist = h->nlist;
+        a.cap = next_pow2(w_eff + RII_THREADS);
+        a.do_plan = subset ? 0 : 1;
+        a.plan = p;
+        const size_t smem = scan_smem_bytes(lutf, a.cap, 0);
+        DISPATCH_M(M, {
+            CKR(set_smem(k_coarse_rank<MT>, smem));
+            k_coarse_rank<MT><<<B, RII_THREADS, smem, st>>>(a);
+        });
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    if (subset) {
+        k_count_members<<<dim3(w_eff, B), RII_THREADS, 0, st>>>(h->offsets.as<long long>(), h->ids.as<int>(), p.ranked, w_eff,
+                                                                  h->bitmap.as<uint32_t>(), h->filt.as<int>());
+        LAUNCHED();
+        p.filt_cnt = h->filt.as<int>();
+        k_plan<<<(B + 127) / 128, 128, 0, st>>>(p, B);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    {
+        int parts = subset ? std::min(max_parts, std::max(1, w_eff))
+                           : (int)std::min<long long>(max_parts, std::max<long long>(1, (c.L + per_cta - 1) / per_cta));
+        out.final = parts == 1;
+        if (!out.final) {
+            CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
+            out.partial = h->partial.as<u64>();
+        }
+        IvfArgs a{};
+        a.T = h->T.as<float>();
+        a.codes = h->d_codes;
+        a.offsets = h->offsets.as<long long>();
+        a.ids = h->ids.as<int>();
+        a.ranked = p.ranked; a.cum = p.cum; a.J = p.J; a.flags = p.flags; a.take_last = p.take_last;
+        a.bitmap = subset ? h->bitmap.as<uint32_t>() : nullptr;
+        a.w_eff = w_eff;
+        a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
+        a.out = out;
+        if (subset) {
+            const size_t smem = scan_smem_bytes(lutf, cap, 64);
+            DISPATCH_M(M, {
+                CKR(set_smem(k_scan_ivf_subset<MT>, smem));
+                k_scan_ivf_subset<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+            });
+        } else {
+            const size_t smem = scan_smem_bytes(lutf, cap, (size_t)w_eff * 8);
+            DISPATCH_M(M, {
+                CKR(set_smem(k_scan_ivf<MT>, smem));
+                k_scan_ivf<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+            });
+        }
+        LAUNCHED();
+        CK(cudaGetLastError());
+        if (!out.final) {
+            const int mcap = next_pow2(c.topk + RII_THREADS);
+            const size_t msmem = scan_smem_bytes(0, mcap, 0);
+            CKR(set_smem(k_merge, msmem));
+            k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
+            LAUNCHED();
+            CK(cudaGetLastError());
+        }
+    }
+    if (checked_flags) *checked_flags = true;
+    return 0;
+}
+
+int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *d_tids, long long S, long long L,
+              int method, long long *d_out_ids, float *d_out_dists, int *d_out_counts, cudaStream_t st)
+{
+    if (B <= 0) return 0;
+    if (h->N <= 0 && h->n_total() <= 0) return fail(RII_ERR_STATE, "query on an empty index");
+    if (topk < 1) return fail(RII_ERR_ARG, "topk must be >= 1");
+    const long long Ntot = h->n_total();
+    if (S < 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 <= len(target_ids) <= N");            // src/rii.h:220
+    if ((long long)topk > (S ? S : Ntot)) return fail(RII_ERR_ARG, "need topk <= N (and topk <= len(target_ids))");  // :200,:219
+    QueryCfg c{topk, S, L, method};
+    int w = 0, w_eff = 0;
+    bool may_flag = false;
+    if (method == RII_METHOD_IVF) {
+        if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
+        if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");           // src/rii.h:251
+        // src/rii.h:267-277
+        size_t ww = (size_t)std::round((double)L * h->nlist / (double)(S == 0 ? Ntot : S));
+        ww += 3;
+        if ((size_t)h->nlist < ww) ww = h->nlist;
+        w = w_eff = (int)ww;
+        // can sum of the first w ranked lists fall short of topk?  (only then the walk continues beyond w)
+        may_flag = S != 0 || (w < h->nlist && h->len_sorted_prefix.size() > (size_t)w && h->len_sorted_prefix[w] < topk &&
+                              h->len_sorted_prefix[w] < L);
+        if (S != 0 && h->has_global) return fail(RII_ERR_LIMIT, "IVF + target_ids on a sharded index is not implemented yet");
+    } else if (method != RII_METHOD_LINEAR) {
+        return fail(RII_ERR_ARG, "unknown method");
+    }
+    const int D = h->M * h->Ds;
+    const int CH = 2048;
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int bc = std::min(CH, B - b0);
+        bool ran_ivf = false;
+        CKR(run_chunk(h, d_Q + (size_t)b0 * D, bc, c, d_tids, d_out_ids + (size_t)b0 * topk, d_out_dists + (size_t)b0 * topk,
+                      d_out_counts + b0, st, w, w_eff, &ran_ivf));
+        if (method == RII_METHOD_IVF && may_flag && w < h->nlist) {
+            // SURVEY A.3, 3rd bullet: fewer than topk candidates in the first w lists -> the reference walks on
+            // through the remaining lists.  Re-run exactly those queries with the full (dist, id) ranking.
+            std::vector<int> flags(bc);
+            CK(cudaMemcpyAsync(flags.data(), h->flags.p, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int i = 0; i < bc; ++i) {
+                if (!(flags[i] & 1)) continue;
+                bool dummy;
+                CKR(run_chunk(h, d_Q + (size_t)(b0 + i) * D, 1, c, d_tids, d_out_ids + (size_t)(b0 + i) * topk,
+                              d_out_dists + (size_t)(b0 + i) * topk, d_out_counts + b0 + i, st, w, h->nlist, &dummy));
+            }
+        }
+    }
+    return 0;
+}
+
+int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tids, int64_t S, int64_t L, int method,
+               int64_t *out_ids, float *out_dists, int32_t *out_counts)
+{
+    if (B <= 0) return 0;
+    if (!Q || !out_ids || !out_dists || !out_counts) return fail(RII_ERR_ARG, "null buffer");
+    if (S > 0 && !tids) return fail(RII_ERR_ARG, "target_ids is null but S > 0");
+    CK(cudaSetDevice(h->device));
+    const int D = h->M * h->Ds;
+    cudaStream_t st = h->stream;
+    CKR(h->q.ensure((size_t)B * D * 4));
+    CKR(h->o_ids.ensure((size_t)B * topk * 8));
+    CKR(h->o_dists.ensure((size_t)B * topk * 4));
+    CKR(h->o_counts.ensure((size_t)B * 4));
+    CK(cudaMemcpyAsync(h->q.p, Q, (size_t)B * D * 4, cudaMemcpyHostToDevice, st));
+    if (S > 0) {
+        if (h->N_total < 0) {  // single shard: the reference indexes codes[tid] unchecked (src/rii.h:225); we refuse
+            for (int64_t i = 0; i < S; ++i)
+                if (tids[i] < 0 || tids[i] >= h->N) return fail(RII_ERR_ARG, "target_ids contains an id outside [0, N)");
+        }
+        CKR(h->tids.ensure((size_t)S * 8));
+        CK(cudaMemcpyAsync(h->tids.p, tids, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    }
+    CKR(query_dev(h, h->q.as<float>(), B, topk, h->tids.as<long long>(), S, L, method, h->o_ids.as<long long>(),
+                  h->o_dists.as<float>(), h->o_counts.as<int>(), st));
+    CK(cudaMemcpyAsync(out_ids, h->o_ids.p, (size_t)B * topk * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_dists, h->o_dists.p, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_counts, h->o_counts.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *rii_last_error(void) { return g_err.c_str(); }
+const char *rii_version(void) { return "0.2.12+b200.1"; }
+int64_t rii_launch_count(void) { return g_launches.load(); }
+
+int rii_create(const float *codewords, int M, int Ks, int Ds, int verbose, int device, int l2_variant, rii_index_t **out)
+{
+    if (!codewords || !out) return fail(RII_ERR_ARG, "null argument");
+    if (M <= 0 || Ks <= 0 || Ds <= 0) return fail(RII_ERR_ARG, "codewords must have shape (M, Ks, Ds) with positive sizes");
+    if (Ks > 256) return fail(RII_ERR_ARG, "Ks must be <= 256 so that each code is one uint8 (rii/rii.py:35)");
+    if (l2_variant == 0) l2_variant = host_l2_variant();
+    if (l2_variant != 16 && l2_variant != 8 && l2_variant != 4) return fail(RII_ERR_ARG, "l2_variant must be 0, 4, 8 or 16");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RII_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    rii_index *h = new rii_index();
+    h->M = M; h->Ks = Ks; h->Ds = Ds; h->verbose = verbose; h->device = device; h->variant = l2_variant;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cw, (size_t)M * Ks * Ds * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cw, codewords, (size_t)M * Ks * Ds * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(RII_ERR_CUDA, std::string("rii_create: ") + cudaGetErrorString(e));
+    }
+    h->h_offsets.assign(1, 0);
+    if (verbose) printf("rii_b200: sm_100a ADC path on device %d (fvec_L2sqr lane width %d)\n", device, l2_variant);
+    *out = h;
+    return 0;
+}
+
+int rii_destroy(rii_index_t *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
+                      &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
+                      &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
+        b->release();
+    if (h->d_cw) cudaFree(h->d_cw);
+    if (h->d_Dm) cudaFree(h->d_Dm);
+    if (h->d_codes) cudaFree(h->d_codes);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag)
+{
+    if (!h || n < 0 || (n > 0 && !codes)) return fail(RII_ERR_ARG, "bad arguments");
+    if (update_flag && h->nlist == 0)  // src/rii.h:166-170
+        return fail(RII_ERR_STATE, "reconfigure() must be called before running add(vecs=X, update_posting_lists=True). "
+                                   "If this is the first addition, please call add_configure(vecs=X)");
+    if (h->N + n >= (1ll << 31)) return fail(RII_ERR_LIMIT, "a shard holds at most 2^31-1 codes (posting lists store int32 ids, src/rii.h:82)");
+    CK(cudaSetDevice(h->device));
+    const long long N0 = h->N;
+    CKR(grow_codes(h, N0 + n));
+    if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->N = N0 + n;
+    if (h->verbose) printf("%lld new vectors are added.\nTotal number of codes is %lld\n", (long long)n, h->N);
+    if (update_flag) {
+        if (h->verbose) printf("Start to update posting lists\n");
+        CKR(update_posting_lists(h, N0, n));
+    }
+    return 0;
+}
+
+int rii_reconfigure(rii_index_t *h, int nlist, int iter)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    if (!(0 < nlist)) return fail(RII_ERR_ARG, "need 0 < nlist");                  // src/rii.h:110
+    if ((long long)nlist > h->N) return fail(RII_ERR_ARG, "need nlist <= N");     // src/rii.h:111
+    if (iter < 0) return fail(RII_ERR_ARG, "iter must be >= 0");
+    if (h->N_total >= 0 && h->N_total != h->N) return fail(RII_ERR_STATE, "rii_reconfigure on a shard: use rii_fit_coarse + rii_set_coarse_centers");
+    CK(cudaSetDevice(h->device));
+    // (1) sampling, src/rii.h:115-124 (libstdc++ shuffle defines which codes are sampled)
+    const long long N = h->N;
+    const long long ns = std::min<long long>(N, (long long)nlist * 100);
+    if (h->verbose) printf("The number of vectors used for training of coarse centers: %lld\n", ns);
+    std::vector<size_t> pick((size_t)N);
+    std::iota(pick.begin(), pick.end(), 0);
+    std::shuffle(pick.begin(), pick.end(), std::default_random_engine(123));
+    pick.resize((size_t)ns);
+    DevBuf d_pick, d_sample;
+    int rc = 0;
+    std::vector<uint8_t> centers((size_t)nlist * h->M);
+    do {
+        if ((rc = d_pick.ensure((size_t)ns * 8)) < 0) break;
+        if ((rc = d_sample.ensure((size_t)ns * h->M)) < 0) break;
+        cudaMemcpyAsync(d_pick.p, pick.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, h->stream);
+        long long tot = ns * h->M;
+        k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_codes, d_pick.as<long long>(), ns, h->M,
+                                                                          d_sample.as<uint8_t>());
+        LAUNCHED();
+        // (2)+(3) PQk-means, src/rii.h:136-146
+        if (h->verbose) printf("Start to run PQk-means\n");
+        rc = fit_coarse(h, d_sample.as<uint8_t>(), ns, nlist, iter, centers.data());
+    } while (0);
+    d_pick.release();
+    d_sample.release();
+    if (rc < 0) return rc;
+    // (4) posting lists, src/rii.h:148-155
+    if (h->verbose) printf("Start to update posting lists\n");
+    CKR(set_centers(h, centers.data(), nlist));
+    return update_posting_lists(h, 0, N);
+}
+
+int rii_clear(rii_index_t *h)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    h->N = 0;
+    h->nlist = 0;
+    h->h_centers.clear();
+    h->h_offsets.assign(1, 0);
+    h->h_ids.clear();
+    h->has_global = false;
+    h->len_sorted_prefix.clear();
+    return 0;
+}
+
+int64_t rii_query_linear(rii_index_t *h, const float *query, int topk, const int64_t *target_ids, int64_t S, int64_t *out_ids,
+                         float *out_dists)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    int32_t cnt = 0;
+    int rc = query_host(h, query, 1, topk, target_ids, S, 0, RII_METHOD_LINEAR, out_ids, out_dists, &cnt);
+    return rc < 0 ? rc : cnt;
+}
+
+int64_t rii_query_ivf(rii_index_t *h, const float *query, int topk, const int64_t *target_ids, int64_t S, int64_t L,
+                      int64_t *out_ids, float *out_dists)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    int32_t cnt = 0;
+    int rc = query_host(h, query, 1, topk, target_ids, S, L, RII_METHOD_IVF, out_ids, out_dists, &cnt);
+    return rc < 0 ? rc : cnt;
+}
+
+int rii_query_batch(rii_index_t *h, const float *queries, int B, int topk, const int64_t *target_ids, int64_t S, int64_t L,
+                    int method, int64_t *out_ids, float *out_dists, int32_t *out_counts)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    return query_host(h, queries, B, topk, target_ids, S, L, method, out_ids, out_dists, out_counts);
+}
+
+int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids, int64_t S,
+                        int64_t L, int method, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return query_dev(h, d_queries, B, topk, (const long long *)d_target_ids, S, L, method, (long long *)d_out_ids, d_out_dists,
+                     d_out_counts, st);
+}
+
+int64_t rii_get_N(const rii_index_t *h) { return h ? h->N : 0; }
+int rii_get_nlist(const rii_index_t *h) { return h ? h->nlist : 0; }
+int rii_get_verbose(const rii_index_t *h) { return h ? h->verbose : 0; }
+int rii_set_verbose(rii_index_t *h, int verbose)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    h->verbose = verbose;
+    return 0;
+}
+int rii_get_dims(const rii_index_t *h, int *M, int *Ks, int *Ds)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    if (M) *M = h->M;
+    if (Ks) *Ks = h->Ks;
+    if (Ds) *Ds = h->Ds;
+    return 0;
+}
+
+int rii_copy_codes(const rii_index_t *h, uint8_t *out)
+{
+    if (!h || !out) return fail(RII_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    if (h->N) CK(cudaMemcpy(out, h->d_codes, (size_t)h->N * h->M, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int rii_copy_coarse_centers(const rii_index_t *h, uint8_t *out)
+{
+    if (!h || !out) return fail(RII_ERR_ARG, "null argument");
+    if (!h->h_centers.empty()) std::memcpy(out, h->h_centers.data(), h->h_centers.size());
+    return 0;
+}
+int rii_copy_posting_lists(const rii_index_t *h, int64_t *offsets, int32_t *ids)
+{
+    if (!h || !offsets) return fail(RII_ERR_ARG, "null argument");
+    for (int i = 0; i <= h->nlist; ++i) offsets[i] = h->h_offsets[i];
+    if (ids && !h->h_ids.empty()) std::memcpy(ids, h->h_ids.data(), h->h_ids.size() * 4);
+    return 0;
+}
+
+int rii_set_state(rii_index_t *h, const uint8_t *coarse_centers, int nlist, const uint8_t *codes, int64_t N,
+                  const int64_t *offsets, const int32_t *ids)
+{
+    if (!h || nlist < 0 || N < 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    CKR(rii_clear(h));
+    if (N) {
+        if (!codes) return fail(RII_ERR_ARG, "codes is null");
+        CKR(rii_add_codes(h, codes, N, 0));
+    }
+    if (nlist) {
+        if (!coarse_centers || !offsets) return fail(RII_ERR_ARG, "coarse centers / offsets are null");
+        CKR(set_centers(h, coarse_centers, nlist));
+        const long long tot = offsets[nlist];
+        if (tot > 0 && !ids) return fail(RII_ERR_ARG, "ids is null");
+        for (int i = 0; i < nlist; ++i)
+            if (offsets[i + 1] < offsets[i]) return fail(RII_ERR_ARG, "posting list offsets must be non-decreasing");
+        for (long long i = 0; i < tot; ++i)
+            if (ids[i] < 0 || ids[i] >= N) return fail(RII_ERR_ARG, "posting list id outside [0, N)");
+        h->h_offsets.assign(offsets, offsets + nlist + 1);
+        h->h_ids.assign(ids, ids + tot);
+        CKR(upload_lists(h));
+    }
+    return 0;
+}
+
+int rii_dtable(rii_index_t *h, const float *queries, int B, float *out)
+{
+    if (!h || !queries || !out || B <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    const int D = h->M * h->Ds, lutf = h->M * h->Ks;
+    CKR(h->q.ensure((size_t)B * D * 4));
+    CKR(h->T.ensure((size_t)B * lutf * 4));
+    CK(cudaMemcpyAsync(h->q.p, queries, (size_t)B * D * 4, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
+    k_dtable<<<grid, RII_THREADS, 0, h->stream>>>(h->q.as<float>(), h->d_cw, h->T.as<float>(), h->M, h->Ks, h->Ds, h->variant);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->T.p, (size_t)B * lutf * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rii_adist_all(rii_index_t *h, const float *query, float *out)
+{
+    if (!h || !query || !out) return fail(RII_ERR_ARG, "bad arguments");
+    if (h->N == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const int D = h->M * h->Ds, lutf = h->M * h->Ks;
+    CKR(h->q.ensure((size_t)D * 4));
+    CKR(h->T.ensure((size_t)lutf * 4));
+    CKR(h->tmp0.ensure((size_t)h->N * 4));
+    CK(cudaMemcpyAsync(h->q.p, query, (size_t)D * 4, cudaMemcpyHostToDevice, h->stream));
+    k_dtable<<<dim3((lutf + RII_THREADS - 1) / RII_THREADS, 1), RII_THREADS, 0, h->stream>>>(h->q.as<float>(), h->d_cw, h->T.as<float>(),
+                                                                                           h->M, h->Ks, h->Ds, h->variant);
+    LAUNCHED();
+    const size_t smem = (size_t)lutf * 4;
+    const unsigned grid = (unsigned)std::min<long long>(1184, (h->N + RII_THREADS - 1) / RII_THREADS);
+    DISPATCH_M(h->M, {
+        CKR(set_smem(k_adc_all<MT>, smem));
+        k_adc_all<MT><<<dim3(grid, 1), RII_THREADS, smem, h->stream>>>(h->T.as<float>(), h->d_codes, h->N, h->M, h->Ks, h->tmp0.as<float>());
+    });
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->tmp0.p, (size_t)h->N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rii_assign(rii_index_t *h, const uint8_t *codes, int64_t n, const uint8_t *centers, int K, int32_t *out_assign, float *out_dist)
+{
+    if (!h || !codes || !centers || !out_assign || n < 0 || K <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    DevBuf dc, dk, da, dd;
+    int rc = 0;
+    do {
+        if ((rc = dc.ensure((size_t)n * h->M)) < 0) break;
+        if ((rc = dk.ensure((size_t)K * h->M)) < 0) break;
+        if ((rc = da.ensure((size_t)n * 4)) < 0) break;
+        if (out_dist && (rc = dd.ensure((size_t)n * 4)) < 0) break;
+        cudaMemcpyAsync(dc.p, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dk.p, centers, (size_t)K * h->M, cudaMemcpyHostToDevice, h->stream);
+        if ((rc = launch_assign(h, dc.as<uint8_t>(), n, dk.as<uint8_t>(), K, da.as<int>(), out_dist ? dd.as<float>() : nullptr)) < 0) break;
+        cudaMemcpyAsync(out_assign, da.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (out_dist) cudaMemcpyAsync(out_dist, dd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(RII_ERR_CUDA, std::string("rii_assign: ") + cudaGetErrorString(e));
+    } while (0);
+    dc.release(); dk.release(); da.release(); dd.release();
+    return rc;
+}
+
+int rii_sym_matrices(rii_index_t *h, float *out)
+{
+    if (!h || !out) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    CKR(ensure_Dm(h));
+    CK(cudaMemcpyAsync(out, h->d_Dm, (size_t)h->M * h->Ks * h->Ks * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total)
+{
+    if (!h || id_base < 0 || N_total < 0) return fail(RII_ERR_ARG, "bad arguments");
+    h->id_base = id_base;
+    h->N_total = N_total;
+    return 0;
+}
+
+int rii_set_coarse_centers(rii_index_t *h, const uint8_t *centers, int nlist)
+{
+    if (!h || !centers || nlist <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    CKR(set_centers(h, centers, nlist));
+    return update_posting_lists(h, 0, h->N);
+}
+
+int rii_fit_coarse(rii_index_t *h, const uint8_t *sample, int64_t ns, int nlist, int iter, uint8_t *centers_out)
+{
+    if (!h || !sample || !centers_out || ns <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    DevBuf ds;
+    int rc = ds.ensure((size_t)ns * h->M);
+    if (rc == 0) {
+        cudaMemcpyAsync(ds.p, sample, (size_t)ns * h->M, cudaMemcpyHostToDevice, h->stream);
+        rc = fit_coarse(h, ds.as<uint8_t>(), ns, nlist, iter, centers_out);
+    }
+    ds.release();
+    return rc;
+}
+
+int rii_copy_list_lengths(const rii_index_t *h, int32_t *out)
+{
+    if (!h || !out) return fail(RII_ERR_ARG, "bad arguments");
+    for (int i = 0; i < h->nlist; ++i) out[i] = (int32_t)(h->h_offsets[i + 1] - h->h_offsets[i]);
+    return 0;
+}
+
+int rii_set_global_lengths(rii_index_t *h, const int32_t *glob_len, const int32_t *pre_len)
+{
+    if (!h || !glob_len || !pre_len || h->nlist <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    CKR(h->glob_len.ensure((size_t)h->nlist * 4));
+    CKR(h->pre_len.ensure((size_t)h->nlist * 4));
+    CK(cudaMemcpy(h->glob_len.p, glob_len, (size_t)h->nlist * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->pre_len.p, pre_len, (size_t)h->nlist * 4, cudaMemcpyHostToDevice));
+    std::vector<int> len(glob_len, glob_len + h->nlist);
+    std::sort(len.begin(), len.end());
+    h->len_sorted_prefix.assign(h->nlist + 1, 0);
+    for (int i = 0; i < h->nlist; ++i) h->len_sorted_prefix[i + 1] = h->len_sorted_prefix[i] + len[i];
+    h->has_global = true;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""`main.RiiCpp` work-alike over the C ABI: same constructor, methods, attributes, return types and dtype
+strictness as the reference's pybind11 class (src/main.cpp:12-54), so that rii/rii.py-style host code and the
+reference's own tests (tests/test_rii.py) run unchanged against the B200 path."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check
+
+__version__ = "0.2.12"
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _strict(a, dtype, ndim, name):
+    """py::arg(name).noconvert() (src/main.cpp:18-26): wrong dtype / layout raises TypeError."""
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.ndim != ndim or not a.flags.c_contiguous:
+        raise TypeError("%s must be a C-contiguous numpy.ndarray[%s] with ndim=%d (no implicit conversion)"
+                        % (name, np.dtype(dtype).name, ndim))
+    return a
+
+
+class RiiCpp(object):
+    def __init__(self, codewords=None, verbose=False, device=0, l2_variant=0):
+        self._h = None
+        self._codewords = None
+        self._device = device
+        self._l2_variant = l2_variant
+        if codewords is not None:
+            self._create(codewords, verbose)
+
+    def _create(self, codewords, verbose):
+        cw = np.ascontiguousarray(codewords, dtype=np.float32)  # src/main.cpp:14 allows implicit conversion
+        if cw.ndim != 3:
+            raise ValueError("codewords must have ndim=3: (M, Ks, Ds)")
+        self._codewords = cw
+        M, Ks, Ds = cw.shape
+        h = C.c_void_p()
+        check(_capi.lib().rii_create(_ptr(cw, C.c_float), M, Ks, Ds, int(bool(verbose)), self._device,
+                                     self._l2_variant, C.byref(h)))
+        self._h = h
+        self.M, self.Ks, self.Ds = M, Ks, Ds
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _capi.lib().rii_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- src/main.cpp:15-28 -------------------------------------------------------------------
+    def reconfigure(self, nlist, iter):
+        check(_capi.lib().rii_reconfigure(self._h, int(nlist), int(iter)))
+
+    def add_codes(self, codes, update_flag):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if codes.ndim != 2 or codes.shape[1] != self.M:
+            raise ValueError("codes must have shape (N, M)")
+        check(_capi.lib().rii_add_codes(self._h, _ptr(codes, C.c_uint8), codes.shape[0], int(bool(update_flag))))
+
+    def query_linear(self, query, topk, target_ids):
+        q = _strict(query, np.float32, 1, "query")
+        t = _strict(target_ids, np.int64, 1, "target_ids")
+        if q.shape[0] != self.M * self.Ds:
+            raise ValueError("query must have M * Ds = %d elements" % (self.M * self.Ds))
+        ids = np.empty(int(topk), np.int64)
+        dists = np.empty(int(topk), np.float32)
+        n = check(_capi.lib().rii_query_linear(self._h, _ptr(q, C.c_float), int(topk), _ptr(t, C.c_int64), t.size,
+                                               _ptr(ids, C.c_int64), _ptr(dists, C.c_float)))
+        return ids[:n].tolist(), dists[:n].tolist()
+
+    def query_ivf(self, query, topk, target_ids, L):
+        q = _strict(query, np.float32, 1, "query")
+        t = _strict(target_ids, np.int64, 1, "target_ids")
+        if q.shape[0] != self.M * self.Ds:
+            raise ValueError("query must have M * Ds = %d elements" % (self.M * self.Ds))
+        ids = np.empty(int(topk), np.int64)
+        dists = np.empty(int(topk), np.float32)
+        n = check(_capi.lib().rii_query_ivf(self._h, _ptr(q, C.c_float), int(topk), _ptr(t, C.c_int64), t.size, int(L),
+                                            _ptr(ids, C.c_int64), _ptr(dists, C.c_float)))
+        return ids[:n].tolist(), dists[:n].tolist()
+
+    def clear(self):
+        check(_capi.lib().rii_clear(self._h))
+
+    # ---- batch entry (new; include/rii_b200.h rii_query_batch) -------------------------------
+    def query_batch(self, queries, topk, target_ids=None, L=0, method="linear"):
+        """queries float32 (B, D) -> (ids int64 (B, topk), dists float32 (B, topk), counts int32 (B))."""
+        Q = _strict(queries, np.float32, 2, "queries")
+        t = np.empty(0, np.int64) if target_ids is None else _strict(target_ids, np.int64, 1, "target_ids")
+        B = Q.shape[0]
+        ids = np.full((B, int(topk)), -1, np.int64)
+        dists = np.full((B, int(topk)), np.inf, np.float32)
+        counts = np.zeros(B, np.int32)
+        m = {"linear": 0, "ivf": 1}[method]
+        check(_capi.lib().rii_query_batch(self._h, _ptr(Q, C.c_float), B, int(topk), _ptr(t, C.c_int64), t.size,
+                                          int(L), m, _ptr(ids, C.c_int64), _ptr(dists, C.c_float),
+                                          _ptr(counts, C.c_int32)))
+        return ids, dists, counts
+
+    # ---- attributes, src/main.cpp:29-34 -----------------------------------------------------
+    @property
+    def verbose(self):
+        return bool(_capi.lib().rii_get_verbose(self._h))
+
+    @verbose.setter
+    def verbose(self, v):
+        check(_capi.lib().rii_set_verbose(self._h, int(bool(v))))
+
+    @property
+    def N(self):
+        return int(_capi.lib().rii_get_N(self._h)) if self._h is not None else 0
+
+    @property
+    def nlist(self):
+        return int(_capi.lib().rii_get_nlist(self._h)) if self._h is not None else 0
+
+    # numpy views of the state (the list-returning properties below copy-convert like the reference)
+    def codes_array(self):
+        out = np.empty((self.N, self.M), np.uint8)
+        if self.N:
+            check(_capi.lib().rii_copy_codes(self._h, _ptr(out, C.c_uint8)))
+        return out
+
+    def coarse_centers_array(self):
+        out = np.empty((self.nlist, self.M), np.uint8)
+        if self.nlist:
+            check(_capi.lib().rii_copy_coarse_centers(self._h, _ptr(out, C.c_uint8)))
+        return out
+
+    def posting_lists_csr(self):
+        offsets = np.zeros(self.nlist + 1, np.int64)
+        ids = np.empty(self.N, np.int32)
+        check(_capi.lib().rii_copy_posting_lists(self._h, _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
+        return offsets, ids[: offsets[-1]]
+
+    @property
+    def coarse_centers(self):
+        return self.coarse_centers_array().tolist()
+
+    @property
+    def flattened_codes(self):
+        return self.codes_array().reshape(-1).tolist()
+
+    @property
+    def posting_lists(self):
+        offsets, ids = self.posting_lists_csr()
+        return [ids[offsets[i]:offsets[i + 1]].tolist() for i in range(self.nlist)]
+
+    # ---- pickle, src/main.cpp:35-54: the same 5-tuple, with arrays instead of nested lists ---
+    def __getstate__(self):
+        offsets, ids = self.posting_lists_csr()
+        return (self._codewords, self.verbose, self.coarse_centers_array(), self.codes_array(), (offsets, ids),
+                self._device, self._l2_variant)
+
+    def __setstate__(self, t):
+        if len(t) not in (5, 7):
+            raise RuntimeError("Invalid state when reading pickled item")
+        self._h = None
+        self._device, self._l2_variant = (t[5], t[6]) if len(t) == 7 else (0, 0)
+        self._create(np.asarray(t[0], np.float32), bool(t[1]))
+        centers = np.ascontiguousarray(t[2], np.uint8).reshape(-1, self.M)
+        codes = np.ascontiguousarray(t[3], np.uint8).reshape(-1, self.M)
+        pl = t[4]
+        if isinstance(pl, tuple):
+            offsets, ids = np.ascontiguousarray(pl[0], np.int64), np.ascontiguousarray(pl[1], np.int32)
+        else:  # the reference's list-of-lists form
+            offsets = np.zeros(len(pl) + 1, np.int64)
+            offsets[1:] = np.cumsum([len(p) for p in pl])
+            ids = np.ascontiguousarray(np.concatenate([np.asarray(p, np.int32) for p in pl]) if offsets[-1] else
+                                       np.zeros(0, np.int32), np.int32)
+        check(_capi.lib().rii_set_state(self._h, _ptr(centers, C.c_uint8), centers.shape[0], _ptr(codes, C.c_uint8),
+                                        codes.shape[0], _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
+
+    # ---- building blocks (parity tests) -------------------------------------------------------
+    def dtable(self, queries):
+        Q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.M * self.Ds)
+        out = np.empty((Q.shape[0], self.M, self.Ks), np.float32)
+        check(_capi.lib().rii_dtable(self._h, _ptr(Q, C.c_float), Q.shape[0], _ptr(out, C.c_float)))
+        return out
+
+    def adist_all(self, query):
+        q = np.ascontiguousarray(query, np.float32)
+        out = np.empty(self.N, np.float32)
+        check(_capi.lib().rii_adist_all(self._h, _ptr(q, C.c_float), _ptr(out, C.c_float)))
+        return out
+
+    def assign(self, codes, centers, return_dist=False):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        centers = np.ascontiguousarray(centers, np.uint8)
+        a = np.empty(codes.shape[0], np.int32)
+        d = np.empty(codes.shape[0], np.float32)
+        check(_capi.lib().rii_assign(self._h, _ptr(codes, C.c_uint8), codes.shape[0], _ptr(centers, C.c_uint8),
+                                     centers.shape[0], _ptr(a, C.c_int32), _ptr(d, C.c_float)))
+        return (a, d) if return_dist else a
+
+    def sym_matrices(self):
+        out = np.empty((self.M, self.Ks, self.Ks), np.float32)
+        check(_capi.lib().rii_sym_matrices(self._h, _ptr(out, C.c_float)))
+        return out

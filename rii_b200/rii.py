@@ -1,0 +1,256 @@
+"""`rii.Rii` public API (rii/rii.py:6-400 of the reference) hosted on the B200 ADC path.
+
+Same properties, methods, argument meaning, assertions and return dtypes; the only engine underneath is
+`rii_b200.main.RiiCpp` (CUDA, via the C ABI).  Additions are opt-in: `query_batch`, `device=`.
+"""
+import copy
+import time
+
+import numpy as np
+
+from . import main
+from . import pq as _pq
+
+
+class Rii(object):
+    """Reconfigurable inverted index over PQ codes (IVFADC with subset search and reconfiguration).
+
+    Args:
+        fine_quantizer: a trained PQ / OPQ instance (`rii_b200.pq` or `nanopq`); rii/rii.py:32-38.
+        device (int): CUDA device ordinal of the index.
+    """
+
+    def __init__(self, fine_quantizer, device=0):
+        assert _pq.is_quantizer(fine_quantizer)
+        assert fine_quantizer.codewords is not None, "Please fit the PQ/OPQ instance first"
+        assert fine_quantizer.Ks <= 256, "Ks must be less than 256 so that each code must be uint8"
+        self.fine_quantizer = copy.deepcopy(fine_quantizer)
+        self.impl_cpp = main.RiiCpp(fine_quantizer.codewords, fine_quantizer.verbose, device=device)
+        self.threshold = None
+
+    # ---- properties, rii/rii.py:40-121 ------------------------------------------------------
+    @property
+    def M(self):
+        return self.fine_quantizer.M
+
+    @property
+    def Ks(self):
+        return self.fine_quantizer.Ks
+
+    @property
+    def N(self):
+        return self.impl_cpp.N
+
+    @property
+    def nlist(self):
+        return self.impl_cpp.nlist
+
+    @property
+    def codewords(self):
+        return self.fine_quantizer.codewords
+
+    @property
+    def coarse_centers(self):
+        if self.nlist == 0:
+            return None
+        return self.impl_cpp.coarse_centers_array().astype(self.fine_quantizer.code_dtype)
+
+    @property
+    def codes(self):
+        if self.N == 0:
+            return None
+        return self.impl_cpp.codes_array().astype(self.fine_quantizer.code_dtype).reshape(self.N, self.M)
+
+    @property
+    def posting_lists(self):
+        return self.impl_cpp.posting_lists
+
+    @property
+    def verbose(self):
+        return self.impl_cpp.verbose
+
+    @verbose.setter
+    def verbose(self, v):
+        self.fine_quantizer.verbose = v
+        self.impl_cpp.verbose = v
+
+    @property
+    def L0(self):
+        if self.nlist == 0:
+            return None
+        return int(np.round(self.N / self.nlist))
+
+    # ---- build, rii/rii.py:123-233 ----------------------------------------------------------
+    def reconfigure(self, nlist=None, iter=5):
+        if nlist is None:
+            nlist = int(np.sqrt(self.N))
+        assert 0 < nlist
+        self.impl_cpp.reconfigure(nlist, iter)
+        self.threshold = estimate_best_threshold_function(
+            e=self, queries=self.fine_quantizer.decode(self.codes[:min(100, self.N)]))
+
+    def add(self, vecs, update_posting_lists="auto"):
+        assert vecs.ndim == 2
+        assert vecs.dtype == np.float32
+        self.impl_cpp.add_codes(self.fine_quantizer.encode(vecs),
+                                self._resolve_update_posting_lists_flag(update_posting_lists))
+
+    def add_configure(self, vecs, nlist=None, iter=5):
+        self.add(vecs=vecs, update_posting_lists=False)
+        self.reconfigure(nlist=nlist, iter=iter)
+        return self
+
+    def merge(self, engine, update_posting_lists="auto"):
+        assert isinstance(engine, Rii)
+        assert self.fine_quantizer == engine.fine_quantizer, \
+            "Two engines to be merged must have the same fine quantizer"
+        if engine.N != 0:
+            self.impl_cpp.add_codes(engine.codes, self._resolve_update_posting_lists_flag(update_posting_lists))
+        if self.verbose:
+            print("The number of codes: {}".format(self.N))
+
+    # ---- search, rii/rii.py:235-320 ---------------------------------------------------------
+    def _prepare(self, topk, L, target_ids, sort_target_ids):
+        assert 0 < self.N
+        assert 0 < self.nlist
+        if topk is None:
+            topk = self.N
+        assert 1 <= topk <= self.N
+        if L is None:
+            L = self._multiple_of_L0_covering_topk(topk=topk)
+        assert topk <= L <= self.N, \
+            "Parameters are weird. Make sure topk<=L<=N:  topk={}, L={}, N={}".format(topk, L, self.N)
+        if target_ids is None:
+            tids = np.array([], dtype=np.int64)
+            len_target_ids = self.N
+        else:
+            assert isinstance(target_ids, np.ndarray)
+            assert target_ids.dtype == np.int64
+            assert target_ids.ndim == 1
+            tids = np.sort(target_ids) if sort_target_ids else np.ascontiguousarray(target_ids)
+            len_target_ids = len(tids)
+        assert topk <= len_target_ids <= self.N, \
+            "Parameters are weird. Make sure topk<=len(target_ids)<=N:  " \
+            "topk={}, len(target_ids)={}, N={}".format(topk, len_target_ids, self.N)
+        return topk, L, tids, len_target_ids
+
+    def query(self, q, topk=1, L=None, target_ids=None, sort_target_ids=True, method="auto"):
+        """ids (topk,) int64 and distances (topk,) float64 of the nearest PQ codes; rii/rii.py:235-320."""
+        assert method in ["auto", "linear", "ivf"]
+        topk, L, tids, len_target_ids = self._prepare(topk, L, target_ids, sort_target_ids)
+        q_ = self.fine_quantizer.rotate(q) if _pq.is_opq(self.fine_quantizer) else q
+        if method == "auto":
+            method = "linear" if self._use_linear(len_target_ids, L) else "ivf"
+        if method == "linear":
+            ids, dists = self.impl_cpp.query_linear(q_, topk, tids)
+        else:
+            ids, dists = self.impl_cpp.query_ivf(q_, topk, tids, L)
+        return np.array(ids, np.int64), np.array(dists)
+
+    def query_batch(self, Q, topk=1, L=None, target_ids=None, sort_target_ids=True, method="ivf"):
+        """Batch form of :func:`query` (not in the reference): Q (B, D) float32 ->
+        ids (B, topk) int64 (-1 padded), dists (B, topk) float64 (inf padded), counts (B,) int32."""
+        assert method in ["linear", "ivf"]
+        assert Q.ndim == 2 and Q.dtype == np.float32
+        topk, L, tids, _ = self._prepare(topk, L, target_ids, sort_target_ids)
+        Q_ = self.fine_quantizer.rotate(Q) if _pq.is_opq(self.fine_quantizer) else Q
+        ids, dists, counts = self.impl_cpp.query_batch(np.ascontiguousarray(Q_, np.float32), topk, tids, L, method)
+        return ids, dists.astype(np.float64), counts
+
+    def clear(self):
+        self.threshold = None
+        self.impl_cpp.clear()
+
+    def print_params(self):
+        print("verbose:", self.verbose)
+        print("M:", self.M)
+        print("Ks:", self.Ks)
+        print("fine_quantizer:", self.fine_quantizer)
+        print("N:", self.N)
+        print("nlist:", self.nlist)
+        print("L0:", self.L0)
+        print("cordwords.shape:", self.codewords.shape)
+        print("coarse_centers.shape:", None if self.nlist == 0 else self.coarse_centers.shape)
+        print("codes.shape:", None if self.codes is None else self.codes.shape)
+        lens = [len(p) for p in self.posting_lists]
+        print("[len(poslist) for poslist in posting_lists]: [" + "".join(str(v) + ", " for v in lens[:11]) +
+              (" ..." if len(lens) > 11 else "") + "]")
+        for topk in 1, 10, 100:
+            L = "None" if self.nlist == 0 else self._multiple_of_L0_covering_topk(topk)
+            print("_multiple_of_L0_covering_topk(topk={}): {}".format(topk, L))
+        print("threshold function thre_{|S|}=f(L):", self.threshold)
+        for S in [10 ** (2 + n) for n in range(5)]:
+            use_linear = None if self.threshold is None else self._use_linear(S, self.L0)
+            print("_use_linear({S}, L={L0}): {use_linear}".format(S=S, L0=self.L0, use_linear=use_linear))
+
+    # ---- helpers, rii/rii.py:374-400 --------------------------------------------------------
+    def _multiple_of_L0_covering_topk(self, topk):
+        return min((topk // self.L0 + 1) * self.L0, self.N)
+
+    def _use_linear(self, len_target_ids, L):
+        return bool(len_target_ids <= self.threshold(L))
+
+    def _resolve_update_posting_lists_flag(self, flag):
+        assert flag in ["auto", True, False]
+        if flag == "auto":
+            return 0 < self.nlist
+        return flag
+
+
+def estimate_best_threshold_function(e, queries):
+    """Fit threshold(L) = |S| at which linear scan and inverted-index search cost the same (rii/rii.py:403-486):
+    for a few L, double |S| until ivf beats linear, bisect 5 times, then fit a line through (L, |S|).
+    Wall-clock driven like the reference, so `method='auto'` is not deterministic; parity tests pass an
+    explicit method."""
+    topk = 1
+    queries = np.ascontiguousarray(queries, np.float32)
+
+    def cost(method, Q, s, L):
+        tids = np.arange(s, dtype=np.int64)
+        t0 = time.time()
+        for q in Q:
+            if method == "linear":
+                e.impl_cpp.query_linear(q, topk, tids)
+            else:
+                e.impl_cpp.query_ivf(q, topk, tids, L)
+        return (time.time() - t0) / Q.shape[0]
+
+    def crossover(L):
+        if e.N <= 128:
+            return e.N
+        sizes = [128]
+        while sizes[-1] * 2 < e.N:
+            sizes.append(sizes[-1] * 2)
+        sizes.append(e.N)
+        for s in sizes:
+            if cost("ivf", queries[:3], s, L) < cost("linear", queries[:3], s, L):
+                if s == 128:
+                    return 128
+                lo, hi = s // 2, s
+                for _ in range(5):
+                    mid = int(np.round((lo + hi) / 2))
+                    if cost("ivf", queries, mid, L) < cost("linear", queries, mid, L):
+                        hi = mid
+                    else:
+                        lo = mid
+                return lo
+        return e.N
+
+    if e.verbose:
+        print("===== Threshold selection ====")
+    xs, ys = [], []
+    for L in [k * e._multiple_of_L0_covering_topk(k) for k in [1, 2, 4, 8, 16]]:
+        if e.N < L:
+            continue
+        xs.append(L)
+        ys.append(crossover(L))
+        if ys[-1] == e.N:
+            break
+    z = [0, ys[0]] if len(xs) == 1 else np.polyfit(xs, ys, 1)
+    p = np.poly1d(z)
+    if e.verbose:
+        print("L:", xs)
+        print("threshold:", ys)
+        print("polyfit coeff:", z)
+        print("resultant func:", p)
+    return p
