@@ -1,0 +1,314 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, rii_b200.main.RiiCpp) against
+  (1) the golden vectors recorded from the unmodified reference (tests/golden/),
+  (2) the oracle restatement on fresh seeded inputs (sizes the oracle finishes in seconds),
+  (3) size-independent properties at BASELINE.json's N = 1M.
+Bar: ids bit-exact under the (distance, id) order, distances bit-exact fp32 (tolerance 0; the contract in
+BASELINE.json is 1e-5 relative)."""
+import numpy as np
+import pytest
+
+from _util import O, assert_same_result, bits, canonical_topk, golden_files, load_golden, synth
+
+pytestmark = pytest.mark.gpu
+
+FILES = golden_files("strict_v4") + golden_files("strict_v3")
+EMPTY = np.array([], np.int64)
+
+
+def engine(cw, codes=None, variant=16):
+    from rii_b200 import main
+    e = main.RiiCpp(cw, False, l2_variant=variant)
+    if codes is not None:
+        e.add_codes(codes, False)
+    return e
+
+
+def load_state(e, g):
+    import ctypes as C
+    from rii_b200 import _capi
+    centers, codes = np.ascontiguousarray(g["centers"]), np.ascontiguousarray(g["codes"])
+    offsets, ids = np.ascontiguousarray(g["offsets"], np.int64), np.ascontiguousarray(g["ids"], np.int32)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    _capi.check(_capi.lib().rii_set_state(e._h, p(centers, C.c_uint8), centers.shape[0], p(codes, C.c_uint8),
+                                          codes.shape[0], p(offsets, C.c_int64), p(ids, C.c_int32)))
+
+
+# ---------------------------------------------------------------- golden vectors (reference-derived) --
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1])
+def test_golden_dtable_adist(path):
+    g = load_golden(path)
+    e = engine(g["cw"], g["codes"], g["variant"])
+    T = e.dtable(g["Q"])
+    for i, q in enumerate(g["Q"]):
+        assert np.array_equal(bits(T[i]), bits(O.dtable(q, g["cw"], g["variant"]))), "dtable %d" % i
+        assert np.array_equal(bits(e.adist_all(q)), bits(g["all_dists"][i])), "adist %d" % i
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1])
+def test_golden_query_linear(path):
+    g = load_golden(path)
+    e = engine(g["cw"], g["codes"], g["variant"])
+    N = len(g["codes"])
+    for j, (i, topk) in enumerate(g["lin_meta"]):
+        q = g["Q"][i]
+        ids, d = e.query_linear(q, int(topk), EMPTY)
+        eid, ed = canonical_topk(np.arange(N), g["all_dists"][i], int(topk))
+        assert_same_result(ids, np.array(d, np.float32), eid, ed, "linear")
+        assert np.array_equal(bits(np.sort(g["lin_%d_d" % j])), bits(np.array(d, np.float32)))
+        sids, sd = e.query_linear(q, int(topk), g["tids"])
+        eid, ed = canonical_topk(g["tids"], g["all_dists"][i][g["tids"]], int(topk))
+        assert_same_result(sids, np.array(sd, np.float32), eid, ed, "linear subset")
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1])
+def test_golden_query_ivf(path):
+    g = load_golden(path)
+    e = engine(g["cw"], variant=g["variant"])
+    load_state(e, g)
+    for j, (i, topk, L, sub, ncand) in enumerate(g["ivf_meta"]):
+        ids, d = e.query_ivf(g["Q"][i], int(topk), g["tids"] if sub else EMPTY, int(L))
+        assert_same_result(ids, np.array(d, np.float32), g["ivf_%d_ids" % j], g["ivf_%d_d" % j],
+                           "ivf case %d (topk=%d L=%d sub=%d)" % (j, topk, L, sub))
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1])
+def test_golden_reconfigure(path):
+    g = load_golden(path)
+    e = engine(g["cw"], g["codes"], g["variant"])
+    e.reconfigure(g["nlist"], g["iter"])
+    assert np.array_equal(e.coarse_centers_array(), g["centers"])
+    offsets, ids = e.posting_lists_csr()
+    assert np.array_equal(offsets, g["offsets"])
+    assert np.array_equal(ids, g["ids"])
+
+
+# ---------------------------------------------------------------- oracle on fresh inputs ---------------
+SHAPES = [(128, 32, 256), (40, 4, 20), (40, 20, 256), (96, 32, 256), (128, 64, 256), (64, 8, 64), (48, 16, 256),
+          (36, 3, 7), (72, 4, 16)]
+
+
+@pytest.mark.parametrize("D,M,Ks", SHAPES)
+def test_oracle_linear_and_subset(D, M, Ks):
+    N = 20000
+    cw, codes, Q = synth(D, M, Ks, N, 4, seed=D * 1000 + M)
+    e = engine(cw, codes)
+    rng = np.random.default_rng(7)
+    tids = np.sort(rng.choice(N, 3000, replace=False)).astype(np.int64)
+    unsorted = rng.permutation(tids)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 10, 100, 1500):
+            ids, d = e.query_linear(q, topk, EMPTY)
+            assert_same_result(ids, np.array(d, np.float32), *O.query_linear(T, codes, topk), "linear k=%d" % topk)
+            ids, d = e.query_linear(q, topk, tids)
+            assert_same_result(ids, np.array(d, np.float32), *O.query_linear(T, codes, topk, tids), "subset")
+        ids, d = e.query_linear(q, 10, unsorted)  # target ids need not be sorted for the linear scan
+        assert_same_result(ids, np.array(d, np.float32), *O.query_linear(T, codes, 10, unsorted), "unsorted subset")
+
+
+@pytest.mark.parametrize("D,M,Ks", [(128, 32, 256), (40, 4, 20), (40, 20, 256), (128, 64, 256)])
+def test_oracle_reconfigure_assign_ivf(D, M, Ks):
+    N, nlist = 30000, 60
+    cw, codes, Q = synth(D, M, Ks, N, 6, seed=D + M)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 3)
+    centers, assign = O.reconfigure(cw, codes, nlist, 3)
+    assert np.array_equal(e.coarse_centers_array(), centers)
+    offsets, ids = O.assign_to_lists(assign, nlist)
+    eo, ei = e.posting_lists_csr()
+    assert np.array_equal(eo, offsets) and np.array_equal(ei, ids)
+    # K6 building block, with distances
+    Dm = O.sym_matrices(cw)
+    assert np.array_equal(bits(e.sym_matrices()), bits(Dm))
+    a, d = e.assign(codes[:5000], centers, return_dist=True)
+    oa, od = O.assign(Dm, codes[:5000], centers, return_dist=True)
+    assert np.array_equal(a, oa) and np.array_equal(bits(d), bits(od))
+    # IVF
+    rng = np.random.default_rng(3)
+    tids = np.sort(rng.choice(N, N // 10, replace=False)).astype(np.int64)
+    L0 = N // nlist
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk, L, t in [(1, L0, None), (10, 4 * L0, None), (100, 32 * L0 // 4, None), (5, N, None), (1, L0, tids),
+                           (20, 3 * L0, tids), (3, len(tids), tids), (50, 17, None) if False else (17, 50, None)]:
+            ids, dd = e.query_ivf(q, topk, EMPTY if t is None else t, L)
+            oi, odd = O.query_ivf(T, codes, centers, offsets, ids=ei, topk=topk, L=L, tids=t)
+            assert_same_result(ids, np.array(dd, np.float32), oi, odd, "ivf k=%d L=%d sub=%s" % (topk, L, t is not None))
+
+
+def test_ivf_walk_beyond_w_and_empty():
+    """SURVEY A.3 3rd/4th bullet: target ids concentrated in far lists -> the walk continues beyond w (we
+    re-run with the full ranking, oracle order (dist, list id)), or nothing is found at all (empty result)."""
+    D, M, Ks, N, nlist = 128, 32, 256, 20000, 40
+    cw, codes, Q = synth(D, M, Ks, N, 4, seed=99)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 2)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        cd = np.array([O.adist_all(T, centers)]).reshape(-1)
+        far = np.argsort(cd)[-6:]
+        tids = np.sort(np.concatenate([ids[offsets[n]:offsets[n + 1]] for n in far])).astype(np.int64)
+        for topk, L in [(5, 20), (3, len(tids)), (len(tids), len(tids))]:
+            got = e.query_ivf(q, topk, tids, L)
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L, tids)
+            assert_same_result(got[0], np.array(got[1], np.float32), exp[0], exp[1], "beyond-w k=%d L=%d" % (topk, L))
+        # L can never be reached and fewer than topk ids are in the first w lists -> empty (src/rii.h:325)
+        few = tids[:3]
+        got = e.query_ivf(q, 3, few, 3)
+        exp = O.query_ivf(T, codes, centers, offsets, ids, 3, 3, few)
+        assert_same_result(got[0], np.array(got[1], np.float32), exp[0], exp[1], "tiny subset")
+
+
+def test_add_update_merge_clear_pickle():
+    import copy
+    import pickle
+    D, M, Ks = 128, 32, 256
+    cw, codes, Q = synth(D, M, Ks, 12000, 3, seed=5)
+    e = engine(cw, codes[:8000])
+    e.reconfigure(30, 2)
+    e.add_codes(codes[8000:], True)  # src/rii.h:189-192
+    assert e.N == 12000
+    centers = e.coarse_centers_array()
+    Dm = O.sym_matrices(cw)
+    assign = np.concatenate([O.assign(Dm, codes[:8000], centers), O.assign(Dm, codes[8000:], centers)])
+    offsets, ids = O.assign_to_lists(assign, 30)
+    eo, ei = e.posting_lists_csr()
+    assert np.array_equal(eo, offsets) and np.array_equal(ei, ids)
+    assert np.array_equal(e.codes_array(), codes)
+    e2 = pickle.loads(pickle.dumps(e))
+    e3 = copy.deepcopy(e)
+    for x in (e2, e3):
+        assert x.N == e.N and x.nlist == e.nlist
+        assert x.posting_lists == e.posting_lists and x.coarse_centers == e.coarse_centers
+        assert x.query_ivf(Q[0], 5, EMPTY, 800) == e.query_ivf(Q[0], 5, EMPTY, 800)
+    e.clear()
+    assert e.N == 0 and e.nlist == 0 and e.posting_lists == [] and e.coarse_centers == []
+    with pytest.raises(Exception):
+        e.add_codes(codes[:10], True)  # no coarse centers: the reference terminates (src/rii.h:166-170)
+
+
+def test_edge_cases():
+    D, M, Ks = 128, 32, 256
+    cw, codes, Q = synth(D, M, Ks, 1000, 2, seed=11)
+    e = engine(cw, codes[:1])
+    assert e.query_linear(Q[0], 1, EMPTY)[0] == [0]
+    e.reconfigure(1, 5)
+    assert e.posting_lists == [[0]]
+    assert e.query_ivf(Q[0], 1, EMPTY, 1)[0] == [0]
+    e = engine(cw, codes)
+    T = O.dtable(Q[0], cw, 16)
+    ids, d = e.query_linear(Q[0], 1000, EMPTY)  # topk == N (maximum)
+    assert_same_result(ids, np.array(d, np.float32), *O.query_linear(T, codes, 1000), "topk=N")
+    dup = np.array([5, 5, 9, 5], np.int64)  # duplicates -> duplicate results (docs: undefined; we keep them)
+    ids, d = e.query_linear(Q[0], 4, dup)
+    assert sorted(ids) == [5, 5, 5, 9]
+    with pytest.raises(TypeError):
+        e.query_linear(Q[0].astype(np.float64), 1, EMPTY)  # .noconvert(), src/main.cpp:18
+    with pytest.raises(TypeError):
+        e.query_linear(Q[0], 1, np.array([1], np.int32))
+    with pytest.raises(ValueError):
+        e.query_linear(Q[0], 1001, EMPTY)  # topk > N: the reference asserts (src/rii.h:200)
+    with pytest.raises(ValueError):
+        e.query_linear(Q[0], 1, np.array([1000], np.int64))  # out-of-range id: UB in the reference, refused here
+    with pytest.raises(Exception):
+        e.query_ivf(Q[0], 1, EMPTY, 10)  # no posting lists yet
+    ids, d, counts = e.query_batch(np.ascontiguousarray(Q), 7, method="linear")
+    for b in range(2):
+        exp = O.query_linear(O.dtable(Q[b], cw, 16), codes, 7)
+        assert_same_result(ids[b], d[b], exp[0], exp[1], "batch")
+    assert counts.tolist() == [7, 7]
+
+
+# ---------------------------------------------------------------- the reference's own property tests --
+def test_reference_properties_public_api():
+    """tests/test_rii.py:117-218 (test_query_linear / test_query_ivf / test_query) against rii_b200.Rii."""
+    import rii_b200 as rii
+    np.random.seed(123)
+    M, Ks, N, D = 20, 256, 1000, 40
+    X = np.random.random((N, D)).astype(np.float32)
+    e = rii.Rii(fine_quantizer=rii.PQ(M=M, Ks=Ks, verbose=False).fit(vecs=X, iter=5)).add_configure(vecs=X, nlist=20)
+    all_ids = np.arange(N, dtype=np.int64)
+    S = np.sort(np.random.choice(N, 300, replace=False)).astype(np.int64)
+    for n, q in enumerate(X[:20]):
+        ids1, d1 = e.impl_cpp.query_linear(q, 10, EMPTY)
+        assert isinstance(ids1, list) and isinstance(ids1[0], int) and isinstance(d1[0], float) and len(ids1) == 10
+        assert all(d1[i] <= d1[i + 1] for i in range(9)) and n in ids1
+        assert (ids1, d1) == tuple(e.impl_cpp.query_linear(q, 10, all_ids))        # :138-140
+        ids_s, _ = e.impl_cpp.query_linear(q, 10, S)
+        assert set(ids_s) <= set(S.tolist())                                       # :143-144
+        assert tuple(e.impl_cpp.query_ivf(q, 10, all_ids, N)) == (ids1, d1)        # :178-181
+        assert tuple(e.impl_cpp.query_ivf(q, 10, S, len(S))) == tuple(e.impl_cpp.query_linear(q, 10, S))  # :183-187
+        ids, dists = e.query(q, topk=50, method="ivf", L=600)
+        assert ids.dtype == np.int64 and dists.dtype == np.float64 and len(ids) == 50
+        assert np.all(np.diff(dists) >= 0)
+        ids, dists = e.query(q, topk=3)  # method='auto' goes through the fitted threshold
+        assert len(ids) == 3
+    # OPQ path: query is rotated first (rii/rii.py:305-306)
+    eo = rii.Rii(fine_quantizer=rii.OPQ(M=4, Ks=20, verbose=False).fit(vecs=X, pq_iter=5, rotation_iter=3))
+    eo.add_configure(vecs=X, nlist=20)
+    assert np.array_equal(eo.codes, eo.fine_quantizer.encode(X))
+    ids, dists = eo.query(X[3], topk=5, method="linear")
+    assert len(ids) == 5 and np.all(np.diff(dists) >= 0)
+    # merge (tests/test_rii.py:252-289)
+    e1 = rii.Rii(fine_quantizer=e.fine_quantizer)
+    e1.add_configure(vecs=X[:400], nlist=5)
+    e2 = rii.Rii(fine_quantizer=e.fine_quantizer)
+    e2.add_configure(vecs=X[400:], nlist=5)
+    e1.merge(e2)
+    assert e1.N == N and np.array_equal(e1.codes, e.fine_quantizer.encode(X))
+    assert sorted(sum(e1.posting_lists, [])) == list(range(N))
+
+
+# ---------------------------------------------------------------- BASELINE sizes: properties ----------
+def test_full_size_properties_c2_c3():
+    """N = 1M, M = 32 (BASELINE C2/C3).  The oracle still finishes a handful of queries in seconds, so a few
+    are checked bit-exactly; the rest through size-independent properties (ivf(L=N) == linear,
+    subset(all ids) == no subset, subset results inside S, sortedness, idempotence)."""
+    D, M, Ks, N, nlist = 128, 32, 256, 1000000, 1000
+    cw, codes, Q = synth(D, M, Ks, N, 16, seed=2024)
+    e = engine(cw, codes)
+    # C2 index: coarse centers from a GPU reconfigure with iter=1; lists == oracle assignment
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    assert offsets[-1] == N and np.array_equal(np.sort(ids), np.arange(N))
+    Dm = O.sym_matrices(cw)
+    sl = slice(123456, 123456 + 20000)
+    assert np.array_equal(O.assign(Dm, codes[sl], centers), _assign_of(offsets, ids, N)[sl])
+    rng = np.random.default_rng(1)
+    tids = np.sort(rng.choice(N, 100000, replace=False)).astype(np.int64)   # C3
+    all_ids = np.arange(N, dtype=np.int64)
+    for i, q in enumerate(Q):
+        lin = e.query_linear(q, 10, EMPTY)
+        assert lin == e.query_linear(q, 10, EMPTY)                           # idempotent
+        assert all(lin[1][j] <= lin[1][j + 1] for j in range(9))
+        assert e.query_linear(q, 10, all_ids) == lin
+        assert e.query_ivf(q, 10, EMPTY, N) == lin                           # ivf over everything == linear
+        sub = e.query_linear(q, 10, tids)
+        assert set(sub[0]) <= set(tids.tolist())
+        assert e.query_ivf(q, 10, tids, len(tids)) == sub
+        ivf = e.query_ivf(q, 1, EMPTY, 32000)                                # C2 operating point
+        assert len(ivf[0]) == 1
+        if i < 3:  # bit-exact against the oracle at full size
+            T = O.dtable(q, cw, 16)
+            assert_same_result(lin[0], np.array(lin[1], np.float32), *O.query_linear(T, codes, 10), "C1/N=1M linear")
+            assert_same_result(sub[0], np.array(sub[1], np.float32), *O.query_linear(T, codes, 10, tids), "C3")
+            o = O.query_ivf(T, codes, centers, offsets, ids, 1, 32000)
+            assert_same_result(ivf[0], np.array(ivf[1], np.float32), o[0], o[1], "C2")
+            o = O.query_ivf(T, codes, centers, offsets, ids, 5, 32000, tids)
+            g = e.query_ivf(q, 5, tids, 32000)
+            assert_same_result(g[0], np.array(g[1], np.float32), o[0], o[1], "C2+C3")
+    # batch entry == loop of single queries
+    bi, bd, bc = e.query_batch(np.ascontiguousarray(Q), 1, L=32000, method="ivf")
+    for i, q in enumerate(Q):
+        one = e.query_ivf(q, 1, EMPTY, 32000)
+        assert bi[i].tolist() == one[0] and bd[i].tolist() == one[1] and bc[i] == 1
+
+
+def _assign_of(offsets, ids, N):
+    a = np.empty(N, np.int32)
+    for no in range(len(offsets) - 1):
+        a[ids[offsets[no]:offsets[no + 1]]] = no
+    return a
