@@ -115,6 +115,22 @@ int rii_copy_list_lengths(const rii_index_t *h, int32_t *out);
 /* Global list lengths and the lengths held by lower ranks (both (nlist) int32), from the all-gather. */
 int rii_set_global_lengths(rii_index_t *h, const int32_t *glob_len, const int32_t *pre_len);
 
+/* First min(N_total, 100*nlist) ids of the reference's sampling shuffle (src/rii.h:115-124; host only).
+ * Call with out_ids == NULL to get the count in *out_n. */
+int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n);
+/* Merge G per-shard results (device buffers: ids int64 (G, B, k) global ids, dists float32 (G, B, k), counts
+ * int32 (G, B)) into the global top-k per query under (distance, id).  The buffers are what an all-gather of
+ * rii_query_batch_dev outputs produces. */
+int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_dists, const int32_t *d_counts, int G,
+                         int B, int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* Per-kernel device time from CUDA events recorded around every launch on the launching stream.
+ * kernel: "dtable" | "scan_linear" | "merge" | "coarse_rank" | "count_members" | "plan" | "scan_ivf" | "assign". */
+int rii_profile_enable(rii_index_t *h, int on);
+int rii_profile_reset(rii_index_t *h);
+int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,28 @@ def serve(variant_dir):
                                else e.query_ivf(q, topk, tids, L))
                 dt = time.perf_counter() - t0
                 r = dict(seconds=dt, n=len(Q), ids=[o[0] for o in out] if a.get("return_ids") else None)
+            elif op == "time_queries_forked":
+                # throughput of `nproc` processes, each a loop of single-query calls over its slice of Q.
+                # Children are forked from this process (index pages shared copy-on-write); QueryIvf uses no
+                # OpenMP (src/rii.h:261), so forking after the OMP-parallel build is safe for this call.
+                import os
+                Q, topk, L, nproc = a["Q"], int(a["topk"]), int(a["L"]), int(a["nproc"])
+                for q in Q[:3]:
+                    e.query_ivf(q, topk, empty, L)
+                slices = np.array_split(np.arange(len(Q)), nproc)
+                pids, t0 = [], time.perf_counter()
+                for sl in slices:
+                    pid = os.fork()
+                    if pid == 0:
+                        try:
+                            for i in sl:
+                                e.query_ivf(Q[i], topk, empty, L)
+                        finally:
+                            os._exit(0)
+                    pids.append(pid)
+                for pid in pids:
+                    os.waitpid(pid, 0)
+                r = dict(seconds=time.perf_counter() - t0, n=len(Q), nproc=nproc)
             elif op == "quit":
                 _write(fout, ("ok", None))
                 return

@@ -308,6 +308,47 @@ __global__ void __launch_bounds__(RII_THREADS) k_merge(const u64 *__restrict__ p
     emit_topk(s.tk, o, b, 0, 1);
 }
 
+// Cross-shard merge: per query, the G per-shard top-k lists (global 64-bit ids, ascending
+// (dist, id) each) gathered over NVLink are merged into the global top-k.  grid (B); P = pow2 >= G*k.
+__global__ void __launch_bounds__(RII_THREADS) k_merge_shards(const long long *__restrict__ ids, const float *__restrict__ dists,
+                                                              const int *__restrict__ counts, int G, int B, int k, int P,
+                                                              long long *out_ids, float *out_dists, int *out_counts)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long *s_id = reinterpret_cast<long long *>(smem_raw);
+    uint32_t *s_d = reinterpret_cast<uint32_t *>(smem_raw + (size_t)P * 8);
+    const int b = blockIdx.x;
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += counts[(size_t)g * B + b];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int g = i / k, j = i % k;
+        bool valid = g < G && j < counts[(size_t)g * B + b];
+        s_id[i] = valid ? ids[((size_t)g * B + b) * k + j] : 0x7fffffffffffffffll;
+        s_d[i] = valid ? __float_as_uint(dists[((size_t)g * B + b) * k + j]) : 0xffffffffu;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= P; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t da = s_d[i], db = s_d[ixj];
+                    long long ia = s_id[i], ib = s_id[ixj];
+                    bool gt = da > db || (da == db && ia > ib);
+                    bool up = (i & kk) == 0;
+                    if (gt == up) { s_d[i] = db; s_d[ixj] = da; s_id[i] = ib; s_id[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    int n = total < k ? total : k;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        out_ids[(size_t)b * k + i] = s_id[i];
+        out_dists[(size_t)b * k + i] = __uint_as_float(s_d[i]);
+    }
+    if (threadIdx.x == 0) out_counts[b] = n;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K4  coarse ranking + candidate plan.  src/rii.h:259-280: ADist to every coarse center, w = number of
 // lists to consider, partial_sort of the first w.  We rank by (coarse dist, list id).  grid (B).

@@ -88,7 +88,19 @@ int host_l2_variant()
 
 }  // namespace
 
+enum { PK_DTABLE = 0, PK_SCAN_LINEAR, PK_MERGE, PK_COARSE, PK_COUNT, PK_PLAN, PK_SCAN_IVF, PK_ASSIGN, PK_N };
+static const char *PK_NAMES[PK_N] = {"dtable", "scan_linear", "merge", "coarse_rank", "count_members", "plan",
+                                      "scan_ivf", "assign"};
+struct ProfRec { int kind; cudaEvent_t a, b; };
+
 struct rii_index {
+    // optional per-kernel CUDA-event timing (rii_profile_*): events are recorded around each launch on the
+    // launching stream and only read back (after a sync) when the totals are asked for.
+    bool prof = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[PK_N] = {0};
+    long long prof_n[PK_N] = {0};
     int M = 0, Ks = 0, Ds = 0, variant = 16, verbose = 0, device = 0;
     long long N = 0, cap_rows = 0;      // local rows
     long long id_base = 0, N_total = -1;  // sharding (N_total < 0: single shard, N_total = N)
@@ -114,6 +126,40 @@ struct rii_index {
 };
 
 namespace {
+
+struct Prof {  // RAII: time one launch when profiling is on
+    rii_index *h; cudaStream_t st; ProfRec r; bool on;
+    Prof(rii_index *h_, cudaStream_t st_, int kind) : h(h_), st(st_), on(h_->prof)
+    {
+        if (!on) return;
+        r.kind = kind;
+        for (cudaEvent_t *e : {&r.a, &r.b}) {
+            if (!h->prof_pool.empty()) { *e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(r.a, st);
+    }
+    ~Prof()
+    {
+        if (!on) return;
+        cudaEventRecord(r.b, st);
+        h->prof_pending.push_back(r);
+    }
+};
+
+void prof_collect(rii_index *h)
+{
+    for (auto &r : h->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            h->prof_ms[r.kind] += ms;
+            h->prof_n[r.kind] += 1;
+        }
+        h->prof_pool.push_back(r.a);
+        h->prof_pool.push_back(r.b);
+    }
+    h->prof_pending.clear();
+}
 
 template <class F> int set_smem(F *kernel, size_t bytes)
 {
@@ -162,6 +208,7 @@ int launch_assign(rii_index *h, const uint8_t *d_codes, long long n, const uint8
     const int tile = RII_THREADS * CPT;
     const size_t smem = lut1 * G + (size_t)tile * h->M;
     const unsigned grid = (unsigned)((n + tile - 1) / tile);
+    Prof pr(h, h->stream, PK_ASSIGN);
 #define LAUNCH_ASSIGN(GG, CC)                                                                                        \
     do {                                                                                                             \
         CKR(set_smem(k_assign<GG, CC>, smem));                                                                       \
@@ -323,6 +370,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // K1
     CKR(h->T.ensure((size_t)B * lutf * 4));
     {
+        Prof pr(h, st, PK_DTABLE);
         dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
         k_dtable<<<grid, RII_THREADS, 0, st>>>(d_Q, h->d_cw, h->T.as<float>(), M, Ks, h->Ds, h->variant);
         LAUNCHED();
@@ -356,16 +404,20 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
         a.out = out;
         const size_t smem = scan_smem_bytes(lutf, cap, 0);
-        DISPATCH_M(M, {
-            CKR(set_smem(k_scan_linear<MT>, smem));
-            k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
-        });
+        {
+            Prof pr(h, st, PK_SCAN_LINEAR);
+            DISPATCH_M(M, {
+                CKR(set_smem(k_scan_linear<MT>, smem));
+                k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+            });
+        }
         LAUNCHED();
         CK(cudaGetLastError());
         if (!out.final) {
             const int mcap = next_pow2(c.topk + RII_THREADS);
             const size_t msmem = scan_smem_bytes(0, mcap, 0);
             CKR(set_smem(k_merge, msmem));
+            Prof pr(h, st, PK_MERGE);
             k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
             LAUNCHED();
             CK(cudaGetLastError());
@@ -412,6 +464,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.do_plan = subset ? 0 : 1;
         a.plan = p;
         const size_t smem = scan_smem_bytes(lutf, a.cap, 0);
+        Prof pr(h, st, PK_COARSE);
         DISPATCH_M(M, {
             CKR(set_smem(k_coarse_rank<MT>, smem));
             k_coarse_rank<MT><<<B, RII_THREADS, smem, st>>>(a);
@@ -420,11 +473,17 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         CK(cudaGetLastError());
     }
     if (subset) {
-        k_count_members<<<dim3(w_eff, B), RII_THREADS, 0, st>>>(h->offsets.as<long long>(), h->ids.as<int>(), p.ranked, w_eff,
-                                                                  h->bitmap.as<uint32_t>(), h->filt.as<int>());
+        {
+            Prof pr(h, st, PK_COUNT);
+            k_count_members<<<dim3(w_eff, B), RII_THREADS, 0, st>>>(h->offsets.as<long long>(), h->ids.as<int>(), p.ranked, w_eff,
+                                                                      h->bitmap.as<uint32_t>(), h->filt.as<int>());
+        }
         LAUNCHED();
         p.filt_cnt = h->filt.as<int>();
-        k_plan<<<(B + 127) / 128, 128, 0, st>>>(p, B);
+        {
+            Prof pr(h, st, PK_PLAN);
+            k_plan<<<(B + 127) / 128, 128, 0, st>>>(p, B);
+        }
         LAUNCHED();
         CK(cudaGetLastError());
     }
@@ -446,6 +505,8 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.w_eff = w_eff;
         a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
         a.out = out;
+        {
+        Prof pr(h, st, PK_SCAN_IVF);
         if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
             DISPATCH_M(M, {
@@ -459,12 +520,14 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 k_scan_ivf<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
             });
         }
+        }
         LAUNCHED();
         CK(cudaGetLastError());
         if (!out.final) {
             const int mcap = next_pow2(c.topk + RII_THREADS);
             const size_t msmem = scan_smem_bytes(0, mcap, 0);
             CKR(set_smem(k_merge, msmem));
+            Prof pr(h, st, PK_MERGE);
             k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
             LAUNCHED();
             CK(cudaGetLastError());
@@ -715,6 +778,63 @@ int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk,
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return query_dev(h, d_queries, B, topk, (const long long *)d_target_ids, S, L, method, (long long *)d_out_ids, d_out_dists,
                      d_out_counts, st);
+}
+
+int rii_profile_enable(rii_index_t *h, int on)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    h->prof = on != 0;
+    return 0;
+}
+int rii_profile_reset(rii_index_t *h)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    prof_collect(h);
+    for (int i = 0; i < PK_N; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    return 0;
+}
+int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches)
+{
+    if (!h || !kernel) return fail(RII_ERR_ARG, "bad arguments");
+    prof_collect(h);
+    for (int i = 0; i < PK_N; ++i)
+        if (!strcmp(kernel, PK_NAMES[i])) {
+            if (ms_total) *ms_total = h->prof_ms[i];
+            if (launches) *launches = h->prof_n[i];
+            return 0;
+        }
+    return fail(RII_ERR_ARG, std::string("unknown kernel name: ") + kernel);
+}
+
+int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
+{
+    // src/rii.h:115-124: first min(N, 100*nlist) entries of std::shuffle(iota(N), default_random_engine(123))
+    if (N_total <= 0 || nlist <= 0 || !out_n) return fail(RII_ERR_ARG, "bad arguments");
+    const long long ns = std::min<long long>(N_total, (long long)nlist * 100);
+    *out_n = ns;
+    if (!out_ids) return 0;
+    std::vector<size_t> pick((size_t)N_total);
+    std::iota(pick.begin(), pick.end(), 0);
+    std::shuffle(pick.begin(), pick.end(), std::default_random_engine(123));
+    for (long long i = 0; i < ns; ++i) out_ids[i] = (int64_t)pick[i];
+    return 0;
+}
+
+int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_dists, const int32_t *d_counts, int G, int B,
+                         int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream)
+{
+    if (!h || !d_ids || !d_dists || !d_counts || G <= 0 || B <= 0 || k <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int P = next_pow2(G * k < 2 ? 2 : G * k);
+    const size_t smem = (size_t)P * 12;
+    CKR(set_smem(k_merge_shards, smem));
+    Prof pr(h, st, PK_MERGE);
+    k_merge_shards<<<B, RII_THREADS, smem, st>>>((const long long *)d_ids, d_dists, d_counts, G, B, k, P, (long long *)d_out_ids,
+                                                 d_out_dists, d_out_counts);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int64_t rii_get_N(const rii_index_t *h) { return h ? h->N : 0; }

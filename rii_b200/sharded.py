@@ -1,0 +1,115 @@
+"""Id-range sharding of one Rii index over the GPUs of a box, one process per GPU.
+
+Rank g owns the global ids [lo_g, hi_g) of `flattened_codes` and, of every posting list, the ids that fall in
+its range (lists are ascending in id, so the concatenation over ranks is the list in stored order).
+Replicated: codebooks, coarse centers, global list lengths.  Exchanges:
+  build  : all-gather of the sampled codes (<= 100*nlist rows) and of the per-rank list lengths (nlist ints);
+  search : all-gather of the per-shard top-k (k x (int64 id, float32 dist) per query) followed by a merge
+           under (distance, id).  No other data-path collective exists: candidates are independent.
+
+The orchestration is engine-agnostic (`ShardEngine` protocol) so that the host logic runs under gloo on CPU
+in the tests with a stand-in engine; the product engine is `CudaShardEngine` (C ABI, NCCL).
+"""
+import ctypes as C
+
+import numpy as np
+
+
+def shard_bounds(n_total, world):
+    return [(g * n_total) // world for g in range(world + 1)]
+
+
+def reference_sample_ids(n_total, nlist):
+    """First min(N, 100*nlist) ids of the reference's sampling shuffle (src/rii.h:115-124) via the C ABI."""
+    from . import _capi
+    n = C.c_int64(0)
+    _capi.check(_capi.lib().rii_sample_ids(n_total, nlist, None, C.byref(n)))
+    out = np.empty(n.value, np.int64)
+    _capi.check(_capi.lib().rii_sample_ids(n_total, nlist, out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)))
+    return out
+
+
+def gather_sample(local_codes, lo, hi, sample_ids, dist=None):
+    """Assemble the PQk-means training sample (rows in shuffle order) from the shards that own the rows."""
+    mask = (sample_ids >= lo) & (sample_ids < hi)
+    pos = np.nonzero(mask)[0]
+    part = (pos, np.ascontiguousarray(local_codes[sample_ids[mask] - lo]))
+    if dist is None or dist.get_world_size() == 1:
+        parts = [part]
+    else:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, part)
+    M = local_codes.shape[1]
+    sample = np.empty((len(sample_ids), M), np.uint8)
+    for p, c in parts:
+        sample[p] = c
+    return sample
+
+
+def exchange_lengths(local_len, rank, dist=None):
+    """-> (global lengths, lengths held by lower ranks), both (nlist,) int32."""
+    if dist is None or dist.get_world_size() == 1:
+        return local_len.astype(np.int32), np.zeros_like(local_len, dtype=np.int32)
+    alls = [None] * dist.get_world_size()
+    dist.all_gather_object(alls, local_len.astype(np.int32))
+    alls = np.stack(alls)
+    return alls.sum(0).astype(np.int32), alls[:rank].sum(0).astype(np.int32)
+
+
+def build_shard_generic(engine, local_codes, lo, n_total, nlist, iter, rank, dist, sample_ids_fn=reference_sample_ids):
+    """The sharded equivalent of add_codes(all) + reconfigure(nlist, iter) (src/rii.h:108-156)."""
+    hi = lo + local_codes.shape[0]
+    engine.add_codes(local_codes)
+    engine.set_shard(lo, n_total)
+    ids = sample_ids_fn(n_total, nlist)
+    sample = gather_sample(local_codes, lo, hi, ids, dist)
+    centers = engine.fit_coarse(sample, nlist, iter)      # replicated, deterministic
+    engine.set_coarse_centers(centers)                     # assigns the local codes
+    glob, pre = exchange_lengths(engine.list_lengths(), rank, dist)
+    engine.set_global_lengths(glob, pre)
+    return centers
+
+
+class CudaShardEngine(object):
+    """`ShardEngine` over rii_b200.main.RiiCpp (one GPU)."""
+
+    def __init__(self, impl):
+        from . import _capi
+        self.e, self.lib, self.check = impl, _capi.lib(), _capi.check
+
+    def _p(self, a, t):
+        return a.ctypes.data_as(C.POINTER(t))
+
+    def add_codes(self, codes):
+        self.e.add_codes(codes, False)
+
+    def set_shard(self, lo, n_total):
+        self.check(self.lib.rii_set_shard(self.e._h, int(lo), int(n_total)))
+
+    def fit_coarse(self, sample, nlist, iter):
+        sample = np.ascontiguousarray(sample, np.uint8)
+        out = np.empty((nlist, self.e.M), np.uint8)
+        self.check(self.lib.rii_fit_coarse(self.e._h, self._p(sample, C.c_uint8), sample.shape[0], nlist, iter,
+                                           self._p(out, C.c_uint8)))
+        return out
+
+    def set_coarse_centers(self, centers):
+        centers = np.ascontiguousarray(centers, np.uint8)
+        self.check(self.lib.rii_set_coarse_centers(self.e._h, self._p(centers, C.c_uint8), centers.shape[0]))
+
+    def list_lengths(self):
+        out = np.empty(self.e.nlist, np.int32)
+        self.check(self.lib.rii_copy_list_lengths(self.e._h, self._p(out, C.c_int32)))
+        return out
+
+    def set_global_lengths(self, glob, pre):
+        glob, pre = np.ascontiguousarray(glob, np.int32), np.ascontiguousarray(pre, np.int32)
+        self.check(self.lib.rii_set_global_lengths(self.e._h, self._p(glob, C.c_int32), self._p(pre, C.c_int32)))
+
+
+def build_shard(impl, codes_all, nlist, iter, rank, world):
+    """bench.py helper: every rank holds the whole (synthetic) code matrix and keeps its id range."""
+    import torch.distributed as dist
+    b = shard_bounds(codes_all.shape[0], world)
+    return build_shard_generic(CudaShardEngine(impl), np.ascontiguousarray(codes_all[b[rank]:b[rank + 1]]), b[rank],
+                               codes_all.shape[0], nlist, iter, rank, dist if world > 1 else None)
