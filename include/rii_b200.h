@@ -124,6 +124,10 @@ int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
 int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_dists, const int32_t *d_counts, int G,
                          int B, int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream);
 
+/* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout scan, 2 = skewed bank-conflict-free scan
+ * (M == 32, no target_ids, topk <= 224).  Results are identical for every setting. */
+int rii_set_option(rii_index_t *h, const char *name, int64_t value);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* Per-kernel device time from CUDA events recorded around every launch on the launching stream.
  * kernel: "dtable" | "scan_linear" | "merge" | "coarse_rank" | "count_members" | "plan" | "scan_ivf" | "assign". */

@@ -798,3 +798,220 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x)
         out[(size_t)b * N + n] = adc_row<M_T, true>(lut, Ks, M, codes + n * M);
 }
+
+// ===================================================================================================
+// K2 v2: bank-conflict-free linear scan for M = 32 ("skewed" schedule).
+//
+// Why: with the natural layout lut[m][ks] every lane of a warp looks up the same m at the same time, the
+// bank is ks % 32 -- random -- and a warp-wide LDS costs ~3.5 crossbar cycles: the scan is bound by the
+// shared-memory crossbar at ~9 lookups/clk/SM, far below what HBM can feed.  Here lane l runs l bytes
+// behind lane 0 through its own stream of code rows, so at any instant the 32 lanes work on 32 different
+// sub-spaces m = (t - l) mod 32, and with the table stored transposed, lut2[ks][m], the bank is m: every
+// LDS is conflict free.  Each lane still adds its candidate's 32 table entries in m = 0..31 order, so the
+// distances stay bit-identical to the reference's sequential sum (src/rii.h:386-394).
+//
+// Mechanics (per warp, no CTA barrier in the main loop):
+//  * lut2 is [256][64] floats: column c holds sub-space c % 32, so the lane's column t + 32 - l never wraps
+//    and the lookup address is ONE byte-permute: (ks << 8) | ((32 - l) * 4), plus the immediate 4 * t.
+//  * code rows are staged global -> shared with cp.async (16 B, coalesced 512 B per warp instruction) into
+//    per-lane regions [carry row | tile A: 8 rows | tile B: 8 rows] (stride 136 words = 8 mod 32, which
+//    makes the lanes' 4-byte code-word reads conflict free as well).  A lane's region is its byte stream;
+//    reading it at word (q - l/4) and funnel-shifting by l % 4 bytes yields the l-byte lag for free.
+//  * a lane finishes one candidate per 32 steps at its own phase: steps t < l still belong to the previous
+//    row (accumulator A), steps t >= l to the new one (B); at the block end A is complete in every lane.
+//  * top-k per warp (ballot-compacted pushes into a small shared buffer, warp-level bitonic compaction),
+//    with a CTA-shared threshold tightened by atomicMin; the CTA merges its warps' lists at the end.
+// ===================================================================================================
+#define SK_WARPS 8
+#define SK_J 8                                   // rows per lane per tile
+#define SK_TILE_ROWS (32 * SK_J)                 // 256 rows = 8 KB of codes
+#define SK_REGION_WORDS (8 + 2 * SK_J * 8)       // 136
+#define SK_REGION_BYTES (SK_REGION_WORDS * 4)    // 544
+#define SK_WARP_BYTES (32 * SK_REGION_BYTES)     // 17408
+#define SK_LUT_BYTES 65536
+#define SK_MAX_K 224
+
+struct WarpTopk {
+    u64 *keys;   // shared, this warp's buffer (cap keys)
+    int cap, k;
+    int count;   // warp-uniform register copy
+};
+
+__device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
+{
+    __syncwarp();
+    int n = w.count;
+    int P = next_pow2(n < 2 ? 2 : n);
+    for (int i = n + lane; i < P; i += 32) w.keys[i] = RII_KEY_MAX;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    u64 a = w.keys[i], b = w.keys[ixj];
+                    bool up = (i & kk) == 0;
+                    if ((a > b) == up) { w.keys[i] = b; w.keys[ixj] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    w.count = n < w.k ? n : w.k;
+    if (w.count == w.k && lane == 0) atomicMin(cta_thr, w.keys[w.k - 1]);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_emit(WarpTopk &w, u64 *cta_thr, int lane, float dist, long long row, bool valid)
+{
+    const u64 thr = *reinterpret_cast<volatile u64 *>(cta_thr);
+    bool pass = false;
+    u64 key = 0;
+    if (valid && __float_as_uint(dist) <= (uint32_t)(thr >> 32)) {
+        key = pack_key(dist, (uint32_t)row);
+        pass = key < thr;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (bal) {
+        if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
+        w.count += __popc(bal);
+        if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
+    }
+}
+
+// one lookup step: addr = (code byte << 8) | lane column offset; v = lut2[addr + 4 t]; (t < l ? A : B) += v
+#define SK_STEP(W, BYTE, T)                                                                                   \
+    {                                                                                                         \
+        uint32_t ad_ = __byte_perm(W, colreg, 0x7504 | ((BYTE) << 4));                                        \
+        float v_ = *reinterpret_cast<const float *>(smem_raw + ad_ + 4 * (T));                                \
+        asm("{.reg .pred p; setp.gt.s32 p, %2, %3; @p add.rn.f32 %0, %0, %4; @!p add.rn.f32 %1, %1, %4;}"   \
+            : "+f"(accA), "+f"(accB)                                                                          \
+            : "r"(lane), "r"(T), "f"(v_));                                                                    \
+    }
+
+// one block = 32 steps = 8 code words of the lane's (lagged) stream, starting at region word offset WOFF
+#define SK_BLOCK(WOFF)                                                                                        \
+    {                                                                                                         \
+        _Pragma("unroll") for (int q_ = 0; q_ < 8; ++q_)                                                      \
+        {                                                                                                     \
+            uint32_t x_ = *reinterpret_cast<const uint32_t *>(smem_raw + (WOFF) + 4 * q_);                    \
+            uint32_t wd_ = __funnelshift_rc(xprev, x_, shift);                                                \
+            xprev = x_;                                                                                       \
+            SK_STEP(wd_, 0, 4 * q_ + 0)                                                                       \
+            SK_STEP(wd_, 1, 4 * q_ + 1)                                                                       \
+            SK_STEP(wd_, 2, 4 * q_ + 2)                                                                       \
+            SK_STEP(wd_, 3, 4 * q_ + 3)                                                                       \
+        }                                                                                                     \
+    }
+
+__global__ void __launch_bounds__(SK_WARPS * 32, 1) k_scan_linear_skew32(LinearArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [lut2 64 KB][SK_WARPS regions][SK_WARPS key buffers][cta_thr]
+    float *lut2 = reinterpret_cast<float *>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int capw = a.cap;  // per-warp key capacity (power of two >= k + 32)
+    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES) + (size_t)wid * capw;
+    u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES) + (size_t)SK_WARPS * capw;
+    const int b = blockIdx.y;
+    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (stray bytes of padded rows may index them)
+        const float *T = a.T + (size_t)b * 32 * a.Ks;
+        for (int e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
+            int ks = e >> 6, c = e & 63;
+            lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+        }
+        if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+    }
+    // this warp's rows
+    const long long rows_per_cta = ((a.N + gridDim.x - 1) / gridDim.x + SK_WARPS * SK_TILE_ROWS - 1) /
+                                   (SK_WARPS * SK_TILE_ROWS) * (SK_WARPS * SK_TILE_ROWS);
+    const long long w0 = (long long)blockIdx.x * rows_per_cta + (long long)wid * (rows_per_cta / SK_WARPS);
+    long long w1 = w0 + rows_per_cta / SK_WARPS;
+    if (w1 > a.N) w1 = a.N;
+    const int ntiles = w1 > w0 ? (int)((w1 - w0 + SK_TILE_ROWS - 1) / SK_TILE_ROWS) : 0;
+
+    const uint32_t region = SK_LUT_BYTES + wid * SK_WARP_BYTES;           // byte offset of this warp's regions
+    const uint32_t rb = region + lane * SK_REGION_BYTES + 4 * (8 - (lane >> 2));  // lane stream base (word lag folded in)
+    const uint32_t shift = 8 * (4 - (lane & 3));                           // funnel shift (32 == no byte lag)
+    const uint32_t colreg = (uint32_t)((32 - lane) * 4);                   // column byte offset, upper bytes zero
+    // cp.async destination of chunk (it, lane): rows are dealt 8 per lane, 16-byte chunks
+    const uint32_t cp_dst = region + (lane >> 4) * SK_REGION_BYTES + 32 + (lane & 15) * 16;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    auto issue_tile = [&](int n) {
+        const long long r0 = w0 + (long long)n * SK_TILE_ROWS;
+        const uint8_t *src = a.codes + r0 * 32;
+        const uint32_t half = (n & 1) ? SK_J * 32 : 0;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const long long row = r0 + it * 16 + (lane >> 1);
+            const int nbytes = row < w1 ? 16 : 0;  // rows past the end are zero filled, results masked
+            const uint32_t dst = smem_base + cp_dst + half + it * 2 * SK_REGION_BYTES;
+            const uint8_t *g = src + (size_t)(it * 32 + lane) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(nbytes ? g : a.codes), "r"(nbytes));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    WarpTopk wt;
+    wt.keys = wkeys;
+    wt.cap = capw;
+    wt.k = a.k;
+    wt.count = 0;
+    // zero the carry row of this lane (read by the lagging steps of the very first block)
+    *reinterpret_cast<uint4 *>(smem_raw + region + lane * SK_REGION_BYTES) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(smem_raw + region + lane * SK_REGION_BYTES + 16) = make_uint4(0, 0, 0, 0);
+    if (ntiles > 0) issue_tile(0);
+    __syncthreads();  // lut2 + cta_thr ready
+
+    float accA = 0.f, accB = 0.f;
+    uint32_t xprev = 0;
+    // One copy of the 32-step block body; g walks the blocks of all tiles, the last iteration is the drain
+    // block (32 more steps that complete the last row of every lane).
+    const int nblocks = ntiles > 0 ? SK_J * ntiles + 1 : 0;
+#pragma unroll 1
+    for (int g = 0; g < nblocks; ++g) {
+        int n = g / SK_J, i = g % SK_J;
+        if (g == SK_J * ntiles) { n = ntiles - 1; i = SK_J; }
+        if (i == 0) {
+            if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
+                unsigned char *reg = smem_raw + region + lane * SK_REGION_BYTES;
+                uint4 c0 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32);
+                uint4 c1 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32 + 16);
+                *reinterpret_cast<uint4 *>(reg) = c0;
+                *reinterpret_cast<uint4 *>(reg + 16) = c1;
+            }
+            asm volatile("cp.async.wait_group 0;");
+            __syncwarp();
+        }
+        const uint32_t rbw = rb + 4 * ((n & 1) * SK_J * 8 + 8 * i);
+        SK_BLOCK(rbw)
+        // the candidate that *started* in the previous block is complete in every lane now
+        const long long row = w0 + (long long)n * SK_TILE_ROWS + 8 * lane + i - 1 - (i == 0 ? SK_TILE_ROWS - SK_J : 0);
+        warp_emit(wt, cta_thr, lane, accA, row, g > 0 && row < w1);
+        accA = accB;
+        accB = 0.f;
+        if (i == 0 && n + 1 < ntiles) {  // the other half's last reader finished with this block
+            __syncwarp();
+            issue_tile(n + 1);
+        }
+    }
+    warp_compact(wt, cta_thr, lane);
+    __syncthreads();
+    // CTA merge of the warp lists through the block-level selector (reusing the lut2 area)
+    {
+        __shared__ int s_cnt[SK_WARPS];
+        if (lane == 0) s_cnt[wid] = wt.count;
+        BlockTopk tk;
+        const int mcap = next_pow2(SK_WARPS * a.k + 1);
+        tk.keys = reinterpret_cast<u64 *>(smem_raw);
+        tk.count = reinterpret_cast<int *>(smem_raw + (size_t)mcap * 8 + 8);
+        tk.thr = reinterpret_cast<u64 *>(smem_raw + (size_t)mcap * 8);
+        tk.cap = mcap;
+        tk.k = a.k;
+        tk.init();
+        const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES);
+        for (int w2 = 0; w2 < SK_WARPS; ++w2)
+            for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
+        emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
+    }
+}

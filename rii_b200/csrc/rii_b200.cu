@@ -122,6 +122,8 @@ struct rii_index {
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
         tmp2, tmp3;
 
+    int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernel, 2 skewed conflict-free kernel (M == 32 only)
+
     long long n_total() const { return N_total >= 0 ? N_total : N; }
 };
 
@@ -404,7 +406,26 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
         a.out = out;
         const size_t smem = scan_smem_bytes(lutf, cap, 0);
-        {
+        // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
+        const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K;
+        const bool use_v2 = v2_ok && (h->opt_scan_kernel == 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
+        if (h->opt_scan_kernel == 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2 needs M == 32, no target_ids and topk <= 224");
+        if (use_v2) {
+            const int capw = std::max(64, next_pow2(c.topk + 32));
+            parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
+                                             std::max<long long>(1, h->N / (SK_WARPS * SK_TILE_ROWS * 4)));
+            out.final = parts == 1;
+            if (!out.final) {
+                CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
+                out.partial = h->partial.as<u64>();
+            }
+            a.out = out;
+            a.cap = capw;
+            const size_t smem2 = (size_t)SK_LUT_BYTES + (size_t)SK_WARPS * SK_WARP_BYTES + (size_t)SK_WARPS * capw * 8 + 16;
+            CKR(set_smem(k_scan_linear_skew32, smem2));
+            Prof pr(h, st, PK_SCAN_LINEAR);
+            k_scan_linear_skew32<<<dim3(parts, B), SK_WARPS * 32, smem2, st>>>(a);
+        } else {
             Prof pr(h, st, PK_SCAN_LINEAR);
             DISPATCH_M(M, {
                 CKR(set_smem(k_scan_linear<MT>, smem));
@@ -778,6 +799,17 @@ int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk,
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return query_dev(h, d_queries, B, topk, (const long long *)d_target_ids, S, L, method, (long long *)d_out_ids, d_out_dists,
                      d_out_counts, st);
+}
+
+int rii_set_option(rii_index_t *h, const char *name, int64_t value)
+{
+    if (!h || !name) return fail(RII_ERR_ARG, "bad arguments");
+    if (!strcmp(name, "scan_kernel")) {
+        if (value < 0 || value > 2) return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 or 2");
+        h->opt_scan_kernel = (int)value;
+        return 0;
+    }
+    return fail(RII_ERR_ARG, std::string("unknown option: ") + name);
 }
 
 int rii_profile_enable(rii_index_t *h, int on)

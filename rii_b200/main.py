@@ -176,6 +176,9 @@ class RiiCpp(object):
         check(_capi.lib().rii_set_state(self._h, _ptr(centers, C.c_uint8), centers.shape[0], _ptr(codes, C.c_uint8),
                                         codes.shape[0], _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
 
+    def set_option(self, name, value):
+        check(_capi.lib().rii_set_option(self._h, name.encode(), int(value)))
+
     # ---- building blocks (parity tests) -------------------------------------------------------
     def dtable(self, queries):
         Q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.M * self.Ds)

@@ -113,3 +113,52 @@ def build_shard(impl, codes_all, nlist, iter, rank, world):
     b = shard_bounds(codes_all.shape[0], world)
     return build_shard_generic(CudaShardEngine(impl), np.ascontiguousarray(codes_all[b[rank]:b[rank + 1]]), b[rank],
                                codes_all.shape[0], nlist, iter, rank, dist if world > 1 else None)
+
+
+def sharded_query(engine, Q, topk, L, method, dist, world):
+    """One batch on every shard, all-gather of the per-shard top-k, merge under (distance, id).
+    `engine.query_local` returns torch tensors (ids int64 (B,k) global ids, dists float32 (B,k), counts int32 (B))
+    on the engine's device; `engine.merge` takes the gathered (G,B,k)/(G,B) tensors."""
+    import torch
+    ids, d, c = engine.query_local(Q, topk, L, method)
+    if world == 1:
+        return ids, d, c
+    B, k = ids.shape
+    g_ids = torch.empty((world, B, k), dtype=ids.dtype, device=ids.device)
+    g_d = torch.empty((world, B, k), dtype=d.dtype, device=d.device)
+    g_c = torch.empty((world, B), dtype=c.dtype, device=c.device)
+    dist.all_gather_into_tensor(g_ids.view(-1), ids.contiguous().view(-1))
+    dist.all_gather_into_tensor(g_d.view(-1), d.contiguous().view(-1))
+    dist.all_gather_into_tensor(g_c.view(-1), c.contiguous().view(-1))
+    return engine.merge(g_ids, g_d, g_c)
+
+
+def _cuda_query_local(self, Q, topk, L, method):
+    import torch
+    B = Q.shape[0]
+    dev = Q.device
+    ids = torch.empty((B, topk), dtype=torch.int64, device=dev)
+    d = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    c = torch.empty((B,), dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    self.check(self.lib.rii_query_batch_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, None, 0, int(L),
+                                            {"linear": 0, "ivf": 1}[method], C.c_void_p(ids.data_ptr()),
+                                            C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()), st))
+    return ids, d, c
+
+
+def _cuda_merge(self, g_ids, g_d, g_c):
+    import torch
+    G, B, k = g_ids.shape
+    ids = torch.empty((B, k), dtype=torch.int64, device=g_ids.device)
+    d = torch.empty((B, k), dtype=torch.float32, device=g_ids.device)
+    c = torch.empty((B,), dtype=torch.int32, device=g_ids.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    self.check(self.lib.rii_merge_shards_dev(self.e._h, C.c_void_p(g_ids.data_ptr()), C.c_void_p(g_d.data_ptr()),
+                                             C.c_void_p(g_c.data_ptr()), G, B, k, C.c_void_p(ids.data_ptr()),
+                                             C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()), st))
+    return ids, d, c
+
+
+CudaShardEngine.query_local = _cuda_query_local
+CudaShardEngine.merge = _cuda_merge

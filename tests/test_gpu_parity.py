@@ -312,3 +312,59 @@ def _assign_of(offsets, ids, N):
     for no in range(len(offsets) - 1):
         a[ids[offsets[no]:offsets[no + 1]]] = no
     return a
+
+
+# ---------------------------------------------------------------- scan kernel v2 (skewed) --------------
+@pytest.mark.parametrize("N", [1, 255, 2049, 20000, 70001])
+def test_skew_kernel_matches_oracle(N):
+    """The bank-conflict-free schedule (k_scan_linear_skew32) must return exactly what the natural-layout
+    kernel and the oracle return: every tail / tile-boundary case."""
+    D, M, Ks = 128, 32, 256
+    cw, codes, Q = synth(D, M, Ks, N, 3, seed=N)
+    e = engine(cw, codes)
+    e.set_option("scan_kernel", 2)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 10, 224):
+            if topk > N:
+                continue
+            ids, d = e.query_linear(q, topk, EMPTY)
+            assert_same_result(ids, np.array(d, np.float32), *O.query_linear(T, codes, topk), "skew N=%d k=%d" % (N, topk))
+    if N >= 10:
+        bi, bd, bc = e.query_batch(np.ascontiguousarray(Q), 10, method="linear")
+        for b, q in enumerate(Q):
+            exp = O.query_linear(O.dtable(q, cw, 16), codes, 10)
+            assert_same_result(bi[b], bd[b], exp[0], exp[1], "skew batch")
+    with pytest.raises(Exception):
+        e.query_linear(Q[0], 1, np.arange(1, dtype=np.int64))  # v2 has no target_ids path when forced
+
+
+def test_skew_kernel_small_ks_and_ties():
+    """Ks < 256 (table rows beyond Ks are never indexed by real codes) and massive exact ties."""
+    cw, codes, Q = synth(128, 32, 16, 50000, 2, seed=3)
+    codes[:, 8:] = 0  # only 16^8 distinct codes -> many exact distance ties; (dist, id) order decides
+    e1, e2 = engine(cw, codes), engine(cw, codes)
+    e1.set_option("scan_kernel", 1)
+    e2.set_option("scan_kernel", 2)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 50, 200):
+            r1, r2 = e1.query_linear(q, topk, EMPTY), e2.query_linear(q, topk, EMPTY)
+            assert r1 == r2
+            assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(T, codes, topk), "ties")
+
+
+def test_skew_kernel_large_n_vs_v1():
+    N = 5000000
+    cw, codes, Q = synth(128, 32, 256, N, 3, seed=77)
+    e = engine(cw, codes)
+    for q in Q:
+        e.set_option("scan_kernel", 1)
+        r1 = e.query_linear(q, 100, EMPTY)
+        e.set_option("scan_kernel", 0)  # auto -> v2 at this size
+        r0 = e.query_linear(q, 100, EMPTY)
+        e.set_option("scan_kernel", 2)
+        r2 = e.query_linear(q, 100, EMPTY)
+        assert r1 == r2 == r0
+    T = O.dtable(Q[0], cw, 16)
+    assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(O.dtable(Q[2], cw, 16), codes, 100), "5M")

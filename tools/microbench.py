@@ -27,6 +27,7 @@ def main_():
     ap.add_argument("--m", type=int, default=32)
     ap.add_argument("--what", default="linear,assign")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--scan-kernel", type=int, default=0)
     a = ap.parse_args()
     lib = _capi.lib()
     dev = torch.device("cuda", 0)
@@ -41,9 +42,11 @@ def main_():
     for s in range(0, N, chunk):
         n = min(chunk, N - s)
         e.add_codes(torch.randint(0, 256, (n, M), dtype=torch.uint8).numpy(), False)
-    st = torch.cuda.current_stream()
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(st)
     sp = C.c_void_p(st.cuda_stream)
     lib.rii_profile_enable(e._h, 1)
+    e.set_option("scan_kernel", a.scan_kernel)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if "linear" in a.what:
         for B, k in [(1, 1), (1, 10), (1, 100), (4, 10), (16, 10)]:
@@ -71,7 +74,7 @@ def main_():
             ms, n = prof(lib, e, "scan_linear")
             per = ms / n
             gbs = B * N * M / (per * 1e-3) / 1e9
-            print(json.dumps({"what": "linear", "N": N, "M": M, "B": B, "topk": k, "scan_ms": round(per, 4),
+            print(json.dumps({"what": "linear", "scan_kernel": a.scan_kernel, "N": N, "M": M, "B": B, "topk": k, "scan_ms": round(per, 4),
                               "query_ms": round(t_tot / a.reps, 4), "code_GBps": round(gbs, 1),
                               "frac_hbm_per_query_bytes": round(N * M / (per / B * 1e-3) / 1e9 / peak, 4),
                               "lookups_per_s_T": round(B * N * M / (per * 1e-3) / 1e12, 3)}))
