@@ -800,41 +800,58 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 }
 
 // ===================================================================================================
-// K2 v2: bank-conflict-free linear scan for M = 32 ("skewed" schedule).
+// K2/K5 v2: bank-conflict-free scan for M = 32 ("skewed" schedule), linear and posting-list (IVF) flavours.
 //
 // Why: with the natural layout lut[m][ks] every lane of a warp looks up the same m at the same time, the
-// bank is ks % 32 -- random -- and a warp-wide LDS costs ~3.5 crossbar cycles: the scan is bound by the
-// shared-memory crossbar at ~9 lookups/clk/SM, far below what HBM can feed.  Here lane l runs l bytes
-// behind lane 0 through its own stream of code rows, so at any instant the 32 lanes work on 32 different
-// sub-spaces m = (t - l) mod 32, and with the table stored transposed, lut2[ks][m], the bank is m: every
-// LDS is conflict free.  Each lane still adds its candidate's 32 table entries in m = 0..31 order, so the
-// distances stay bit-identical to the reference's sequential sum (src/rii.h:386-394).
+// bank is ks % 32 -- random -- and a warp-wide LDS costs ~2.6-3.5 crossbar cycles (ncu: profiles/r01_*):
+// the scan is bound by the shared-memory crossbar at ~2.1-2.4 T lookups/s, a third of what HBM can feed.
+// Here lane l runs l bytes behind lane 0 through its own stream of code rows, so at any instant the 32
+// lanes work on 32 different sub-spaces m = (t - l) mod 32, and with the table stored transposed,
+// lut2[ks][m], the bank is m: every LDS is conflict free.  Each lane still adds its candidate's 32 table
+// entries in m = 0..31 order, so distances stay bit-identical to the reference's sequential sum
+// (src/rii.h:386-394).
 //
-// Mechanics (per warp, no CTA barrier in the main loop):
+// Mechanics (per warp; no CTA barrier in the main loop):
 //  * lut2 is [256][64] floats: column c holds sub-space c % 32, so the lane's column t + 32 - l never wraps
 //    and the lookup address is ONE byte-permute: (ks << 8) | ((32 - l) * 4), plus the immediate 4 * t.
-//  * code rows are staged global -> shared with cp.async (16 B, coalesced 512 B per warp instruction) into
-//    per-lane regions [carry row | tile A: 8 rows | tile B: 8 rows] (stride 136 words = 8 mod 32, which
-//    makes the lanes' 4-byte code-word reads conflict free as well).  A lane's region is its byte stream;
-//    reading it at word (q - l/4) and funnel-shifting by l % 4 bytes yields the l-byte lag for free.
+//  * code rows are staged global -> shared with cp.async into per-lane regions
+//    [carry row | half A: 4 rows | half B: 4 rows] (stride 72 words = 8 mod 32, which makes the lanes' 4-byte
+//    code-word reads conflict free as well).  A lane's region is its byte stream; reading it at word
+//    (q - l/4) and funnel-shifting by l % 4 bytes yields the l-byte lag for free.  Linear: 16-byte chunks
+//    dealt round-robin (512 contiguous bytes per warp instruction).  IVF: every lane gathers its own rows
+//    (ids fetched one tile ahead with 4-byte cp.async into a small id ring).
 //  * a lane finishes one candidate per 32 steps at its own phase: steps t < l still belong to the previous
 //    row (accumulator A), steps t >= l to the new one (B); at the block end A is complete in every lane.
 //  * top-k per warp (ballot-compacted pushes into a small shared buffer, warp-level bitonic compaction),
 //    with a CTA-shared threshold tightened by atomicMin; the CTA merges its warps' lists at the end.
 // ===================================================================================================
-#define SK_WARPS 8
-#define SK_J 8                                   // rows per lane per tile
-#define SK_TILE_ROWS (32 * SK_J)                 // 256 rows = 8 KB of codes
-#define SK_REGION_WORDS (8 + 2 * SK_J * 8)       // 136
-#define SK_REGION_BYTES (SK_REGION_WORDS * 4)    // 544
-#define SK_WARP_BYTES (32 * SK_REGION_BYTES)     // 17408
+#define SK_J 4                                   // rows per lane per tile
+#define SK_TILE_ROWS (32 * SK_J)                 // 128 rows = 4 KB of codes
+#define SK_HALF_WORDS (SK_J * 8)                 // 32
+#define SK_REGION_WORDS (8 + 2 * SK_HALF_WORDS)  // 72
+#define SK_REGION_BYTES (SK_REGION_WORDS * 4)    // 288
+#define SK_WARP_BYTES (32 * SK_REGION_BYTES)     // 9216
 #define SK_LUT_BYTES 65536
+#define SK_ID_STRIDE (2 * SK_J + 1)              // id ring words per lane (IVF): 2 tiles + 1 pad
+#define SK_ID_BYTES (32 * SK_ID_STRIDE * 4)      // 1152
 #define SK_MAX_K 224
+
+struct SkewArgs {
+    const float *T;            // (B, 32*Ks)
+    const uint8_t *codes;      // (N, 32)
+    long long N;               // linear: rows of the shard
+    const long long *offsets;  // IVF: CSR
+    const int *ids;
+    const int *ranked, *cum, *J, *flags;  // IVF plan
+    int w_eff;
+    int Ks, k, cap;            // cap = per-warp key capacity (power of two >= k + 32)
+    TopkOut out;
+};
 
 struct WarpTopk {
     u64 *keys;   // shared, this warp's buffer (cap keys)
     int cap, k;
-    int count;   // warp-uniform register copy
+    int count;   // warp-uniform
 };
 
 __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
@@ -861,21 +878,12 @@ __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
     __syncwarp();
 }
 
-__device__ __forceinline__ void warp_emit(WarpTopk &w, u64 *cta_thr, int lane, float dist, long long row, bool valid)
+// slow path of an emission: some lane passed the threshold
+__device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, u64 key, bool pass, unsigned bal)
 {
-    const u64 thr = *reinterpret_cast<volatile u64 *>(cta_thr);
-    bool pass = false;
-    u64 key = 0;
-    if (valid && __float_as_uint(dist) <= (uint32_t)(thr >> 32)) {
-        key = pack_key(dist, (uint32_t)row);
-        pass = key < thr;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (bal) {
-        if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
-        w.count += __popc(bal);
-        if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
-    }
+    if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
+    w.count += __popc(bal);
+    if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
 }
 
 // one lookup step: addr = (code byte << 8) | lane column offset; v = lut2[addr + 4 t]; (t < l ? A : B) += v
@@ -888,7 +896,7 @@ __device__ __forceinline__ void warp_emit(WarpTopk &w, u64 *cta_thr, int lane, f
             : "r"(lane), "r"(T), "f"(v_));                                                                    \
     }
 
-// one block = 32 steps = 8 code words of the lane's (lagged) stream, starting at region word offset WOFF
+// one block = 32 steps = 8 code words of the lane's (lagged) stream, starting at byte offset WOFF
 #define SK_BLOCK(WOFF)                                                                                        \
     {                                                                                                         \
         _Pragma("unroll") for (int q_ = 0; q_ < 8; ++q_)                                                      \
@@ -903,51 +911,125 @@ __device__ __forceinline__ void warp_emit(WarpTopk &w, u64 *cta_thr, int lane, f
         }                                                                                                     \
     }
 
-__global__ void __launch_bounds__(SK_WARPS * 32, 1) k_scan_linear_skew32(LinearArgs a)
+// end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
+#define SK_EMIT(ID)                                                                                           \
+    {                                                                                                         \
+        bool pass_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                                 \
+        u64 key_ = 0;                                                                                         \
+        if (pass_) {                                                                                          \
+            key_ = pack_key(accA, (uint32_t)(ID));                                                            \
+            pass_ = key_ < thr;                                                                               \
+        }                                                                                                     \
+        const unsigned bal_ = __ballot_sync(0xffffffffu, pass_);                                              \
+        if (bal_) {                                                                                           \
+            warp_push(wt, cta_thr, lane, key_, pass_, bal_);                                                  \
+            thr = *reinterpret_cast<volatile u64 *>(cta_thr);                                                 \
+            thr_hi = (uint32_t)(thr >> 32);                                                                   \
+        }                                                                                                     \
+        accA = accB;                                                                                          \
+        accB = 0.f;                                                                                           \
+    }
+
+template <int NW, bool IVF>
+__global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [lut2 64 KB][SK_WARPS regions][SK_WARPS key buffers][cta_thr]
+    // layout: [lut2 64 KB][NW regions][NW id rings (IVF)][NW key buffers][cta_thr][s_off, s_cum (IVF)]
     float *lut2 = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int capw = a.cap;  // per-warp key capacity (power of two >= k + 32)
-    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES) + (size_t)wid * capw;
-    u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES) + (size_t)SK_WARPS * capw;
+    const int capw = a.cap;
+    const uint32_t ring_off = SK_LUT_BYTES + NW * SK_WARP_BYTES;
+    const uint32_t keys_off = ring_off + (IVF ? NW * SK_ID_BYTES : 0);
+    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
+    u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
+    long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8);
+    int *s_cum = reinterpret_cast<int *>(s_off + (IVF ? a.w_eff : 0));
     const int b = blockIdx.y;
-    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (stray bytes of padded rows may index them)
+    int J = 0;
+    if constexpr (IVF) J = (a.flags[b] != 0) ? 0 : a.J[b];
+    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
         const float *T = a.T + (size_t)b * 32 * a.Ks;
         for (int e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
             int ks = e >> 6, c = e & 63;
             lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
         }
+        if constexpr (IVF)
+            for (int j = threadIdx.x; j < J; j += blockDim.x) {
+                s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
+                s_off[j] = a.offsets[a.ranked[(size_t)b * a.w_eff + j]];
+            }
         if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
     }
-    // this warp's rows
-    const long long rows_per_cta = ((a.N + gridDim.x - 1) / gridDim.x + SK_WARPS * SK_TILE_ROWS - 1) /
-                                   (SK_WARPS * SK_TILE_ROWS) * (SK_WARPS * SK_TILE_ROWS);
-    const long long w0 = (long long)blockIdx.x * rows_per_cta + (long long)wid * (rows_per_cta / SK_WARPS);
-    long long w1 = w0 + rows_per_cta / SK_WARPS;
-    if (w1 > a.N) w1 = a.N;
-    const int ntiles = w1 > w0 ? (int)((w1 - w0 + SK_TILE_ROWS - 1) / SK_TILE_ROWS) : 0;
+    __syncthreads();
+    // this warp's slice of the candidate space: [base, base + cnt)
+    const long long total = IVF ? (J ? (long long)s_cum[J - 1] : 0) : a.N;
+    const long long per_cta = ((total + gridDim.x - 1) / gridDim.x + NW * SK_TILE_ROWS - 1) / (NW * SK_TILE_ROWS) *
+                              (NW * SK_TILE_ROWS);
+    const long long base = (long long)blockIdx.x * per_cta + (long long)wid * (per_cta / NW);
+    long long end = base + per_cta / NW;
+    if (end > total) end = total;
+    const int cnt = end > base ? (int)(end - base) : 0;
+    const int ntiles = (cnt + SK_TILE_ROWS - 1) / SK_TILE_ROWS;
 
-    const uint32_t region = SK_LUT_BYTES + wid * SK_WARP_BYTES;           // byte offset of this warp's regions
-    const uint32_t rb = region + lane * SK_REGION_BYTES + 4 * (8 - (lane >> 2));  // lane stream base (word lag folded in)
-    const uint32_t shift = 8 * (4 - (lane & 3));                           // funnel shift (32 == no byte lag)
-    const uint32_t colreg = (uint32_t)((32 - lane) * 4);                   // column byte offset, upper bytes zero
-    // cp.async destination of chunk (it, lane): rows are dealt 8 per lane, 16-byte chunks
-    const uint32_t cp_dst = region + (lane >> 4) * SK_REGION_BYTES + 32 + (lane & 15) * 16;
+    const uint32_t region = SK_LUT_BYTES + wid * SK_WARP_BYTES;
+    const uint32_t myreg = region + lane * SK_REGION_BYTES;
+    const uint32_t rb = myreg + 4 * (8 - (lane >> 2));  // lane stream base with the word part of the lag folded in
+    const uint32_t shift = 8 * (4 - (lane & 3));         // funnel shift (32 == no byte lag)
+    const uint32_t colreg = (uint32_t)((32 - lane) * 4); // column byte offset, upper bytes zero
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t myring = ring_off + wid * SK_ID_BYTES + lane * SK_ID_STRIDE * 4;
+    // linear: destination of 16-byte chunk (it, lane): rows are dealt SK_J per lane
+    const uint32_t cp_dst = region + (lane >> 3) * SK_REGION_BYTES + 32 + (lane & 7) * 16;
 
-    auto issue_tile = [&](int n) {
-        const long long r0 = w0 + (long long)n * SK_TILE_ROWS;
-        const uint8_t *src = a.codes + r0 * 32;
+    auto issue_tile = [&](int n) {  // linear
+        const long long r0 = base + (long long)n * SK_TILE_ROWS;
+        const uint8_t *g = a.codes + r0 * 32 + lane * 16;
+        const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
+        if (r0 + SK_TILE_ROWS <= end) {  // full tile: 8 x 512 contiguous bytes per warp, immediates only
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
+        } else {                          // last tile: rows past the end are zero filled, their results masked
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
+                const int nbytes = r0 + it * 16 + (lane >> 1) < end ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
+                             "l"(nbytes ? g + it * 512 : a.codes), "r"(nbytes));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    auto issue_ids = [&](int n) {  // IVF: posting-list ids of this lane's SK_J candidates of tile n
+        int c = (int)base + n * SK_TILE_ROWS + SK_J * lane;
+        const int cend = (int)end;
+        int seg = 0;
+        if (c < cend) {
+            int lo = 0, hi = J - 1;  // first segment with cum > c
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (s_cum[mid] > c) hi = mid; else lo = mid + 1;
+            }
+            seg = lo;
+        }
+#pragma unroll
+        for (int j = 0; j < SK_J; ++j, ++c) {
+            const bool ok = c < cend;
+            if (ok) while (s_cum[seg] <= c) ++seg;
+            const int *src = ok ? a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0)) : a.ids;
+            const uint32_t dst = smem_base + myring + ((n & 1) * SK_J + j) * 4;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    auto issue_rows = [&](int n) {  // IVF: gather this lane's rows into its own region
         const uint32_t half = (n & 1) ? SK_J * 32 : 0;
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const long long row = r0 + it * 16 + (lane >> 1);
-            const int nbytes = row < w1 ? 16 : 0;  // rows past the end are zero filled, results masked
-            const uint32_t dst = smem_base + cp_dst + half + it * 2 * SK_REGION_BYTES;
-            const uint8_t *g = src + (size_t)(it * 32 + lane) * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(nbytes ? g : a.codes), "r"(nbytes));
+        for (int j = 0; j < SK_J; ++j) {
+            const int id = *reinterpret_cast<const int *>(smem_raw + myring + ((n & 1) * SK_J + j) * 4);
+            const uint8_t *src = a.codes + (size_t)id * 32;
+            const uint32_t dst = smem_base + myreg + 32 + half + j * 32;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16));
         }
         asm volatile("cp.async.commit_group;");
     };
@@ -958,60 +1040,91 @@ __global__ void __launch_bounds__(SK_WARPS * 32, 1) k_scan_linear_skew32(LinearA
     wt.k = a.k;
     wt.count = 0;
     // zero the carry row of this lane (read by the lagging steps of the very first block)
-    *reinterpret_cast<uint4 *>(smem_raw + region + lane * SK_REGION_BYTES) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4 *>(smem_raw + region + lane * SK_REGION_BYTES + 16) = make_uint4(0, 0, 0, 0);
-    if (ntiles > 0) issue_tile(0);
-    __syncthreads();  // lut2 + cta_thr ready
-
+    *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
+    if (ntiles > 0) {
+        if constexpr (IVF) {
+            issue_ids(0);
+            asm volatile("cp.async.wait_group 0;");
+            issue_rows(0);
+        } else {
+            issue_tile(0);
+        }
+    }
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
-    // One copy of the 32-step block body; g walks the blocks of all tiles, the last iteration is the drain
-    // block (32 more steps that complete the last row of every lane).
-    const int nblocks = ntiles > 0 ? SK_J * ntiles + 1 : 0;
+    u64 thr = RII_KEY_MAX;
+    uint32_t thr_hi = 0xffffffffu;
+    // local index of the candidate whose distance completes at the end of the current block: it started one
+    // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
+    uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
+    int last_id = 0;
 #pragma unroll 1
-    for (int g = 0; g < nblocks; ++g) {
-        int n = g / SK_J, i = g % SK_J;
-        if (g == SK_J * ntiles) { n = ntiles - 1; i = SK_J; }
-        if (i == 0) {
-            if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
-                unsigned char *reg = smem_raw + region + lane * SK_REGION_BYTES;
-                uint4 c0 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32);
-                uint4 c1 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32 + 16);
-                *reinterpret_cast<uint4 *>(reg) = c0;
-                *reinterpret_cast<uint4 *>(reg + 16) = c1;
-            }
-            asm volatile("cp.async.wait_group 0;");
-            __syncwarp();
+    for (int n = 0; n < ntiles; ++n) {
+        if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
+            unsigned char *reg = smem_raw + myreg;
+            uint4 x0 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32);
+            uint4 x1 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32 + 16);
+            *reinterpret_cast<uint4 *>(reg) = x0;
+            *reinterpret_cast<uint4 *>(reg + 16) = x1;
         }
-        const uint32_t rbw = rb + 4 * ((n & 1) * SK_J * 8 + 8 * i);
+        asm volatile("cp.async.wait_group 0;");  // tile n has landed
+        if constexpr (!IVF) __syncwarp();        // (linear: rows were written by other lanes of the warp)
+        if constexpr (IVF) {
+            if (n + 1 < ntiles) issue_ids(n + 1);  // the slot's last reader was saved in last_id
+        }
+        thr = *reinterpret_cast<volatile u64 *>(cta_thr);
+        thr_hi = (uint32_t)(thr >> 32);
+        const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
+        const uint32_t ringw = myring + (n & 1) * SK_J * 4;
         SK_BLOCK(rbw)
-        // the candidate that *started* in the previous block is complete in every lane now
-        const long long row = w0 + (long long)n * SK_TILE_ROWS + 8 * lane + i - 1 - (i == 0 ? SK_TILE_ROWS - SK_J : 0);
-        warp_emit(wt, cta_thr, lane, accA, row, g > 0 && row < w1);
-        accA = accB;
-        accB = 0.f;
-        if (i == 0 && n + 1 < ntiles) {  // the other half's last reader finished with this block
+        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
+        eloc += SK_TILE_ROWS - SK_J + 1;
+        if constexpr (!IVF) {  // the other half's last reader finished with this block
             __syncwarp();
-            issue_tile(n + 1);
+            if (n + 1 < ntiles) issue_tile(n + 1);
         }
+#pragma unroll
+        for (int i = 1; i < SK_J; ++i) {
+            SK_BLOCK(rbw + 32 * i)
+            SK_EMIT(IVF ? (uint32_t)(*reinterpret_cast<const int *>(smem_raw + ringw + 4 * (i - 1))) : (uint32_t)(base + eloc))
+            eloc += 1;
+            if constexpr (IVF) {
+                if (i == 1 && n + 1 < ntiles) {  // ids of tile n+1 have had a block to arrive; gather its rows
+                    asm volatile("cp.async.wait_group 0;");
+                    issue_rows(n + 1);
+                }
+            }
+        }
+        if constexpr (IVF) last_id = *reinterpret_cast<const int *>(smem_raw + ringw + 4 * (SK_J - 1));
+    }
+    if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
+        const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
+        SK_BLOCK(rbw)
+        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
     }
     warp_compact(wt, cta_thr, lane);
     __syncthreads();
-    // CTA merge of the warp lists through the block-level selector (reusing the lut2 area)
-    {
-        __shared__ int s_cnt[SK_WARPS];
+    {   // CTA merge of the warp lists through the block-level selector (reusing the lut2 area)
+        __shared__ int s_cnt[NW];
         if (lane == 0) s_cnt[wid] = wt.count;
         BlockTopk tk;
-        const int mcap = next_pow2(SK_WARPS * a.k + 1);
+        const int mcap = next_pow2(NW * a.k + 1);
         tk.keys = reinterpret_cast<u64 *>(smem_raw);
         tk.count = reinterpret_cast<int *>(smem_raw + (size_t)mcap * 8 + 8);
         tk.thr = reinterpret_cast<u64 *>(smem_raw + (size_t)mcap * 8);
         tk.cap = mcap;
         tk.k = a.k;
         tk.init();
-        const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw + SK_LUT_BYTES + SK_WARPS * SK_WARP_BYTES);
-        for (int w2 = 0; w2 < SK_WARPS; ++w2)
+        const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw + keys_off);
+        for (int w2 = 0; w2 < NW; ++w2)
             for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
         emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
     }
+}
+
+static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)
+{
+    return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (ivf ? (size_t)nw * SK_ID_BYTES : 0) + (size_t)nw * capw * 8 + 16 + 64 +
+           (ivf ? (size_t)w_eff * 12 + 16 : 0);
 }

@@ -358,6 +358,34 @@ int grow_codes(rii_index *h, long long rows)
     return 0;
 }
 
+// ---- v2 (skewed) scan launcher: the most warps per SM whose shared-memory footprint fits ---------------
+int skew_pick_nw(bool ivf, int capw, int w_eff)
+{
+    for (int nw : {16, 14, 12})
+        if (skew_smem_bytes(nw, ivf, capw, w_eff) <= SMEM_MAX) return nw;
+    return 0;
+}
+
+template <int NW, bool IVF> int launch_skew_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
+{
+    CKR(set_smem(k_scan_skew32<NW, IVF>, smem));
+    k_scan_skew32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
+    return 0;
+}
+
+int launch_skew(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
+{
+    const size_t smem = skew_smem_bytes(nw, ivf, a.cap, a.w_eff);
+    if (ivf) {
+        if (nw == 16) return launch_skew_t<16, true>(a, parts, B, smem, st);
+        if (nw == 14) return launch_skew_t<14, true>(a, parts, B, smem, st);
+        return launch_skew_t<12, true>(a, parts, B, smem, st);
+    }
+    if (nw == 16) return launch_skew_t<16, false>(a, parts, B, smem, st);
+    if (nw == 14) return launch_skew_t<14, false>(a, parts, B, smem, st);
+    return launch_skew_t<12, false>(a, parts, B, smem, st);
+}
+
 // ---- the query pipeline on device buffers -----------------------------------------------------------
 struct QueryCfg {
     int topk;
@@ -407,24 +435,23 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.out = out;
         const size_t smem = scan_smem_bytes(lutf, cap, 0);
         // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
-        const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K;
+        const int capw = std::max(64, next_pow2(c.topk + 32));
+        const int nw = skew_pick_nw(false, capw, 0);
+        const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
         const bool use_v2 = v2_ok && (h->opt_scan_kernel == 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
         if (h->opt_scan_kernel == 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2 needs M == 32, no target_ids and topk <= 224");
         if (use_v2) {
-            const int capw = std::max(64, next_pow2(c.topk + 32));
             parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
-                                             std::max<long long>(1, h->N / (SK_WARPS * SK_TILE_ROWS * 4)));
+                                             std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
             out.final = parts == 1;
             if (!out.final) {
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
                 out.partial = h->partial.as<u64>();
             }
-            a.out = out;
-            a.cap = capw;
-            const size_t smem2 = (size_t)SK_LUT_BYTES + (size_t)SK_WARPS * SK_WARP_BYTES + (size_t)SK_WARPS * capw * 8 + 16;
-            CKR(set_smem(k_scan_linear_skew32, smem2));
+            SkewArgs sa{};
+            sa.T = a.T; sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             Prof pr(h, st, PK_SCAN_LINEAR);
-            k_scan_linear_skew32<<<dim3(parts, B), SK_WARPS * 32, smem2, st>>>(a);
+            CKR(launch_skew(nw, false, sa, parts, B, st));
         } else {
             Prof pr(h, st, PK_SCAN_LINEAR);
             DISPATCH_M(M, {
@@ -526,9 +553,29 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.w_eff = w_eff;
         a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
         a.out = out;
+        // v2 (skewed, bank-conflict-free) when it applies: M == 32, no target_ids, small topk, plan fits smem
+        const int capw2 = std::max(64, next_pow2(c.topk + 32));
+        const int nw2 = skew_pick_nw(true, capw2, w_eff);
+        const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && nw2 > 0;
+        const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
+        if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
+        SkewArgs sa{};
+        if (use_v2) {
+            parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
+                                             std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)));
+            out.final = parts == 1;
+            if (!out.final) {
+                CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
+                out.partial = h->partial.as<u64>();
+            }
+            sa.T = a.T; sa.codes = a.codes; sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
+            sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
+        }
         {
         Prof pr(h, st, PK_SCAN_IVF);
-        if (subset) {
+        if (use_v2) {
+            CKR(launch_skew(nw2, true, sa, parts, B, st));
+        } else if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
             DISPATCH_M(M, {
                 CKR(set_smem(k_scan_ivf_subset<MT>, smem));

@@ -368,3 +368,31 @@ def test_skew_kernel_large_n_vs_v1():
         assert r1 == r2 == r0
     T = O.dtable(Q[0], cw, 16)
     assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(O.dtable(Q[2], cw, 16), codes, 100), "5M")
+
+
+def test_ivf_skew_kernel_vs_v1_and_oracle():
+    """k_scan_ivf_skew32 (auto-selected for M = 32, no target_ids, topk <= 96) against the natural-layout
+    kernel and the oracle: single-candidate plans, mid-list cuts, several CTAs per query, batches."""
+    D, M, Ks, N, nlist = 128, 32, 256, 60000, 50
+    cw, codes, Q = synth(D, M, Ks, N, 5, seed=31)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 2)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    cases = [(1, 1), (1, 7), (3, 255), (1, 256), (10, 257), (96, 96), (5, 1200), (1, 2048), (20, 2049), (50, 33333), (96, N)]
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk, L in cases:
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
+            e.set_option("scan_kernel", 2)
+            r2 = e.query_ivf(q, topk, EMPTY, L)
+            e.set_option("scan_kernel", 1)
+            r1 = e.query_ivf(q, topk, EMPTY, L)
+            assert r1 == r2, (topk, L)
+            assert_same_result(r2[0], np.array(r2[1], np.float32), exp[0], exp[1], "ivf skew k=%d L=%d" % (topk, L))
+    e.set_option("scan_kernel", 0)
+    Qb = np.ascontiguousarray(np.tile(Q, (60, 1)))  # 300 queries -> one CTA per query
+    bi, bd, bc = e.query_batch(Qb, 4, L=3000, method="ivf")
+    for b in range(0, 300, 37):
+        exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, 4, 3000)
+        assert_same_result(bi[b], bd[b], exp[0], exp[1], "ivf skew batch %d" % b)
