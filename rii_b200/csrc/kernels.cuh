@@ -374,28 +374,26 @@ struct PlanArgs {
     int *flags;            // (B) bit0: needs full ranking (walk beyond w), bit1: empty result
 };
 
-__device__ void make_plan(const PlanArgs &p, int b)
+// f / pre / loc are indexed by RANK j (0..w_eff): (filtered or global) length of the j-th ranked list, the part
+// of it held by lower ranks (null: 0) and the part held locally (null: subset mode, counts are local already).
+__device__ void make_plan(const PlanArgs &p, int b, const int *f_by_rank, const int *pre_by_rank, const int *loc_by_rank)
 {
-    // single thread; w is small (tens) on every BASELINE config
-    const int *ranked = p.ranked + (size_t)b * p.w_eff;
+    // single thread over <= w_eff entries that the caller staged (shared memory in the fused coarse kernel)
     int *cum = p.cum + (size_t)b * p.w_eff;
     long long P = 0;
     int J = 0, flag = 0, local = 0;
     bool done = false;
     int take_last = 0;
     for (int j = 0; j < p.w_eff; ++j) {
-        int no = ranked[j];
-        long long f = p.filt_cnt ? p.filt_cnt[(size_t)b * p.w_eff + j] : p.glob_len[no];
+        long long f = f_by_rank[j];
         long long take = f;
         if (P + f >= p.L) { take = p.L - P; done = true; }            // src/rii.h:302-304
         P += take;
-        long long lt;
-        if (p.filt_cnt) lt = take;  // subset: counted in filtered ids (single shard)
-        else {
-            long long pre = p.pre_len ? p.pre_len[no] : 0;
-            lt = take - pre;
+        long long lt = take;
+        if (loc_by_rank) {
+            lt = take - (pre_by_rank ? pre_by_rank[j] : 0);
             if (lt < 0) lt = 0;
-            if (lt > p.loc_len[no]) lt = p.loc_len[no];
+            if (lt > loc_by_rank[j]) lt = loc_by_rank[j];
         }
         local += (int)lt;
         cum[j] = local;
@@ -444,15 +442,24 @@ __global__ void __launch_bounds__(RII_THREADS) k_coarse_rank(CoarseArgs a)
     }
     s.tk.compact();
     int *ranked = a.plan.ranked + (size_t)b * a.plan.w_eff;
-    for (int i = threadIdx.x; i < a.plan.w_eff; i += blockDim.x) ranked[i] = (int)key_id(s.tk.keys[i]);
+    int *s_f = reinterpret_cast<int *>(s.tail), *s_pre = s_f + a.plan.w_eff, *s_loc = s_pre + a.plan.w_eff;
+    for (int i = threadIdx.x; i < a.plan.w_eff; i += blockDim.x) {
+        const int no = (int)key_id(s.tk.keys[i]);
+        ranked[i] = no;
+        if (a.do_plan) {  // stage the list lengths in rank order (parallel loads; the plan itself is a short serial scan)
+            s_f[i] = a.plan.glob_len[no];
+            s_pre[i] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
+            s_loc[i] = a.plan.loc_len[no];
+        }
+    }
     __syncthreads();
-    if (a.do_plan && threadIdx.x == 0) make_plan(a.plan, b);
+    if (a.do_plan && threadIdx.x == 0) make_plan(a.plan, b, s_f, s_pre, s_loc);
 }
 
 __global__ void k_plan(PlanArgs p, int B)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) make_plan(p, b);
+    if (b < B) make_plan(p, b, p.filt_cnt + (size_t)b * p.w_eff, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -819,7 +826,7 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 //    code-word reads conflict free as well).  A lane's region is its byte stream; reading it at word
 //    (q - l/4) and funnel-shifting by l % 4 bytes yields the l-byte lag for free.  Linear: 16-byte chunks
 //    dealt round-robin (512 contiguous bytes per warp instruction).  IVF: every lane gathers its own rows
-//    (ids fetched one tile ahead with 4-byte cp.async into a small id ring).
+//    (posting-list ids loaded one tile ahead into registers).
 //  * a lane finishes one candidate per 32 steps at its own phase: steps t < l still belong to the previous
 //    row (accumulator A), steps t >= l to the new one (B); at the block end A is complete in every lane.
 //  * top-k per warp (ballot-compacted pushes into a small shared buffer, warp-level bitonic compaction),
@@ -832,8 +839,6 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 #define SK_REGION_BYTES (SK_REGION_WORDS * 4)    // 288
 #define SK_WARP_BYTES (32 * SK_REGION_BYTES)     // 9216
 #define SK_LUT_BYTES 65536
-#define SK_ID_STRIDE (2 * SK_J + 1)              // id ring words per lane (IVF): 2 tiles + 1 pad
-#define SK_ID_BYTES (32 * SK_ID_STRIDE * 4)      // 1152
 #define SK_MAX_K 224
 
 struct SkewArgs {
@@ -878,9 +883,15 @@ __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
     __syncwarp();
 }
 
-// slow path of an emission: some lane passed the threshold
-__device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, u64 key, bool pass, unsigned bal)
+// slow path of an emission: some lane beat the cached distance threshold.  Re-test against the exact,
+// current (distance, id) threshold, append the survivors (ballot-compacted), compact when nearly full.
+__device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, float dist, uint32_t id, bool pre)
 {
+    const u64 thr = *reinterpret_cast<volatile u64 *>(cta_thr);
+    const u64 key = pack_key(dist, id);
+    const bool pass = pre && key < thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (!bal) return;
     if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
     w.count += __popc(bal);
     if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
@@ -914,17 +925,10 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, u64 
 // end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
 #define SK_EMIT(ID)                                                                                           \
     {                                                                                                         \
-        bool pass_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                                 \
-        u64 key_ = 0;                                                                                         \
-        if (pass_) {                                                                                          \
-            key_ = pack_key(accA, (uint32_t)(ID));                                                            \
-            pass_ = key_ < thr;                                                                               \
-        }                                                                                                     \
-        const unsigned bal_ = __ballot_sync(0xffffffffu, pass_);                                              \
-        if (bal_) {                                                                                           \
-            warp_push(wt, cta_thr, lane, key_, pass_, bal_);                                                  \
-            thr = *reinterpret_cast<volatile u64 *>(cta_thr);                                                 \
-            thr_hi = (uint32_t)(thr >> 32);                                                                   \
+        const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
+        if (__any_sync(0xffffffffu, pre_)) {                                                                  \
+            warp_push(wt, cta_thr, lane, accA, (uint32_t)(ID), pre_);                                         \
+            thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);                            \
         }                                                                                                     \
         accA = accB;                                                                                          \
         accB = 0.f;                                                                                           \
@@ -934,12 +938,11 @@ template <int NW, bool IVF>
 __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [lut2 64 KB][NW regions][NW id rings (IVF)][NW key buffers][cta_thr][s_off, s_cum (IVF)]
+    // layout: [lut2 64 KB][NW regions][NW key buffers][cta_thr][s_off, s_cum (IVF)]
     float *lut2 = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
-    const uint32_t ring_off = SK_LUT_BYTES + NW * SK_WARP_BYTES;
-    const uint32_t keys_off = ring_off + (IVF ? NW * SK_ID_BYTES : 0);
+    const uint32_t keys_off = SK_LUT_BYTES + NW * SK_WARP_BYTES;
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
     u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
     long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8);
@@ -977,7 +980,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     const uint32_t shift = 8 * (4 - (lane & 3));         // funnel shift (32 == no byte lag)
     const uint32_t colreg = (uint32_t)((32 - lane) * 4); // column byte offset, upper bytes zero
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t myring = ring_off + wid * SK_ID_BYTES + lane * SK_ID_STRIDE * 4;
     // linear: destination of 16-byte chunk (it, lane): rows are dealt SK_J per lane
     const uint32_t cp_dst = region + (lane >> 3) * SK_REGION_BYTES + 32 + (lane & 7) * 16;
 
@@ -999,34 +1001,30 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.commit_group;");
     };
-    auto issue_ids = [&](int n) {  // IVF: posting-list ids of this lane's SK_J candidates of tile n
+    // IVF: posting-list ids of this lane's SK_J candidates of a tile, fetched one tile ahead into registers.
+    // seg0 = segment of the lane's first candidate; candidates advance by SK_TILE_ROWS per tile, so the next
+    // tile's search resumes from it (segments are ~N/nlist long: 0-1 steps).
+    int seg0 = 0;
+    int idc[SK_J], idn[SK_J];
+#pragma unroll
+    for (int j = 0; j < SK_J; ++j) idc[j] = idn[j] = 0;
+    auto fetch_ids = [&](int n, int (&dst)[SK_J]) {
         int c = (int)base + n * SK_TILE_ROWS + SK_J * lane;
         const int cend = (int)end;
-        int seg = 0;
-        if (c < cend) {
-            int lo = 0, hi = J - 1;  // first segment with cum > c
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (s_cum[mid] > c) hi = mid; else lo = mid + 1;
-            }
-            seg = lo;
-        }
+        if (c < cend) while (s_cum[seg0] <= c) ++seg0;
+        int seg = seg0;
 #pragma unroll
         for (int j = 0; j < SK_J; ++j, ++c) {
             const bool ok = c < cend;
             if (ok) while (s_cum[seg] <= c) ++seg;
-            const int *src = ok ? a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0)) : a.ids;
-            const uint32_t dst = smem_base + myring + ((n & 1) * SK_J + j) * 4;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0));
+            dst[j] = ok ? __ldg(a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) : 0;
         }
-        asm volatile("cp.async.commit_group;");
     };
-    auto issue_rows = [&](int n) {  // IVF: gather this lane's rows into its own region
+    auto issue_rows = [&](int n, const int (&ids)[SK_J]) {  // IVF: gather this lane's rows into its own region
         const uint32_t half = (n & 1) ? SK_J * 32 : 0;
 #pragma unroll
         for (int j = 0; j < SK_J; ++j) {
-            const int id = *reinterpret_cast<const int *>(smem_raw + myring + ((n & 1) * SK_J + j) * 4);
-            const uint8_t *src = a.codes + (size_t)id * 32;
+            const uint8_t *src = a.codes + (size_t)ids[j] * 32;
             const uint32_t dst = smem_base + myreg + 32 + half + j * 32;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16));
@@ -1044,17 +1042,24 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
         if constexpr (IVF) {
-            issue_ids(0);
-            asm volatile("cp.async.wait_group 0;");
-            issue_rows(0);
+            {   // first segment with cum > c (binary search once; later tiles resume from seg0)
+                const int c = (int)base + SK_J * lane;
+                int lo = 0, hi = J - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (s_cum[mid] > c) hi = mid; else lo = mid + 1;
+                }
+                seg0 = lo;
+            }
+            fetch_ids(0, idc);
+            issue_rows(0, idc);
         } else {
             issue_tile(0);
         }
     }
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
-    u64 thr = RII_KEY_MAX;
-    uint32_t thr_hi = 0xffffffffu;
+    uint32_t thr_hi = 0xffffffffu;  // cached distance part of the CTA threshold (stale == merely less strict)
     // local index of the candidate whose distance completes at the end of the current block: it started one
     // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
     uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
@@ -1071,12 +1076,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         asm volatile("cp.async.wait_group 0;");  // tile n has landed
         if constexpr (!IVF) __syncwarp();        // (linear: rows were written by other lanes of the warp)
         if constexpr (IVF) {
-            if (n + 1 < ntiles) issue_ids(n + 1);  // the slot's last reader was saved in last_id
+            if (n + 1 < ntiles) fetch_ids(n + 1, idn);  // plain loads: consumed one block later
         }
-        thr = *reinterpret_cast<volatile u64 *>(cta_thr);
-        thr_hi = (uint32_t)(thr >> 32);
+        thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);
         const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
-        const uint32_t ringw = myring + (n & 1) * SK_J * 4;
         SK_BLOCK(rbw)
         SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
         eloc += SK_TILE_ROWS - SK_J + 1;
@@ -1087,16 +1090,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 #pragma unroll
         for (int i = 1; i < SK_J; ++i) {
             SK_BLOCK(rbw + 32 * i)
-            SK_EMIT(IVF ? (uint32_t)(*reinterpret_cast<const int *>(smem_raw + ringw + 4 * (i - 1))) : (uint32_t)(base + eloc))
+            SK_EMIT(IVF ? (uint32_t)idc[i - 1] : (uint32_t)(base + eloc))
             eloc += 1;
             if constexpr (IVF) {
-                if (i == 1 && n + 1 < ntiles) {  // ids of tile n+1 have had a block to arrive; gather its rows
-                    asm volatile("cp.async.wait_group 0;");
-                    issue_rows(n + 1);
-                }
+                if (i == 1 && n + 1 < ntiles) issue_rows(n + 1, idn);  // the ids have had a block to arrive
             }
         }
-        if constexpr (IVF) last_id = *reinterpret_cast<const int *>(smem_raw + ringw + 4 * (SK_J - 1));
+        if constexpr (IVF) {
+            last_id = idc[SK_J - 1];
+#pragma unroll
+            for (int j = 0; j < SK_J; ++j) idc[j] = idn[j];
+        }
     }
     if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
         const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
@@ -1125,6 +1129,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 
 static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)
 {
-    return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (ivf ? (size_t)nw * SK_ID_BYTES : 0) + (size_t)nw * capw * 8 + 16 + 64 +
+    return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (size_t)nw * capw * 8 + 16 + 64 +
            (ivf ? (size_t)w_eff * 12 + 16 : 0);
 }

@@ -511,7 +511,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.cap = next_pow2(w_eff + RII_THREADS);
         a.do_plan = subset ? 0 : 1;
         a.plan = p;
-        const size_t smem = scan_smem_bytes(lutf, a.cap, 0);
+        const size_t smem = scan_smem_bytes(lutf, a.cap, (size_t)w_eff * 12);
         Prof pr(h, st, PK_COARSE);
         DISPATCH_M(M, {
             CKR(set_smem(k_coarse_rank<MT>, smem));
