@@ -261,11 +261,12 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    # algorithmic bytes of the dominant kernel (posting-list scan), per launch of B queries:
-    # per query V*4 (ids visited) + C*M (codes gathered) + 4*M*Ks (its distance table); V = C = L
+    # algorithmic bytes of the dominant kernel (posting-list scan), per launch: per query C*M code bytes
+    # (C = L candidates) + 4*M*Ks (its distance table).  SURVEY's V*4 bytes of visited ids are NOT counted: the
+    # kernel streams a list-ordered code copy and reads ids only for survivors.
     shard = 1.0 / world
     q_per_launch = K * B / max(scan_n.value, 1)  # the library processes a step in chunks of <= 2048 queries
-    alg = q_per_launch * (L * shard * (4 + M) + 4 * M * CFG["Ks"])
+    alg = q_per_launch * (L * shard * M + 4 * M * CFG["Ks"])
     launch_ms = scan_ms.value / max(scan_n.value, 1)
     achieved = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
     line = {
@@ -279,7 +280,7 @@ def run_ours(args):
                    "index_build_s": round(t_build, 2)},
         "recall_at_1": round(recall, 4),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-        "roofline": {"kernel": "k_scan_ivf<32>", "bound": "hbm", "achieved": None if achieved is None else round(achieved, 1),
+        "roofline": {"kernel": "k_scan_skew32<NW=16, IVF>", "bound": "hbm", "achieved": None if achieved is None else round(achieved, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": None if achieved is None else round(achieved / peak, 4), "traffic": None,
                      "algorithmic_bytes_per_launch": int(alg), "queries_per_launch": int(q_per_launch),

@@ -744,6 +744,17 @@ __global__ void k_gather_rows(const uint8_t *__restrict__ codes, const long long
     out[i] = codes[pick[r] * M + m];
 }
 
+// list-ordered copy of the codes: out[p] = codes[ids[p]] (32-byte rows, 16 bytes per thread)
+__global__ void k_gather_rows32_by_list(const uint8_t *__restrict__ codes, const int *__restrict__ ids, long long n,
+                                        uint8_t *__restrict__ out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
+    if (i >= n * 2) return;
+    const long long p = i >> 1;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(codes + (size_t)ids[p] * 32) + (i & 1));
+    reinterpret_cast<uint4 *>(out)[i] = v;
+}
+
 // histogram of code bytes per (cluster, subspace): hist[k][m][ks].  src/pqkmeans.cpp:229-233
 __global__ void k_vote_hist(const uint8_t *__restrict__ codes, const int *__restrict__ assign, long long n, int M,
                             int Ks, int *hist)
@@ -825,8 +836,11 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 //    [carry row | half A: 4 rows | half B: 4 rows] (stride 72 words = 8 mod 32, which makes the lanes' 4-byte
 //    code-word reads conflict free as well).  A lane's region is its byte stream; reading it at word
 //    (q - l/4) and funnel-shifting by l % 4 bytes yields the l-byte lag for free.  Linear: 16-byte chunks
-//    dealt round-robin (512 contiguous bytes per warp instruction).  IVF: every lane gathers its own rows
-//    (posting-list ids loaded one tile ahead into registers).
+//    dealt round-robin (512 contiguous bytes per warp instruction).  IVF: the scan reads a LIST-ORDERED copy of
+//    the codes (row p of the copy = code of ids[p], rebuilt with the posting lists), so a planned segment is a
+//    contiguous run of rows and is staged exactly like the linear scan; ids are only looked up for survivors.
+//    (A per-lane id-indirected gather was measured first: it halves the issue rate -- 2 x 32 sector requests
+//    per 32 rows congest the LSU queue; profiles/r01_ncu_k_scan_skew32_ivf_v2b.txt.)
 //  * a lane finishes one candidate per 32 steps at its own phase: steps t < l still belong to the previous
 //    row (accumulator A), steps t >= l to the new one (B); at the block end A is complete in every lane.
 //  * top-k per warp (ballot-compacted pushes into a small shared buffer, warp-level bitonic compaction),
@@ -843,7 +857,7 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 
 struct SkewArgs {
     const float *T;            // (B, 32*Ks)
-    const uint8_t *codes;      // (N, 32)
+    const uint8_t *codes;      // linear: (N, 32) by id.  IVF: (N, 32) list-ordered copy (row p <-> ids[p])
     long long N;               // linear: rows of the shard
     const long long *offsets;  // IVF: CSR
     const int *ids;
@@ -927,7 +941,8 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
     {                                                                                                         \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
-            warp_push(wt, cta_thr, lane, accA, (uint32_t)(ID), pre_);                                         \
+            const uint32_t id_ = IVF ? (pre_ ? cand_id(ID) : 0u) : (ID);                                      \
+            warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
             thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);                            \
         }                                                                                                     \
         accA = accB;                                                                                          \
@@ -1001,35 +1016,43 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.commit_group;");
     };
-    // IVF: posting-list ids of this lane's SK_J candidates of a tile, fetched one tile ahead into registers.
-    // seg0 = segment of the lane's first candidate; candidates advance by SK_TILE_ROWS per tile, so the next
-    // tile's search resumes from it (segments are ~N/nlist long: 0-1 steps).
-    int seg0 = 0;
-    int idc[SK_J], idn[SK_J];
-#pragma unroll
-    for (int j = 0; j < SK_J; ++j) idc[j] = idn[j] = 0;
-    auto fetch_ids = [&](int n, int (&dst)[SK_J]) {
-        int c = (int)base + n * SK_TILE_ROWS + SK_J * lane;
+    // IVF: tile n = flattened candidates [c0, c0 + 128) of the plan; segment j covers [cum[j-1], cum[j]) and starts
+    // at row s_off[j] of the list-ordered code copy.  segw = segment of c0 (warp-uniform, carried along).
+    int segw = 0;
+    auto issue_tile_seg = [&](int n) {
+        const int c0 = (int)base + n * SK_TILE_ROWS;
         const int cend = (int)end;
-        if (c < cend) while (s_cum[seg0] <= c) ++seg0;
-        int seg = seg0;
+        while (segw < J - 1 && s_cum[segw] <= c0) ++segw;
+        const int seg_lo = segw ? s_cum[segw - 1] : 0;
+        const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
+        if (c0 + SK_TILE_ROWS <= cend && c0 + SK_TILE_ROWS <= s_cum[segw]) {  // one segment, full tile: pure stream
+            const uint8_t *g = a.codes + (size_t)(s_off[segw] + (c0 - seg_lo)) * 32 + lane * 16;
 #pragma unroll
-        for (int j = 0; j < SK_J; ++j, ++c) {
-            const bool ok = c < cend;
-            if (ok) while (s_cum[seg] <= c) ++seg;
-            dst[j] = ok ? __ldg(a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) : 0;
-        }
-    };
-    auto issue_rows = [&](int n, const int (&ids)[SK_J]) {  // IVF: gather this lane's rows into its own region
-        const uint32_t half = (n & 1) ? SK_J * 32 : 0;
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
+        } else {                                                             // crosses a segment boundary / tail
 #pragma unroll
-        for (int j = 0; j < SK_J; ++j) {
-            const uint8_t *src = a.codes + (size_t)ids[j] * 32;
-            const uint32_t dst = smem_base + myreg + 32 + half + j * 32;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16));
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
+                const int c = c0 + it * 16 + (lane >> 1);
+                const bool ok = c < cend;
+                int seg = segw;
+                if (ok) while (s_cum[seg] <= c) ++seg;
+                const uint8_t *g = a.codes + (size_t)(s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) * 32 + (lane & 1) * 16;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
+                             "l"(ok ? g : a.codes), "r"(ok ? 16 : 0));
+            }
         }
         asm volatile("cp.async.commit_group;");
+    };
+    // IVF: posting-list id of flattened candidate c (survivors only)
+    auto cand_id = [&](uint32_t c) -> uint32_t {
+        if (c >= (uint32_t)total) return 0u;
+        int lo = 0, hi = J - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_cum[mid] > (int)c) hi = mid; else lo = mid + 1;
+        }
+        return (uint32_t)__ldg(a.ids + s_off[lo] + ((int)c - (lo ? s_cum[lo - 1] : 0)));
     };
 
     WarpTopk wt;
@@ -1041,21 +1064,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
-        if constexpr (IVF) {
-            {   // first segment with cum > c (binary search once; later tiles resume from seg0)
-                const int c = (int)base + SK_J * lane;
-                int lo = 0, hi = J - 1;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (s_cum[mid] > c) hi = mid; else lo = mid + 1;
-                }
-                seg0 = lo;
-            }
-            fetch_ids(0, idc);
-            issue_rows(0, idc);
-        } else {
-            issue_tile(0);
-        }
+        if constexpr (IVF) issue_tile_seg(0);
+        else issue_tile(0);
     }
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
@@ -1063,7 +1073,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     // local index of the candidate whose distance completes at the end of the current block: it started one
     // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
     uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
-    int last_id = 0;
 #pragma unroll 1
     for (int n = 0; n < ntiles; ++n) {
         if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
@@ -1074,38 +1083,28 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             *reinterpret_cast<uint4 *>(reg + 16) = x1;
         }
         asm volatile("cp.async.wait_group 0;");  // tile n has landed
-        if constexpr (!IVF) __syncwarp();        // (linear: rows were written by other lanes of the warp)
-        if constexpr (IVF) {
-            if (n + 1 < ntiles) fetch_ids(n + 1, idn);  // plain loads: consumed one block later
-        }
+        __syncwarp();                            // rows were written by other lanes of the warp
         thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);
         const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
+        SK_EMIT((uint32_t)(base + eloc))
         eloc += SK_TILE_ROWS - SK_J + 1;
-        if constexpr (!IVF) {  // the other half's last reader finished with this block
-            __syncwarp();
-            if (n + 1 < ntiles) issue_tile(n + 1);
+        __syncwarp();  // the other half's last reader finished with this block
+        if (n + 1 < ntiles) {
+            if constexpr (IVF) issue_tile_seg(n + 1);
+            else issue_tile(n + 1);
         }
 #pragma unroll
         for (int i = 1; i < SK_J; ++i) {
             SK_BLOCK(rbw + 32 * i)
-            SK_EMIT(IVF ? (uint32_t)idc[i - 1] : (uint32_t)(base + eloc))
+            SK_EMIT((uint32_t)(base + eloc))
             eloc += 1;
-            if constexpr (IVF) {
-                if (i == 1 && n + 1 < ntiles) issue_rows(n + 1, idn);  // the ids have had a block to arrive
-            }
-        }
-        if constexpr (IVF) {
-            last_id = idc[SK_J - 1];
-#pragma unroll
-            for (int j = 0; j < SK_J; ++j) idc[j] = idn[j];
         }
     }
     if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
         const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
+        SK_EMIT((uint32_t)(base + eloc))
     }
     warp_compact(wt, cta_thr, lane);
     __syncthreads();

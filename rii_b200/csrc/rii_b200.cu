@@ -111,6 +111,7 @@ struct rii_index {
     float *d_Dm = nullptr;
     uint8_t *d_codes = nullptr;
     DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
+    DevBuf codes_list;  // (N, 32) list-ordered copy of the codes (row p <-> ids[p]); M == 32 only
     bool has_global = false;
 
     std::vector<uint8_t> h_centers;      // (nlist, M)
@@ -239,6 +240,14 @@ int upload_lists(rii_index *h)
     std::vector<int> len(nlist);
     for (int i = 0; i < nlist; ++i) len[i] = (int)(h->h_offsets[i + 1] - h->h_offsets[i]);
     if (nlist) CK(cudaMemcpyAsync(h->loc_len.p, len.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->M == 32 && !h->h_ids.empty()) {  // list-ordered code copy for the streaming posting-list scan (kernels.cuh, K5 v2)
+        const long long n = (long long)h->h_ids.size();
+        CKR(h->codes_list.ensure((size_t)n * 32));
+        k_gather_rows32_by_list<<<(unsigned)((n * 2 + 255) / 256), 256, 0, h->stream>>>(h->d_codes, h->ids.as<int>(), n,
+                                                                                       h->codes_list.as<uint8_t>());
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(h->stream));
     if (!h->has_global) {
         std::sort(len.begin(), len.end());
@@ -556,7 +565,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         // v2 (skewed, bank-conflict-free) when it applies: M == 32, no target_ids, small topk, plan fits smem
         const int capw2 = std::max(64, next_pow2(c.topk + 32));
         const int nw2 = skew_pick_nw(true, capw2, w_eff);
-        const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && nw2 > 0;
+        const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
         const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
         if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
         SkewArgs sa{};
@@ -568,7 +577,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
                 out.partial = h->partial.as<u64>();
             }
-            sa.T = a.T; sa.codes = a.codes; sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
+            sa.T = a.T; sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
         }
         {
@@ -727,7 +736,7 @@ int rii_destroy(rii_index_t *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
+    for (DevBuf *b : {&h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
         b->release();
