@@ -65,6 +65,22 @@ __device__ float l2sqr_lanes(const float *__restrict__ x, const float *__restric
     return __fadd_rn(__fadd_rn(a4[0], a4[1]), __fadd_rn(a4[2], a4[3]));
 }
 
+// One table entry with the query sub-vector already in registers when Ds <= 4 (every BASELINE shape):
+// (s0 + s1) + (s2 + s3) with absent lanes contributing +0 (src/distance.h:148-169).
+__device__ __forceinline__ float l2sqr_small(const float (&q)[4], const float *__restrict__ c, int Ds)
+{
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (Ds == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(c));
+        s0 = sqdiff(q[0], v.x); s1 = sqdiff(q[1], v.y); s2 = sqdiff(q[2], v.z); s3 = sqdiff(q[3], v.w);
+    } else {
+        s0 = sqdiff(q[0], __ldg(c));
+        if (Ds > 1) s1 = sqdiff(q[1], __ldg(c + 1));
+        if (Ds > 2) s2 = sqdiff(q[2], __ldg(c + 2));
+    }
+    return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+}
+
 // grid (ceil(M*Ks/256), B).  Q: (B, M*Ds), cw: (M, Ks, Ds), T: (B, M*Ks)
 __global__ void __launch_bounds__(RII_THREADS) k_dtable(const float *__restrict__ Q, const float *__restrict__ cw,
                                                         float *__restrict__ T, int M, int Ks, int Ds, int variant)
@@ -412,7 +428,10 @@ __device__ void make_plan(const PlanArgs &p, int b, const int *f_by_rank, const 
 }
 
 struct CoarseArgs {
-    const float *T;          // (B, M*Ks)
+    const float *T;          // (B, M*Ks), or null: build the table in-kernel from Q / cw (K1 fused)
+    const float *Q;          // (B, M*Ds)
+    const float *cw;         // (M, Ks, Ds)
+    int Ds, variant;
     const uint8_t *centers;  // (nlist, M)
     int M, Ks, nlist, cap;
     int do_plan;
@@ -425,7 +444,13 @@ __global__ void __launch_bounds__(RII_THREADS) k_coarse_rank(CoarseArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.plan.w_eff);
     const int b = blockIdx.x;
-    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    if (a.T) {
+        load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    } else {  // K1 fused: T[m][ks] straight into shared memory (codewords are read coalesced)
+        const float *q = a.Q + (size_t)b * a.M * a.Ds;
+        for (int e = threadIdx.x; e < a.M * a.Ks; e += RII_THREADS)
+            s.lut[e] = l2sqr_lanes(q + (size_t)(e / a.Ks) * a.Ds, a.cw + (size_t)e * a.Ds, a.Ds, a.variant);
+    }
     s.tk.init();
     for (int pos = 0; pos < a.nlist; pos += RII_THREADS) {
         s.tk.reserve(RII_THREADS);
@@ -856,7 +881,10 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 #define SK_MAX_K 224
 
 struct SkewArgs {
-    const float *T;            // (B, 32*Ks)
+    const float *T;            // (B, 32*Ks), or null: build the table in-kernel from Q / cw (K1 fused)
+    const float *Q;            // (B, 32*Ds)
+    const float *cw;           // (32, Ks, Ds)
+    int Ds, variant;
     const uint8_t *codes;      // linear: (N, 32) by id.  IVF: (N, 32) list-ordered copy (row p <-> ids[p])
     long long N;               // linear: rows of the shard
     const long long *offsets;  // IVF: CSR
@@ -966,10 +994,30 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     int J = 0;
     if constexpr (IVF) J = (a.flags[b] != 0) ? 0 : a.J[b];
     {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
-        const float *T = a.T + (size_t)b * 32 * a.Ks;
-        for (int e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
-            int ks = e >> 6, c = e & 63;
-            lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+        if (a.T) {
+            const float *T = a.T + (size_t)b * 32 * a.Ks;
+#pragma unroll 8
+            for (int e = threadIdx.x; e < 256 * 64; e += NW * 32) {
+                int ks = e >> 6, c = e & 63;
+                lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+            }
+        } else {
+            // K1 fused (src/rii.h:361-373): entry (m = lane, ks) -> both columns m and m + 32 of row ks; the
+            // lane's query sub-vector stays in registers, stores are bank-conflict free.
+            const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
+            float qv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.Ds <= 4)
+                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+#pragma unroll 8
+            for (int ks = wid; ks < 256; ks += NW) {
+                float v = 0.f;
+                if (ks < a.Ks) {
+                    const float *c = a.cw + ((size_t)lane * a.Ks + ks) * a.Ds;
+                    v = a.Ds <= 4 ? l2sqr_small(qv, c, a.Ds) : l2sqr_lanes(qm, c, a.Ds, a.variant);
+                }
+                lut2[ks * 64 + lane] = v;
+                lut2[ks * 64 + lane + 32] = v;
+            }
         }
         if constexpr (IVF)
             for (int j = threadIdx.x; j < J; j += blockDim.x) {

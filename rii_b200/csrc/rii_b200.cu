@@ -406,15 +406,20 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
               float *d_out_dists, int *d_out_counts, cudaStream_t st, int w, int w_eff, bool *checked_flags)
 {
     const int M = h->M, Ks = h->Ks, lutf = M * Ks;
-    // K1
-    CKR(h->T.ensure((size_t)B * lutf * 4));
-    {
+    // K1: the v2 scan kernels and the coarse kernel build their tables in-kernel from (Q, codewords); only the
+    // natural-layout (v1) scan kernels read tables from HBM, so k_dtable runs lazily.
+    bool have_T = false;
+    auto ensure_T = [&]() -> int {
+        if (have_T) return 0;
+        CKR(h->T.ensure((size_t)B * lutf * 4));
         Prof pr(h, st, PK_DTABLE);
         dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
         k_dtable<<<grid, RII_THREADS, 0, st>>>(d_Q, h->d_cw, h->T.as<float>(), M, Ks, h->Ds, h->variant);
         LAUNCHED();
         CK(cudaGetLastError());
-    }
+        have_T = true;
+        return 0;
+    };
     const int round = RII_THREADS * RII_ROWS_PER_THREAD;
     const int cap = next_pow2(c.topk + round);
     TopkOut out{};
@@ -434,7 +439,6 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             out.partial = h->partial.as<u64>();
         }
         LinearArgs a{};
-        a.T = h->T.as<float>();
         a.codes = h->d_codes;
         a.tids = c.S ? d_tids : nullptr;
         a.S = c.S;
@@ -458,10 +462,13 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 out.partial = h->partial.as<u64>();
             }
             SkewArgs sa{};
-            sa.T = a.T; sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             Prof pr(h, st, PK_SCAN_LINEAR);
             CKR(launch_skew(nw, false, sa, parts, B, st));
         } else {
+            CKR(ensure_T());
+            a.T = h->T.as<float>();
             Prof pr(h, st, PK_SCAN_LINEAR);
             DISPATCH_M(M, {
                 CKR(set_smem(k_scan_linear<MT>, smem));
@@ -514,7 +521,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     }
     {
         CoarseArgs a{};
-        a.T = h->T.as<float>();
+        a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
         a.centers = h->centers.as<uint8_t>();
         a.M = M; a.Ks = Ks; a.nlist = h->nlist;
         a.cap = next_pow2(w_eff + RII_THREADS);
@@ -553,7 +560,6 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             out.partial = h->partial.as<u64>();
         }
         IvfArgs a{};
-        a.T = h->T.as<float>();
         a.codes = h->d_codes;
         a.offsets = h->offsets.as<long long>();
         a.ids = h->ids.as<int>();
@@ -577,8 +583,13 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
                 out.partial = h->partial.as<u64>();
             }
-            sa.T = a.T; sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
+        }
+        if (!use_v2) {
+            CKR(ensure_T());
+            a.T = h->T.as<float>();
         }
         {
         Prof pr(h, st, PK_SCAN_IVF);
