@@ -68,8 +68,9 @@ int64_t rii_query_ivf(rii_index_t *h, const float *query, int topk, const int64_
  * out_counts: (B) results per query. */
 int rii_query_batch(rii_index_t *h, const float *queries, int B, int topk, const int64_t *target_ids, int64_t S,
                     int64_t L, int method, int64_t *out_ids, float *out_dists, int32_t *out_counts);
-/* Same with DEVICE buffers, enqueued on `stream` (a cudaStream_t, 0 = the index's own stream) and not
- * synchronised unless the rare full-ranking re-run (walk beyond w) is needed.
+/* Same with DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = the CUDA default stream) and not
+ * synchronised unless the rare full-ranking re-run (walk beyond w) is needed.  The handle's scratch
+ * buffers are shared: one call in flight per handle.
  * d_target_ids: device int64 (S) or NULL. */
 int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids,
                         int64_t S, int64_t L, int method, int64_t *d_out_ids, float *d_out_dists,
@@ -134,6 +135,9 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 int rii_profile_enable(rii_index_t *h, int on);
 int rii_profile_reset(rii_index_t *h);
 int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches);
+/* With option "debug_clocks" = 1 the v2 scan kernel records clock64() per CTA at [start, table ready, scan done,
+ * end]; this copies the (n_ctas, 4) values of the last launch to the host. */
+int rii_debug_clocks(rii_index_t *h, int64_t n_ctas, int64_t *out);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ SYMBOLS = {
     "rii_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "rii_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rii_profile_reset": (C.c_int, [_vp]),
+    "rii_debug_clocks": (C.c_int, [_vp, C.c_int64, _i64p]),
     "rii_profile_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), _i64p]),
 }
 

@@ -893,6 +893,7 @@ struct SkewArgs {
     int w_eff;
     int Ks, k, cap;            // cap = per-warp key capacity (power of two >= k + 32)
     TopkOut out;
+    long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)
 };
 
 struct WarpTopk {
@@ -985,6 +986,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     float *lut2 = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
+    long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     const uint32_t keys_off = SK_LUT_BYTES + NW * SK_WARP_BYTES;
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
     u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
@@ -1027,6 +1030,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
     }
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     // this warp's slice of the candidate space: [base, base + cnt)
     const long long total = IVF ? (J ? (long long)s_cum[J - 1] : 0) : a.N;
     const long long per_cta = ((total + gridDim.x - 1) / gridDim.x + NW * SK_TILE_ROWS - 1) / (NW * SK_TILE_ROWS) *
@@ -1156,6 +1160,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     }
     warp_compact(wt, cta_thr, lane);
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[2] = clock64();
     {   // CTA merge of the warp lists through the block-level selector (reusing the lut2 area)
         __shared__ int s_cnt[NW];
         if (lane == 0) s_cnt[wid] = wt.count;
@@ -1172,6 +1177,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
         emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
     }
+    if (dbg && threadIdx.x == 0) dbg[3] = clock64();
 }
 
 static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)

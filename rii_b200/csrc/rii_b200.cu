@@ -123,6 +123,8 @@ struct rii_index {
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
         tmp2, tmp3;
 
+    DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
+    int opt_debug_clocks = 0;
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernel, 2 skewed conflict-free kernel (M == 32 only)
 
     long long n_total() const { return N_total >= 0 ? N_total : N; }
@@ -464,6 +466,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             SkewArgs sa{};
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
             Prof pr(h, st, PK_SCAN_LINEAR);
             CKR(launch_skew(nw, false, sa, parts, B, st));
         } else {
@@ -586,6 +589,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
         }
         if (!use_v2) {
             CKR(ensure_T());
@@ -747,7 +751,7 @@ int rii_destroy(rii_index_t *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
+    for (DevBuf *b : {&h->dbg, &h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
         b->release();
@@ -863,7 +867,7 @@ int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk,
 {
     if (!h) return fail(RII_ERR_ARG, "null index");
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA (legacy) default stream, as everywhere in CUDA
     return query_dev(h, d_queries, B, topk, (const long long *)d_target_ids, S, L, method, (long long *)d_out_ids, d_out_dists,
                      d_out_counts, st);
 }
@@ -876,7 +880,23 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
         h->opt_scan_kernel = (int)value;
         return 0;
     }
+    if (!strcmp(name, "debug_clocks")) {
+        h->opt_debug_clocks = value != 0;
+        return 0;
+    }
     return fail(RII_ERR_ARG, std::string("unknown option: ") + name);
+}
+
+int rii_debug_clocks(rii_index_t *h, int64_t n_ctas, int64_t *out)
+{
+    // out: (n_ctas, 4) clock64() values recorded by the last v2 scan launch (option "debug_clocks" = 1)
+    if (!h || !out || n_ctas <= 0) return fail(RII_ERR_ARG, "bad arguments");
+    if ((size_t)n_ctas * 32 > h->dbg.cap) return fail(RII_ERR_ARG, "no debug clocks recorded for that many CTAs");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->dbg.p, (size_t)n_ctas * 32, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int rii_profile_enable(rii_index_t *h, int on)
@@ -924,7 +944,7 @@ int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_di
 {
     if (!h || !d_ids || !d_dists || !d_counts || G <= 0 || B <= 0 || k <= 0) return fail(RII_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     const int P = next_pow2(G * k < 2 ? 2 : G * k);
     const size_t smem = (size_t)P * 12;
     CKR(set_smem(k_merge_shards, smem));

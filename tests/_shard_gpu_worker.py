@@ -47,4 +47,11 @@ def run():
 
 
 if __name__ == "__main__":
-    run()
+    try:
+        run()
+    except BaseException:
+        import traceback
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "shard_worker_rank%s.log" % os.environ.get("RANK", "x")), "w") as f:
+            traceback.print_exc(file=f)
+        raise

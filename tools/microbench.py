@@ -39,9 +39,10 @@ def main_():
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     N = a.n
     chunk = 8000000
-    for s in range(0, N, chunk):
-        n = min(chunk, N - s)
-        e.add_codes(torch.randint(0, 256, (n, M), dtype=torch.uint8).numpy(), False)
+    if "linear" in a.what:
+        for s in range(0, N, chunk):
+            n = min(chunk, N - s)
+            e.add_codes(torch.randint(0, 256, (n, M), dtype=torch.uint8).numpy(), False)
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
     sp = C.c_void_p(st.cuda_stream)
@@ -78,6 +79,36 @@ def main_():
                               "query_ms": round(t_tot / a.reps, 4), "code_GBps": round(gbs, 1),
                               "frac_hbm_per_query_bytes": round(N * M / (per / B * 1e-3) / 1e9 / peak, 4),
                               "lookups_per_s_T": round(B * N * M / (per * 1e-3) / 1e12, 3)}))
+    if "ivf" in a.what:
+        # C2-shaped batch (N = 1M random codes, nlist = 1000, L = 32000, topk = 1) with per-CTA phase clocks
+        n_iv, B, L = 1000000, 2048, 32000
+        e3 = main.RiiCpp(cw, False, l2_variant=16)
+        e3.add_codes(torch.randint(0, 256, (n_iv, M), dtype=torch.uint8).numpy(), False)
+        e3.reconfigure(1000, 1)
+        lib.rii_profile_enable(e3._h, 1)
+        e3.set_option("debug_clocks", 1)
+        Q = torch.rand((B, D), device=dev)
+        oi = torch.empty((B, 1), dtype=torch.int64, device=dev)
+        od = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        oc = torch.empty((B,), dtype=torch.int32, device=dev)
+        for it in range(5):
+            if it == 2:
+                torch.cuda.synchronize()
+                lib.rii_profile_reset(e3._h)
+            _capi.check(lib.rii_query_batch_dev(e3._h, C.c_void_p(Q.data_ptr()), B, 1, None, 0, L, 1,
+                                                C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()),
+                                                C.c_void_p(oc.data_ptr()), sp))
+        torch.cuda.synchronize()
+        clk = np.zeros((B, 4), np.int64)
+        _capi.check(lib.rii_debug_clocks(e3._h, B, clk.ctypes.data_as(C.POINTER(C.c_int64))))
+        d = np.diff(clk, axis=1)
+        out = {"what": "ivf_batch", "B": B, "L": L}
+        for name in ("coarse_rank", "scan_ivf", "dtable"):
+            ms, n = prof(lib, e3, name)
+            out[name + "_ms"] = round(ms / max(n, 1), 4)
+        out["cta_cycles_mean"] = {"table": float(d[:, 0].mean()), "scan": float(d[:, 1].mean()), "tail": float(d[:, 2].mean()),
+                                  "total": float((clk[:, 3] - clk[:, 0]).mean())}
+        print(json.dumps(out))
     if "assign" in a.what:
         n_as = min(N, 1000000)
         e2 = main.RiiCpp(cw, False, l2_variant=16)
