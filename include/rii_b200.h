@@ -103,6 +103,10 @@ int rii_assign(rii_index_t *h, const uint8_t *codes, int64_t n, const uint8_t *c
 /* Codeword distance matrices (M, Ks, Ks) float32.  src/pqkmeans.cpp:23-34. */
 int rii_sym_matrices(rii_index_t *h, float *out);
 
+/* PQ encoder (the step before the path: fine_quantizer.encode, rii/rii.py:185): vecs float32 (n, M*Ds) ->
+ * out_codes uint8 (n, M); nearest codeword per sub-space, fp32 sequential sum, first minimum wins. */
+int rii_encode(rii_index_t *h, const float *vecs, int64_t n, uint8_t *out_codes);
+
 /* ---- id-range sharding (one index object per GPU) -------------------------- */
 /* This shard holds global ids [id_base, id_base + N_local) of an index of N_total codes. */
 int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total);

@@ -828,6 +828,45 @@ __global__ void __launch_bounds__(256) k_vote_centers(const float *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PQ encoder (the step before the path, call site rii/rii.py:185 fine_quantizer.encode):
+// codes[n][m] = argmin_ks sum_i (x[n][m*Ds+i] - C[m][ks][i])^2, fp32 sequential in i, first minimum wins.
+// grid (ceil(n/256), M); the subspace's codebook (Ks*Ds floats) is broadcast-read from shared memory.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RII_THREADS) k_pq_encode(const float *__restrict__ X, long long n, const float *__restrict__ cw,
+                                                           int M, int Ks, int Ds, uint8_t *__restrict__ codes)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *cb = reinterpret_cast<float *>(smem_raw);
+    const int m = blockIdx.y;
+    for (int i = threadIdx.x; i < Ks * Ds; i += blockDim.x) cb[i] = __ldg(cw + (size_t)m * Ks * Ds + i);
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float *x = X + row * (size_t)(M * Ds) + (size_t)m * Ds;
+    float best = 3.402823466e+38f;
+    int arg = 0;
+    if (Ds <= 8) {
+        float xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = i < Ds ? __ldg(x + i) : 0.f;
+        for (int ks = 0; ks < Ks; ++ks) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < Ds) d = __fadd_rn(d, sqdiff(xv[i], cb[ks * Ds + i]));
+            if (d < best) { best = d; arg = ks; }
+        }
+    } else {
+        for (int ks = 0; ks < Ks; ++ks) {
+            float d = 0.f;
+            for (int i = 0; i < Ds; ++i) d = __fadd_rn(d, sqdiff(__ldg(x + i), cb[ks * Ds + i]));
+            if (d < best) { best = d; arg = ks; }
+        }
+    }
+    codes[row * M + m] = (uint8_t)arg;
+}
+
 // all ADC distances of a row range (diagnostics / K-parity tests): out[b][n]
 template <int M_T>
 __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict__ T, const uint8_t *__restrict__ codes,
@@ -970,8 +1009,7 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
     {                                                                                                         \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
-            const uint32_t id_ = IVF ? (pre_ ? cand_id(ID) : 0u) : (ID);                                      \
-            warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
+            warp_push(wt, cta_thr, lane, accA, (uint32_t)(ID), pre_);                                         \
             thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);                            \
         }                                                                                                     \
         accA = accB;                                                                                          \
@@ -1011,7 +1049,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             float qv[4] = {0.f, 0.f, 0.f, 0.f};
             if (a.Ds <= 4)
                 for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
-#pragma unroll 8
+#pragma unroll
             for (int ks = wid; ks < 256; ks += NW) {
                 float v = 0.f;
                 if (ks < a.Ks) {
@@ -1096,15 +1134,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.commit_group;");
     };
-    // IVF: posting-list id of flattened candidate c (survivors only)
-    auto cand_id = [&](uint32_t c) -> uint32_t {
-        if (c >= (uint32_t)total) return 0u;
-        int lo = 0, hi = J - 1;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (s_cum[mid] > (int)c) hi = mid; else lo = mid + 1;
+    // IVF: posting-list ids of this lane's SK_J candidates of tile n (plain loads issued one tile ahead of their
+    // first use, so the survivors' (distance, id) keys never wait on a dependent global load).
+    int seg0 = 0;  // segment of the lane's first candidate of the previous fetch (candidates advance by 128 per tile)
+    int idc[SK_J], idn[SK_J];
+#pragma unroll
+    for (int j = 0; j < SK_J; ++j) idc[j] = idn[j] = 0;
+    auto fetch_ids = [&](int n, int (&dst)[SK_J]) {
+        int c = (int)base + n * SK_TILE_ROWS + SK_J * lane;
+        const int cend = (int)end;
+        if (c < cend) while (s_cum[seg0] <= c) ++seg0;
+        int seg = seg0;
+#pragma unroll
+        for (int j = 0; j < SK_J; ++j, ++c) {
+            const bool ok = c < cend;
+            if (ok) while (s_cum[seg] <= c) ++seg;
+            dst[j] = ok ? __ldg(a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) : 0;
         }
-        return (uint32_t)__ldg(a.ids + s_off[lo] + ((int)c - (lo ? s_cum[lo - 1] : 0)));
     };
 
     WarpTopk wt;
@@ -1116,8 +1162,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
-        if constexpr (IVF) issue_tile_seg(0);
-        else issue_tile(0);
+        if constexpr (IVF) {
+            issue_tile_seg(0);
+            fetch_ids(0, idc);
+        } else {
+            issue_tile(0);
+        }
     }
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
@@ -1125,6 +1175,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     // local index of the candidate whose distance completes at the end of the current block: it started one
     // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
     uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
+    int last_id = 0;
 #pragma unroll 1
     for (int n = 0; n < ntiles; ++n) {
         if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
@@ -1139,43 +1190,93 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);
         const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT((uint32_t)(base + eloc))
+        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
         eloc += SK_TILE_ROWS - SK_J + 1;
         __syncwarp();  // the other half's last reader finished with this block
         if (n + 1 < ntiles) {
-            if constexpr (IVF) issue_tile_seg(n + 1);
-            else issue_tile(n + 1);
+            if constexpr (IVF) {
+                issue_tile_seg(n + 1);
+                fetch_ids(n + 1, idn);
+            } else {
+                issue_tile(n + 1);
+            }
         }
 #pragma unroll
         for (int i = 1; i < SK_J; ++i) {
             SK_BLOCK(rbw + 32 * i)
-            SK_EMIT((uint32_t)(base + eloc))
+            SK_EMIT(IVF ? (uint32_t)idc[i - 1] : (uint32_t)(base + eloc))
             eloc += 1;
+        }
+        if constexpr (IVF) {
+            last_id = idc[SK_J - 1];
+#pragma unroll
+            for (int j = 0; j < SK_J; ++j) idc[j] = idn[j];
         }
     }
     if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
         const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT((uint32_t)(base + eloc))
+        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
     }
     warp_compact(wt, cta_thr, lane);
     __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();
-    {   // CTA merge of the warp lists through the block-level selector (reusing the lut2 area)
+    {   // CTA merge of the (sorted) warp lists, reusing the lut2 area for the keys
         __shared__ int s_cnt[NW];
         if (lane == 0) s_cnt[wid] = wt.count;
-        BlockTopk tk;
-        const int mcap = next_pow2(NW * a.k + 1);
-        tk.keys = reinterpret_cast<u64 *>(smem_raw);
-        tk.count = reinterpret_cast<int *>(smem_raw + (size_t)mcap * 8 + 8);
-        tk.thr = reinterpret_cast<u64 *>(smem_raw + (size_t)mcap * 8);
-        tk.cap = mcap;
-        tk.k = a.k;
-        tk.init();
+        __syncthreads();
+        int tot = 0;
+        for (int w2 = 0; w2 < NW; ++w2) tot += s_cnt[w2];
         const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw + keys_off);
-        for (int w2 = 0; w2 < NW; ++w2)
-            for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
-        emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
+        if (tot <= 256) {
+            // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
+            if (wid == 0) {
+                u64 *mk = reinterpret_cast<u64 *>(smem_raw);
+                const int P = next_pow2(tot < 2 ? 2 : tot);
+                int o = 0;
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    for (int i = lane; i < s_cnt[w2]; i += 32) mk[o + i] = allkeys[(size_t)w2 * capw + i];
+                    o += s_cnt[w2];
+                }
+                for (int i = tot + lane; i < P; i += 32) mk[i] = RII_KEY_MAX;
+                __syncwarp();
+                for (int kk = 2; kk <= P; kk <<= 1)
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        for (int i = lane; i < P; i += 32) {
+                            int ixj = i ^ j;
+                            if (ixj > i) {
+                                u64 x = mk[i], y = mk[ixj];
+                                bool up = (i & kk) == 0;
+                                if ((x > y) == up) { mk[i] = y; mk[ixj] = x; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                const int n = tot < a.k ? tot : a.k;
+                if (a.out.final) {
+                    for (int i = lane; i < n; i += 32) {
+                        a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(mk[i]);
+                        a.out.out_dists[(size_t)b * a.k + i] = key_dist(mk[i]);
+                    }
+                    if (lane == 0) a.out.out_counts[b] = n;
+                } else {
+                    u64 *dst = a.out.partial + ((size_t)b * gridDim.x + blockIdx.x) * a.k;
+                    for (int i = lane; i < a.k; i += 32) dst[i] = i < n ? mk[i] : RII_KEY_MAX;
+                }
+            }
+        } else {
+            BlockTopk tk;
+            const int mcap = next_pow2(NW * a.k + 1);
+            tk.keys = reinterpret_cast<u64 *>(smem_raw);
+            tk.count = reinterpret_cast<int *>(smem_raw + (size_t)mcap * 8 + 8);
+            tk.thr = reinterpret_cast<u64 *>(smem_raw + (size_t)mcap * 8);
+            tk.cap = mcap;
+            tk.k = a.k;
+            tk.init();
+            for (int w2 = 0; w2 < NW; ++w2)
+                for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
+            emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
+        }
     }
     if (dbg && threadIdx.x == 0) dbg[3] = clock64();
 }

@@ -1098,6 +1098,36 @@ int rii_sym_matrices(rii_index_t *h, float *out)
     return 0;
 }
 
+int rii_encode(rii_index_t *h, const float *vecs, int64_t n, uint8_t *out_codes)
+{
+    if (!h || !vecs || !out_codes || n < 0) return fail(RII_ERR_ARG, "bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const int D = h->M * h->Ds;
+    const size_t smem = (size_t)h->Ks * h->Ds * 4;
+    CKR(set_smem(k_pq_encode, smem));
+    DevBuf dx, dc;
+    int rc = 0;
+    const long long CH = 4ll << 20;  // rows per pass
+    do {
+        if ((rc = dx.ensure((size_t)std::min<long long>(n, CH) * D * 4)) < 0) break;
+        if ((rc = dc.ensure((size_t)std::min<long long>(n, CH) * h->M)) < 0) break;
+        for (long long s0 = 0; s0 < n && rc == 0; s0 += CH) {
+            const long long c = std::min<long long>(CH, n - s0);
+            cudaMemcpyAsync(dx.p, vecs + (size_t)s0 * D, (size_t)c * D * 4, cudaMemcpyHostToDevice, h->stream);
+            k_pq_encode<<<dim3((unsigned)((c + RII_THREADS - 1) / RII_THREADS), h->M), RII_THREADS, smem, h->stream>>>(
+                dx.as<float>(), c, h->d_cw, h->M, h->Ks, h->Ds, dc.as<uint8_t>());
+            LAUNCHED();
+            cudaMemcpyAsync(out_codes + (size_t)s0 * h->M, dc.p, (size_t)c * h->M, cudaMemcpyDeviceToHost, h->stream);
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) rc = fail(RII_ERR_CUDA, std::string("rii_encode: ") + cudaGetErrorString(e));
+        }
+    } while (0);
+    dx.release();
+    dc.release();
+    return rc;
+}
+
 int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total)
 {
     if (!h || id_base < 0 || N_total < 0) return fail(RII_ERR_ARG, "bad arguments");

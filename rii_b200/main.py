@@ -176,6 +176,15 @@ class RiiCpp(object):
         check(_capi.lib().rii_set_state(self._h, _ptr(centers, C.c_uint8), centers.shape[0], _ptr(codes, C.c_uint8),
                                         codes.shape[0], _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
 
+    def encode(self, vecs):
+        """GPU PQ encoder: float32 (n, D) -> uint8 (n, M) (nearest codeword per sub-space, first minimum wins)."""
+        X = np.ascontiguousarray(vecs, np.float32)
+        if X.ndim != 2 or X.shape[1] != self.M * self.Ds:
+            raise ValueError("vecs must have shape (n, M * Ds)")
+        out = np.empty((X.shape[0], self.M), np.uint8)
+        check(_capi.lib().rii_encode(self._h, _ptr(X, C.c_float), X.shape[0], _ptr(out, C.c_uint8)))
+        return out
+
     def set_option(self, name, value):
         check(_capi.lib().rii_set_option(self._h, name.encode(), int(value)))
 

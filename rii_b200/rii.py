@@ -89,11 +89,17 @@ class Rii(object):
         self.threshold = estimate_best_threshold_function(
             e=self, queries=self.fine_quantizer.decode(self.codes[:min(100, self.N)]))
 
-    def add(self, vecs, update_posting_lists="auto"):
+    def add(self, vecs, update_posting_lists="auto", gpu_encode=False):
+        """rii/rii.py:152-186.  gpu_encode=True (opt-in, not in the reference) encodes on the GPU (rii_encode) instead
+        of fine_quantizer.encode; same nearest-codeword rule, rounding may differ from nanopq on exact ties."""
         assert vecs.ndim == 2
         assert vecs.dtype == np.float32
-        self.impl_cpp.add_codes(self.fine_quantizer.encode(vecs),
-                                self._resolve_update_posting_lists_flag(update_posting_lists))
+        if gpu_encode:
+            v = self.fine_quantizer.rotate(vecs) if _pq.is_opq(self.fine_quantizer) else vecs
+            codes = self.impl_cpp.encode(v)
+        else:
+            codes = self.fine_quantizer.encode(vecs)
+        self.impl_cpp.add_codes(codes, self._resolve_update_posting_lists_flag(update_posting_lists))
 
     def add_configure(self, vecs, nlist=None, iter=5):
         self.add(vecs=vecs, update_posting_lists=False)
