@@ -18,7 +18,7 @@ __device__ __forceinline__ float sqdiff(float a, float b)
     return __fmul_rn(t, t);
 }
 
-__device__ float l2sqr_lanes(const float *__restrict__ x, const float *__restrict__ y, int d, int variant)
+__device__ __noinline__ float l2sqr_lanes(const float *__restrict__ x, const float *__restrict__ y, int d, int variant)
 {
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
     if (d >= 8) {
@@ -923,6 +923,7 @@ struct SkewArgs {
     const float *T;            // (B, 32*Ks), or null: build the table in-kernel from Q / cw (K1 fused)
     const float *Q;            // (B, 32*Ds)
     const float *cw;           // (32, Ks, Ds)
+    const float *cw_t;         // (Ks, 32, Ds): the same codewords, sub-space fastest (coalesced in-kernel table build)
     int Ds, variant;
     const uint8_t *codes;      // linear: (N, 32) by id.  IVF: (N, 32) list-ordered copy (row p <-> ids[p])
     long long N;               // linear: rows of the shard
@@ -1007,10 +1008,11 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
 // end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
 #define SK_EMIT(ID)                                                                                           \
     {                                                                                                         \
+        thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                                           \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
-            warp_push(wt, cta_thr, lane, accA, (uint32_t)(ID), pre_);                                         \
-            thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);                            \
+            const uint32_t id_ = IVF ? (pre_ ? cand_id(ID) : 0u) : (ID);                                      \
+            warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
         }                                                                                                     \
         accA = accB;                                                                                          \
         accB = 0.f;                                                                                           \
@@ -1034,32 +1036,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     const int b = blockIdx.y;
     int J = 0;
     if constexpr (IVF) J = (a.flags[b] != 0) ? 0 : a.J[b];
-    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
-        if (a.T) {
-            const float *T = a.T + (size_t)b * 32 * a.Ks;
-#pragma unroll 8
-            for (int e = threadIdx.x; e < 256 * 64; e += NW * 32) {
-                int ks = e >> 6, c = e & 63;
-                lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
-            }
-        } else {
-            // K1 fused (src/rii.h:361-373): entry (m = lane, ks) -> both columns m and m + 32 of row ks; the
-            // lane's query sub-vector stays in registers, stores are bank-conflict free.
-            const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
-            float qv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (a.Ds <= 4)
-                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
-#pragma unroll
-            for (int ks = wid; ks < 256; ks += NW) {
-                float v = 0.f;
-                if (ks < a.Ks) {
-                    const float *c = a.cw + ((size_t)lane * a.Ks + ks) * a.Ds;
-                    v = a.Ds <= 4 ? l2sqr_small(qv, c, a.Ds) : l2sqr_lanes(qm, c, a.Ds, a.variant);
-                }
-                lut2[ks * 64 + lane] = v;
-                lut2[ks * 64 + lane + 32] = v;
-            }
-        }
+    {
         if constexpr (IVF)
             for (int j = threadIdx.x; j < J; j += blockDim.x) {
                 s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
@@ -1067,8 +1044,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             }
         if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
     }
-    __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+    __syncthreads();  // plan (IVF) and threshold are visible; the table is built after the first tile is in flight
+
     // this warp's slice of the candidate space: [base, base + cnt)
     const long long total = IVF ? (J ? (long long)s_cum[J - 1] : 0) : a.N;
     const long long per_cta = ((total + gridDim.x - 1) / gridDim.x + NW * SK_TILE_ROWS - 1) / (NW * SK_TILE_ROWS) *
@@ -1134,23 +1111,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.commit_group;");
     };
-    // IVF: posting-list ids of this lane's SK_J candidates of tile n (plain loads issued one tile ahead of their
-    // first use, so the survivors' (distance, id) keys never wait on a dependent global load).
-    int seg0 = 0;  // segment of the lane's first candidate of the previous fetch (candidates advance by 128 per tile)
-    int idc[SK_J], idn[SK_J];
-#pragma unroll
-    for (int j = 0; j < SK_J; ++j) idc[j] = idn[j] = 0;
-    auto fetch_ids = [&](int n, int (&dst)[SK_J]) {
-        int c = (int)base + n * SK_TILE_ROWS + SK_J * lane;
-        const int cend = (int)end;
-        if (c < cend) while (s_cum[seg0] <= c) ++seg0;
-        int seg = seg0;
-#pragma unroll
-        for (int j = 0; j < SK_J; ++j, ++c) {
-            const bool ok = c < cend;
-            if (ok) while (s_cum[seg] <= c) ++seg;
-            dst[j] = ok ? __ldg(a.ids + s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) : 0;
+    // IVF: posting-list id of flattened candidate c (survivors only)
+    auto cand_id = [&](uint32_t c) -> uint32_t {
+        if (c >= (uint32_t)total) return 0u;
+        int lo = 0, hi = J - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_cum[mid] > (int)c) hi = mid; else lo = mid + 1;
         }
+        return (uint32_t)__ldg(a.ids + s_off[lo] + ((int)c - (lo ? s_cum[lo - 1] : 0)));
     };
 
     WarpTopk wt;
@@ -1162,20 +1131,51 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
-        if constexpr (IVF) {
-            issue_tile_seg(0);
-            fetch_ids(0, idc);
+        if constexpr (IVF) issue_tile_seg(0);
+        else issue_tile(0);
+    }
+    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
+        if (a.T) {
+            const float *T = a.T + (size_t)b * 32 * a.Ks;
+#pragma unroll 8
+            for (int e = threadIdx.x; e < 256 * 64; e += NW * 32) {
+                int ks = e >> 6, c = e & 63;
+                lut2[e] = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+            }
         } else {
-            issue_tile(0);
+            // K1 fused (src/rii.h:361-373): entry (m = lane, ks) -> both columns m and m + 32 of row ks; the
+            // lane's query sub-vector stays in registers, codewords come from the sub-space-fastest copy (one
+            // contiguous 32*Ds-float row per ks), stores are bank-conflict free.
+            const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
+            if (a.Ds <= 4) {
+                float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+#pragma unroll 8
+                for (int ks = wid; ks < 256; ks += NW) {
+                    float v = 0.f;
+                    if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds);
+                    lut2[ks * 64 + lane] = v;
+                    lut2[ks * 64 + lane + 32] = v;
+                }
+            } else {
+#pragma unroll 1
+                for (int ks = wid; ks < 256; ks += NW) {
+                    float v = 0.f;
+                    if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds, a.variant);
+                    lut2[ks * 64 + lane] = v;
+                    lut2[ks * 64 + lane + 32] = v;
+                }
+            }
         }
     }
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
-    uint32_t thr_hi = 0xffffffffu;  // cached distance part of the CTA threshold (stale == merely less strict)
+    uint32_t thr_hi;  // distance part of the CTA threshold, re-read from shared memory at every emission
     // local index of the candidate whose distance completes at the end of the current block: it started one
     // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
     uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
-    int last_id = 0;
 #pragma unroll 1
     for (int n = 0; n < ntiles; ++n) {
         if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
@@ -1187,36 +1187,26 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.wait_group 0;");  // tile n has landed
         __syncwarp();                            // rows were written by other lanes of the warp
-        thr_hi = (uint32_t)(*reinterpret_cast<volatile u64 *>(cta_thr) >> 32);
         const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
+        SK_EMIT((uint32_t)(base + eloc))
         eloc += SK_TILE_ROWS - SK_J + 1;
         __syncwarp();  // the other half's last reader finished with this block
         if (n + 1 < ntiles) {
-            if constexpr (IVF) {
-                issue_tile_seg(n + 1);
-                fetch_ids(n + 1, idn);
-            } else {
-                issue_tile(n + 1);
-            }
+            if constexpr (IVF) issue_tile_seg(n + 1);
+            else issue_tile(n + 1);
         }
 #pragma unroll
         for (int i = 1; i < SK_J; ++i) {
             SK_BLOCK(rbw + 32 * i)
-            SK_EMIT(IVF ? (uint32_t)idc[i - 1] : (uint32_t)(base + eloc))
+            SK_EMIT((uint32_t)(base + eloc))
             eloc += 1;
-        }
-        if constexpr (IVF) {
-            last_id = idc[SK_J - 1];
-#pragma unroll
-            for (int j = 0; j < SK_J; ++j) idc[j] = idn[j];
         }
     }
     if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
         const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
         SK_BLOCK(rbw)
-        SK_EMIT(IVF ? (uint32_t)last_id : (uint32_t)(base + eloc))
+        SK_EMIT((uint32_t)(base + eloc))
     }
     warp_compact(wt, cta_thr, lane);
     __syncthreads();

@@ -108,6 +108,7 @@ struct rii_index {
     cudaStream_t stream = nullptr;
 
     float *d_cw = nullptr;
+    float *d_cw_t = nullptr;  // (Ks, M, Ds) copy of the codewords: sub-space fastest (coalesced in-kernel table build)
     float *d_Dm = nullptr;
     uint8_t *d_codes = nullptr;
     DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
@@ -464,7 +465,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 out.partial = h->partial.as<u64>();
             }
             SkewArgs sa{};
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
             Prof pr(h, st, PK_SCAN_LINEAR);
@@ -586,7 +587,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
                 out.partial = h->partial.as<u64>();
             }
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
@@ -736,6 +737,14 @@ int rii_create(const float *codewords, int M, int Ks, int Ds, int verbose, int d
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cw, (size_t)M * Ks * Ds * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cw, codewords, (size_t)M * Ks * Ds * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cw_t, (size_t)M * Ks * Ds * sizeof(float));
+    if (e == cudaSuccess) {
+        std::vector<float> t((size_t)M * Ks * Ds);
+        for (int m = 0; m < M; ++m)
+            for (int ks = 0; ks < Ks; ++ks)
+                for (int i = 0; i < Ds; ++i) t[((size_t)ks * M + m) * Ds + i] = codewords[((size_t)m * Ks + ks) * Ds + i];
+        e = cudaMemcpy(h->d_cw_t, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         delete h;
         return fail(RII_ERR_CUDA, std::string("rii_create: ") + cudaGetErrorString(e));
@@ -756,6 +765,7 @@ int rii_destroy(rii_index_t *h)
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
         b->release();
     if (h->d_cw) cudaFree(h->d_cw);
+    if (h->d_cw_t) cudaFree(h->d_cw_t);
     if (h->d_Dm) cudaFree(h->d_Dm);
     if (h->d_codes) cudaFree(h->d_codes);
     if (h->stream) cudaStreamDestroy(h->stream);
