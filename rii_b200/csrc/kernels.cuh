@@ -448,8 +448,18 @@ __global__ void __launch_bounds__(RII_THREADS) k_coarse_rank(CoarseArgs a)
         load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
     } else {  // K1 fused: T[m][ks] straight into shared memory (codewords are read coalesced)
         const float *q = a.Q + (size_t)b * a.M * a.Ds;
-        for (int e = threadIdx.x; e < a.M * a.Ks; e += RII_THREADS)
-            s.lut[e] = l2sqr_lanes(q + (size_t)(e / a.Ks) * a.Ds, a.cw + (size_t)e * a.Ds, a.Ds, a.variant);
+        if (a.Ds <= 4) {  // every BASELINE shape: loads of 8 entries in flight per thread
+#pragma unroll 8
+            for (int e = threadIdx.x; e < a.M * a.Ks; e += RII_THREADS) {
+                const float *qm = q + (size_t)(e / a.Ks) * a.Ds;
+                float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+                s.lut[e] = l2sqr_small(qv, a.cw + (size_t)e * a.Ds, a.Ds);
+            }
+        } else {
+            for (int e = threadIdx.x; e < a.M * a.Ks; e += RII_THREADS)
+                s.lut[e] = l2sqr_lanes(q + (size_t)(e / a.Ks) * a.Ds, a.cw + (size_t)e * a.Ds, a.Ds, a.variant);
+        }
     }
     s.tk.init();
     for (int pos = 0; pos < a.nlist; pos += RII_THREADS) {
@@ -1008,11 +1018,12 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
 // end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
 #define SK_EMIT(ID)                                                                                           \
     {                                                                                                         \
-        thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                                           \
+        if constexpr (IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                        \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
             const uint32_t id_ = IVF ? (pre_ ? cand_id(ID) : 0u) : (ID);                                      \
             warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
+            thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                                       \
         }                                                                                                     \
         accA = accB;                                                                                          \
         accB = 0.f;                                                                                           \
@@ -1172,7 +1183,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     float accA = 0.f, accB = 0.f;
     uint32_t xprev = 0;
-    uint32_t thr_hi;  // distance part of the CTA threshold, re-read from shared memory at every emission
+    // distance part of the CTA threshold: long linear scans re-read it once per tile and after every push (a stale
+    // value is merely less strict); the short per-query IVF scans re-read it at every emission
+    uint32_t thr_hi = 0xffffffffu;
     // local index of the candidate whose distance completes at the end of the current block: it started one
     // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
     uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
@@ -1187,6 +1200,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         asm volatile("cp.async.wait_group 0;");  // tile n has landed
         __syncwarp();                            // rows were written by other lanes of the warp
+        if constexpr (!IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
         const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
         SK_BLOCK(rbw)
         SK_EMIT((uint32_t)(base + eloc))
