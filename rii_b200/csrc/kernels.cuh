@@ -392,10 +392,11 @@ struct PlanArgs {
 
 // f / pre / loc are indexed by RANK j (0..w_eff): (filtered or global) length of the j-th ranked list, the part
 // of it held by lower ranks (null: 0) and the part held locally (null: subset mode, counts are local already).
-__device__ void make_plan(const PlanArgs &p, int b, const int *f_by_rank, const int *pre_by_rank, const int *loc_by_rank)
+__device__ void make_plan(const PlanArgs &p, int b, const int *f_by_rank, const int *pre_by_rank, const int *loc_by_rank,
+                          int *cum_out = nullptr)
 {
-    // single thread over <= w_eff entries that the caller staged (shared memory in the fused coarse kernel)
-    int *cum = p.cum + (size_t)b * p.w_eff;
+    // single thread over <= w_eff entries that the caller staged (shared memory in the fused kernels)
+    int *cum = cum_out ? cum_out : p.cum + (size_t)b * p.w_eff;
     long long P = 0;
     int J = 0, flag = 0, local = 0;
     bool done = false;
@@ -941,7 +942,10 @@ struct SkewArgs {
     const int *ids;
     const int *ranked, *cum, *J, *flags;  // IVF plan
     int w_eff;
-    int Ks, k, cap;            // cap = per-warp key capacity (power of two >= k + 32)
+    int Ks, k, cap;            // cap = per-warp key capacity (power of two >= max(k, w_eff) + 32)
+    const uint8_t *centers;    // IVF fused: (nlist, 32) coarse centers, or null (plan comes from a separate k_coarse_rank)
+    int nlist;
+    PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)
 };
@@ -1021,7 +1025,7 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
         if constexpr (IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                        \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
-            const uint32_t id_ = IVF ? (pre_ ? cand_id(ID) : 0u) : (ID);                                      \
+            const uint32_t id_ = segm ? (pre_ ? cand_id(ID) : 0u) : (ID);                                     \
             warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
             thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                                       \
         }                                                                                                     \
@@ -1029,11 +1033,33 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
         accB = 0.f;                                                                                           \
     }
 
+// bitonic sort of P (power of two) keys in shared memory by ONE warp (warp barriers only)
+__device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
+{
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    u64 x = k[i], y = k[ixj];
+                    bool up = (i & kk) == 0;
+                    if ((x > y) == up) { k[i] = y; k[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+// Phases: IVF launches with a.centers != null run TWO passes of the same engine in one CTA -- pass 0 ranks the
+// coarse centers (a plain linear scan over the (nlist, 32) center table with k = w_eff; K4, src/rii.h:259-280),
+// the plan is made in shared memory (make_plan), pass 1 scans the planned posting-list segments (K5).  One table
+// build, one launch, no round trip of ranked lists / plans through HBM.
 template <int NW, bool IVF>
 __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [lut2 64 KB][NW regions][NW key buffers][cta_thr][s_off, s_cum (IVF)]
+    // layout: [lut2 64 KB][NW regions][NW key buffers][cta_thr][IVF: s_off i64[w] | s_cum, s_f, s_pre, s_loc i32[w] | s_plan i32[4]]
     float *lut2 = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
@@ -1043,29 +1069,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
     u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
     long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8);
-    int *s_cum = reinterpret_cast<int *>(s_off + (IVF ? a.w_eff : 0));
+    const int wq = IVF ? a.w_eff : 0;
+    int *s_cum = reinterpret_cast<int *>(s_off + wq);
+    int *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;  // s_plan: [J, flags]
     const int b = blockIdx.y;
+    const bool fused = IVF && a.centers != nullptr;
     int J = 0;
-    if constexpr (IVF) J = (a.flags[b] != 0) ? 0 : a.J[b];
-    {
-        if constexpr (IVF)
+    if constexpr (IVF) {
+        if (!fused) {
+            J = (a.flags[b] != 0) ? 0 : a.J[b];
             for (int j = threadIdx.x; j < J; j += blockDim.x) {
                 s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
                 s_off[j] = a.offsets[a.ranked[(size_t)b * a.w_eff + j]];
             }
-        if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+        }
     }
-    __syncthreads();  // plan (IVF) and threshold are visible; the table is built after the first tile is in flight
-
-    // this warp's slice of the candidate space: [base, base + cnt)
-    const long long total = IVF ? (J ? (long long)s_cum[J - 1] : 0) : a.N;
-    const long long per_cta = ((total + gridDim.x - 1) / gridDim.x + NW * SK_TILE_ROWS - 1) / (NW * SK_TILE_ROWS) *
-                              (NW * SK_TILE_ROWS);
-    const long long base = (long long)blockIdx.x * per_cta + (long long)wid * (per_cta / NW);
-    long long end = base + per_cta / NW;
-    if (end > total) end = total;
-    const int cnt = end > base ? (int)(end - base) : 0;
-    const int ntiles = (cnt + SK_TILE_ROWS - 1) / SK_TILE_ROWS;
+    if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+    __syncthreads();  // plan (unfused IVF) and threshold are visible; the table is built after the first tile is in flight
 
     const uint32_t region = SK_LUT_BYTES + wid * SK_WARP_BYTES;
     const uint32_t myreg = region + lane * SK_REGION_BYTES;
@@ -1076,9 +1096,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     // linear: destination of 16-byte chunk (it, lane): rows are dealt SK_J per lane
     const uint32_t cp_dst = region + (lane >> 3) * SK_REGION_BYTES + 32 + (lane & 7) * 16;
 
-    auto issue_tile = [&](int n) {  // linear
+    // per-pass state
+    const uint8_t *pc = a.codes;   // row table of the pass
+    long long total = 0, base = 0, end = 0;
+    int cnt = 0, ntiles = 0;
+    int segw = 0;
+    WarpTopk wt;
+    wt.keys = wkeys;
+    wt.cap = capw;
+    wt.k = a.k;
+    wt.count = 0;
+
+    auto set_range = [&](long long tot, int nsplit, int split) {  // this warp's slice [base, base + cnt) of [0, tot)
+        total = tot;
+        const long long per_cta = ((tot + nsplit - 1) / nsplit + NW * SK_TILE_ROWS - 1) / (NW * SK_TILE_ROWS) * (NW * SK_TILE_ROWS);
+        base = (long long)split * per_cta + (long long)wid * (per_cta / NW);
+        end = base + per_cta / NW;
+        if (end > tot) end = tot;
+        cnt = end > base ? (int)(end - base) : 0;
+        ntiles = (cnt + SK_TILE_ROWS - 1) / SK_TILE_ROWS;
+    };
+    auto issue_tile = [&](int n) {  // rows [base + 128 n, +128) of the contiguous table pc
         const long long r0 = base + (long long)n * SK_TILE_ROWS;
-        const uint8_t *g = a.codes + r0 * 32 + lane * 16;
+        const uint8_t *g = pc + r0 * 32 + lane * 16;
         const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
         if (r0 + SK_TILE_ROWS <= end) {  // full tile: 8 x 512 contiguous bytes per warp, immediates only
 #pragma unroll
@@ -1089,14 +1129,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
                 const int nbytes = r0 + it * 16 + (lane >> 1) < end ? 16 : 0;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
-                             "l"(nbytes ? g + it * 512 : a.codes), "r"(nbytes));
+                             "l"(nbytes ? g + it * 512 : pc), "r"(nbytes));
             }
         }
         asm volatile("cp.async.commit_group;");
     };
-    // IVF: tile n = flattened candidates [c0, c0 + 128) of the plan; segment j covers [cum[j-1], cum[j]) and starts
-    // at row s_off[j] of the list-ordered code copy.  segw = segment of c0 (warp-uniform, carried along).
-    int segw = 0;
+    // IVF pass 1: tile n = flattened candidates [c0, c0 + 128) of the plan; segment j covers [cum[j-1], cum[j]) and
+    // starts at row s_off[j] of the list-ordered code copy.  segw = segment of c0 (warp-uniform, carried along).
     auto issue_tile_seg = [&](int n) {
         const int c0 = (int)base + n * SK_TILE_ROWS;
         const int cend = (int)end;
@@ -1104,7 +1143,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         const int seg_lo = segw ? s_cum[segw - 1] : 0;
         const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
         if (c0 + SK_TILE_ROWS <= cend && c0 + SK_TILE_ROWS <= s_cum[segw]) {  // one segment, full tile: pure stream
-            const uint8_t *g = a.codes + (size_t)(s_off[segw] + (c0 - seg_lo)) * 32 + lane * 16;
+            const uint8_t *g = pc + (size_t)(s_off[segw] + (c0 - seg_lo)) * 32 + lane * 16;
 #pragma unroll
             for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
@@ -1115,14 +1154,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
                 const bool ok = c < cend;
                 int seg = segw;
                 if (ok) while (s_cum[seg] <= c) ++seg;
-                const uint8_t *g = a.codes + (size_t)(s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) * 32 + (lane & 1) * 16;
+                const uint8_t *g = pc + (size_t)(s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) * 32 + (lane & 1) * 16;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
-                             "l"(ok ? g : a.codes), "r"(ok ? 16 : 0));
+                             "l"(ok ? g : pc), "r"(ok ? 16 : 0));
             }
         }
         asm volatile("cp.async.commit_group;");
     };
-    // IVF: posting-list id of flattened candidate c (survivors only)
+    // IVF pass 1: posting-list id of flattened candidate c (survivors only)
     auto cand_id = [&](uint32_t c) -> uint32_t {
         if (c >= (uint32_t)total) return 0u;
         int lo = 0, hi = J - 1;
@@ -1133,16 +1172,22 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         return (uint32_t)__ldg(a.ids + s_off[lo] + ((int)c - (lo ? s_cum[lo - 1] : 0)));
     };
 
-    WarpTopk wt;
-    wt.keys = wkeys;
-    wt.cap = capw;
-    wt.k = a.k;
-    wt.count = 0;
+    // ---- pass setup: the first tile goes out before the table is built ---------------------------------
+    bool segm = IVF && !fused;  // true: pass over planned posting-list segments; false: plain row range
+    if (fused) {
+        pc = a.centers;
+        wt.k = a.w_eff;
+        set_range(a.nlist, 1, 0);
+    } else if (IVF) {
+        set_range(J ? (long long)s_cum[J - 1] : 0, gridDim.x, blockIdx.x);
+    } else {
+        set_range(a.N, gridDim.x, blockIdx.x);
+    }
     // zero the carry row of this lane (read by the lagging steps of the very first block)
     *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
-        if constexpr (IVF) issue_tile_seg(0);
+        if (segm) issue_tile_seg(0);
         else issue_tile(0);
     }
     {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
@@ -1180,50 +1225,106 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
     }
     __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
-    float accA = 0.f, accB = 0.f;
-    uint32_t xprev = 0;
-    // distance part of the CTA threshold: long linear scans re-read it once per tile and after every push (a stale
-    // value is merely less strict); the short per-query IVF scans re-read it at every emission
-    uint32_t thr_hi = 0xffffffffu;
-    // local index of the candidate whose distance completes at the end of the current block: it started one
-    // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
-    uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
+    if (dbg && threadIdx.x == 0 && !fused) dbg[1] = clock64();
+
+    const int npass = fused ? 2 : 1;
 #pragma unroll 1
-    for (int n = 0; n < ntiles; ++n) {
-        if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
-            unsigned char *reg = smem_raw + myreg;
-            uint4 x0 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32);
-            uint4 x1 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32 + 16);
-            *reinterpret_cast<uint4 *>(reg) = x0;
-            *reinterpret_cast<uint4 *>(reg + 16) = x1;
+    for (int pass = 0; pass < npass; ++pass) {
+        if (pass == 1) {
+            // ---- between the passes: merge the warps' center lists, rank, plan (all in shared memory) -----------
+            // every warp list is sorted and cta_thr <= the w-th key of some warp, i.e. an upper bound of the global
+            // w-th key: only keys <= cta_thr can be in the global top-w
+            u64 *pool = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES);  // the regions are idle now
+            int *pool_n = s_plan + 2;
+            if (threadIdx.x == 0) *pool_n = 0;
+            __syncthreads();
+            {
+                const u64 thr = *cta_thr;
+                for (int i = lane; i < wt.count; i += 32) {
+                    const u64 key = wt.keys[i];
+                    if (key <= thr) pool[atomicAdd(pool_n, 1)] = key;
+                }
+            }
+            __syncthreads();
+            if (wid == 0) {
+                const int np = *pool_n;
+                const int P = next_pow2(np < 2 ? 2 : np);
+                for (int i = np + lane; i < P; i += 32) pool[i] = RII_KEY_MAX;
+                warp_sort_smem(pool, P, lane);
+                int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
+                for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist == number of pooled keys or more
+                    const int no = (int)key_id(pool[j]);
+                    ranked_g[j] = no;
+                    s_f[j] = a.plan.glob_len[no];
+                    s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
+                    s_loc[j] = a.plan.loc_len[no];
+                    s_off[j] = a.offsets[no];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    make_plan(a.plan, b, s_f, s_pre, s_loc, s_cum);
+                    s_plan[0] = a.plan.flags[b] != 0 ? 0 : a.plan.J[b];
+                    *cta_thr = RII_KEY_MAX;
+                }
+            }
+            __syncthreads();
+            if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+            J = s_plan[0];
+            pc = a.codes;
+            segm = true;
+            segw = 0;
+            wt.k = a.k;
+            wt.count = 0;
+            set_range(J ? (long long)s_cum[J - 1] : 0, 1, 0);
+            *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
+            if (ntiles > 0) issue_tile_seg(0);
         }
-        asm volatile("cp.async.wait_group 0;");  // tile n has landed
-        __syncwarp();                            // rows were written by other lanes of the warp
-        if constexpr (!IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
-        const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
-        SK_BLOCK(rbw)
-        SK_EMIT((uint32_t)(base + eloc))
-        eloc += SK_TILE_ROWS - SK_J + 1;
-        __syncwarp();  // the other half's last reader finished with this block
-        if (n + 1 < ntiles) {
-            if constexpr (IVF) issue_tile_seg(n + 1);
-            else issue_tile(n + 1);
-        }
-#pragma unroll
-        for (int i = 1; i < SK_J; ++i) {
-            SK_BLOCK(rbw + 32 * i)
+
+        float accA = 0.f, accB = 0.f;
+        uint32_t xprev = 0;
+        // distance part of the CTA threshold: long linear scans re-read it once per tile and after every push (a
+        // stale value is merely less strict); the short per-query IVF passes re-read it at every emission
+        uint32_t thr_hi = 0xffffffffu;
+        // local index of the candidate whose distance completes at the end of the current block: it started one
+        // block earlier, so the first block completes nothing (index "-1" of the previous tile: fails eloc < cnt)
+        uint32_t eloc = (uint32_t)(SK_J * lane + SK_J - 1 - SK_TILE_ROWS);
+#pragma unroll 1
+        for (int n = 0; n < ntiles; ++n) {
+            if ((n & 1) == 0 && n > 0) {  // entering half A again: the stream continues from B's last row via the carry row
+                unsigned char *reg = smem_raw + myreg;
+                uint4 x0 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32);
+                uint4 x1 = *reinterpret_cast<uint4 *>(reg + 32 + (2 * SK_J - 1) * 32 + 16);
+                *reinterpret_cast<uint4 *>(reg) = x0;
+                *reinterpret_cast<uint4 *>(reg + 16) = x1;
+            }
+            asm volatile("cp.async.wait_group 0;");  // tile n has landed
+            __syncwarp();                            // rows were written by other lanes of the warp
+            if constexpr (!IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
+            const uint32_t rbw = rb + 4 * ((n & 1) * SK_HALF_WORDS);
+            SK_BLOCK(rbw)
             SK_EMIT((uint32_t)(base + eloc))
-            eloc += 1;
+            eloc += SK_TILE_ROWS - SK_J + 1;
+            __syncwarp();  // the other half's last reader finished with this block
+            if (n + 1 < ntiles) {
+                if (segm) issue_tile_seg(n + 1);
+                else issue_tile(n + 1);
+            }
+#pragma unroll
+            for (int i = 1; i < SK_J; ++i) {
+                SK_BLOCK(rbw + 32 * i)
+                SK_EMIT((uint32_t)(base + eloc))
+                eloc += 1;
+            }
         }
+        if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
+            const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
+            SK_BLOCK(rbw)
+            SK_EMIT((uint32_t)(base + eloc))
+        }
+        warp_compact(wt, cta_thr, lane);
+        __syncthreads();
     }
-    if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
-        const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
-        SK_BLOCK(rbw)
-        SK_EMIT((uint32_t)(base + eloc))
-    }
-    warp_compact(wt, cta_thr, lane);
-    __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();
     {   // CTA merge of the (sorted) warp lists, reusing the lut2 area for the keys
         __shared__ int s_cnt[NW];
@@ -1243,19 +1344,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
                     o += s_cnt[w2];
                 }
                 for (int i = tot + lane; i < P; i += 32) mk[i] = RII_KEY_MAX;
-                __syncwarp();
-                for (int kk = 2; kk <= P; kk <<= 1)
-                    for (int j = kk >> 1; j > 0; j >>= 1) {
-                        for (int i = lane; i < P; i += 32) {
-                            int ixj = i ^ j;
-                            if (ixj > i) {
-                                u64 x = mk[i], y = mk[ixj];
-                                bool up = (i & kk) == 0;
-                                if ((x > y) == up) { mk[i] = y; mk[ixj] = x; }
-                            }
-                        }
-                        __syncwarp();
-                    }
+                warp_sort_smem(mk, P, lane);
                 const int n = tot < a.k ? tot : a.k;
                 if (a.out.final) {
                     for (int i = lane; i < n; i += 32) {
@@ -1288,5 +1377,5 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)
 {
     return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (size_t)nw * capw * 8 + 16 + 64 +
-           (ivf ? (size_t)w_eff * 12 + 16 : 0);
+           (ivf ? (size_t)w_eff * 24 + 32 : 0);
 }

@@ -126,6 +126,7 @@ struct rii_index {
 
     DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
     int opt_debug_clocks = 0;
+    int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernel, 2 skewed conflict-free kernel (M == 32 only)
 
     long long n_total() const { return N_total >= 0 ? N_total : N; }
@@ -523,7 +524,19 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         LAUNCHED();
         CKR(h->filt.ensure((size_t)B * w_eff * 4));
     }
-    {
+    // v2 (skewed, bank-conflict-free) posting-list scan when it applies: M == 32, no target_ids, small topk, plan
+    // fits shared memory.  With one CTA per query (parts == 1) the coarse ranking and the plan are fused into the
+    // same kernel (two passes of one engine): no k_coarse_rank launch at all.
+    const int capw2 = std::max(64, next_pow2(std::max(c.topk, w_eff) + 32));
+    const int nw2 = skew_pick_nw(true, capw2, w_eff);
+    const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
+    const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
+    if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
+    const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
+                                                           std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
+                                : 0;
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse;
+    if (!fuse) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
         a.centers = h->centers.as<uint8_t>();
@@ -572,16 +585,9 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         a.w_eff = w_eff;
         a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
         a.out = out;
-        // v2 (skewed, bank-conflict-free) when it applies: M == 32, no target_ids, small topk, plan fits smem
-        const int capw2 = std::max(64, next_pow2(c.topk + 32));
-        const int nw2 = skew_pick_nw(true, capw2, w_eff);
-        const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
-        const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-        if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
         SkewArgs sa{};
         if (use_v2) {
-            parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
-                                             std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)));
+            parts = parts_v2;
             out.final = parts == 1;
             if (!out.final) {
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
@@ -590,6 +596,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
+            if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
         }
         if (!use_v2) {
@@ -888,6 +895,10 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
     if (!strcmp(name, "scan_kernel")) {
         if (value < 0 || value > 2) return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 or 2");
         h->opt_scan_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "fuse_coarse")) {
+        h->opt_fuse_coarse = value != 0;
         return 0;
     }
     if (!strcmp(name, "debug_clocks")) {

@@ -422,3 +422,27 @@ def test_gpu_pq_encoder():
     e2 = rii.Rii(fine_quantizer=codec)
     e2.add(X, gpu_encode=True)
     assert np.array_equal(e2.codes, got)
+
+
+def test_fused_coarse_plan_scan_equals_unfused():
+    """One-CTA-per-query batches run coarse ranking + plan + posting-list scan in ONE kernel (two passes of the
+    skewed engine); results must equal the unfused pipeline (k_coarse_rank + k_scan_skew32) and the oracle,
+    including plans that end mid-list, at the w-th list, and the empty result."""
+    D, M, Ks, N, nlist = 128, 32, 256, 80000, 200
+    cw, codes, Q = synth(D, M, Ks, N, 160, seed=77)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    Qb = np.ascontiguousarray(Q)
+    for topk, L in [(1, 400), (7, 3000), (96, 97), (3, N), (20, 12345), (1, 1)]:
+        e.set_option("fuse_coarse", 1)
+        f = e.query_batch(Qb, topk, L=L, method="ivf")
+        e.set_option("fuse_coarse", 0)
+        u = e.query_batch(Qb, topk, L=L, method="ivf")
+        assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1])), (topk, L)
+        for b in range(0, 160, 23):
+            exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
+            n = int(f[2][b])
+            assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "fused k=%d L=%d b=%d" % (topk, L, b))
+    e.set_option("fuse_coarse", 1)
