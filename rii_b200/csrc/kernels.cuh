@@ -943,6 +943,7 @@ struct SkewArgs {
     const int *ranked, *cum, *J, *flags;  // IVF plan
     int w_eff;
     int Ks, k, cap;            // cap = per-warp key capacity (power of two >= max(k, w_eff) + 32)
+    uint32_t smem_bytes;       // dynamic shared memory of the launch (the kernel lays its regions out around the table)
     const uint8_t *centers;    // IVF fused: (nlist, 32) coarse centers, or null (plan comes from a separate k_coarse_rank)
     int nlist;
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
@@ -994,29 +995,36 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
     if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
 }
 
-// one lookup step: addr = (code byte << 8) | lane column offset; v = lut2[addr + 4 t]; (t < l ? A : B) += v
+// one lookup step.  The table sits at the 64 KB-aligned ABSOLUTE shared address 0x10000, so the byte-permute of
+// (code word, colreg = 0x00010000 | lane column offset) IS the lookup address: 0x10000 | ks << 8 | col; the step
+// index goes into the load's immediate.  (t < l ? A : B) += v with a predicated add pair.
 #define SK_STEP(W, BYTE, T)                                                                                   \
     {                                                                                                         \
-        uint32_t ad_ = __byte_perm(W, colreg, 0x7504 | ((BYTE) << 4));                                        \
-        float v_ = *reinterpret_cast<const float *>(smem_raw + ad_ + 4 * (T));                                \
+        const uint32_t ad_ = __byte_perm(W, colreg, 0x7604 | ((BYTE) << 4));                                  \
+        float v_;                                                                                             \
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v_) : "r"(ad_), "n"(4 * (T)));                      \
         asm("{.reg .pred p; setp.gt.s32 p, %2, %3; @p add.rn.f32 %0, %0, %4; @!p add.rn.f32 %1, %1, %4;}"   \
             : "+f"(accA), "+f"(accB)                                                                          \
-            : "r"(lane), "r"(T), "f"(v_));                                                                    \
+            : "r"(lane), "n"(T), "f"(v_));                                                                    \
     }
 
-// one block = 32 steps = 8 code words of the lane's (lagged) stream, starting at byte offset WOFF
+// 4 steps = one code word of the lane's (lagged) stream
+#define SK_WORD(WOFF, Q)                                                                                      \
+    {                                                                                                         \
+        const uint32_t x_ = *reinterpret_cast<const uint32_t *>(smem_raw + (WOFF) + 4 * (Q));                 \
+        const uint32_t wd_ = __funnelshift_rc(xprev, x_, shift);                                              \
+        xprev = x_;                                                                                           \
+        SK_STEP(wd_, 0, 4 * (Q) + 0)                                                                          \
+        SK_STEP(wd_, 1, 4 * (Q) + 1)                                                                          \
+        SK_STEP(wd_, 2, 4 * (Q) + 2)                                                                          \
+        SK_STEP(wd_, 3, 4 * (Q) + 3)                                                                          \
+    }
+
+// one block = 32 steps = 8 code words starting at byte offset WOFF of the dynamic shared memory
 #define SK_BLOCK(WOFF)                                                                                        \
     {                                                                                                         \
-        _Pragma("unroll") for (int q_ = 0; q_ < 8; ++q_)                                                      \
-        {                                                                                                     \
-            uint32_t x_ = *reinterpret_cast<const uint32_t *>(smem_raw + (WOFF) + 4 * q_);                    \
-            uint32_t wd_ = __funnelshift_rc(xprev, x_, shift);                                                \
-            xprev = x_;                                                                                       \
-            SK_STEP(wd_, 0, 4 * q_ + 0)                                                                       \
-            SK_STEP(wd_, 1, 4 * q_ + 1)                                                                       \
-            SK_STEP(wd_, 2, 4 * q_ + 2)                                                                       \
-            SK_STEP(wd_, 3, 4 * q_ + 3)                                                                       \
-        }                                                                                                     \
+        SK_WORD(WOFF, 0) SK_WORD(WOFF, 1) SK_WORD(WOFF, 2) SK_WORD(WOFF, 3)                                   \
+        SK_WORD(WOFF, 4) SK_WORD(WOFF, 5) SK_WORD(WOFF, 6) SK_WORD(WOFF, 7)                                   \
     }
 
 // end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
@@ -1059,13 +1067,17 @@ template <int NW, bool IVF>
 __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [lut2 64 KB][NW regions][NW key buffers][cta_thr][IVF: s_off i64[w] | s_cum, s_f, s_pre, s_loc i32[w] | s_plan i32[4]]
-    float *lut2 = reinterpret_cast<float *>(smem_raw);
+    // layout (dynamic shared memory, window starts at absolute shared address sbase ~ 1 KB):
+    //   [NW key buffers][cta_thr][IVF: s_off i64[w] | s_cum, s_f, s_pre, s_loc i32[w] | s_plan i32[4]][n_lo regions] ...
+    //   lut2 (64 KB) at ABSOLUTE shared address 0x10000 ... [n_hi regions]
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t lut_off = 0x10000u - smem_base;
+    float *lut2 = reinterpret_cast<float *>(smem_raw + lut_off);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
     long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-    const uint32_t keys_off = SK_LUT_BYTES + NW * SK_WARP_BYTES;
+    const uint32_t keys_off = 0;
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
     u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
     long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8);
@@ -1087,12 +1099,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
     __syncthreads();  // plan (unfused IVF) and threshold are visible; the table is built after the first tile is in flight
 
-    const uint32_t region = SK_LUT_BYTES + wid * SK_WARP_BYTES;
+    const uint32_t lo_reg0 = (uint32_t)(((size_t)NW * capw * 8 + 16 + (IVF ? (size_t)a.w_eff * 24 + 32 : 0) + 15) & ~(size_t)15);
+    const uint32_t hi_reg0 = lut_off + SK_LUT_BYTES;
+    const int n_lo = (int)((lut_off - lo_reg0) / SK_WARP_BYTES);
+    if (n_lo + (int)((a.smem_bytes - hi_reg0) / SK_WARP_BYTES) < NW) __trap();  // host sized the launch wrongly
+    const uint32_t region = wid < n_lo ? lo_reg0 + wid * SK_WARP_BYTES : hi_reg0 + (wid - n_lo) * SK_WARP_BYTES;
     const uint32_t myreg = region + lane * SK_REGION_BYTES;
     const uint32_t rb = myreg + 4 * (8 - (lane >> 2));  // lane stream base with the word part of the lag folded in
     const uint32_t shift = 8 * (4 - (lane & 3));         // funnel shift (32 == no byte lag)
-    const uint32_t colreg = (uint32_t)((32 - lane) * 4); // column byte offset, upper bytes zero
-    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t colreg = 0x00010000u | (uint32_t)((32 - lane) * 4);  // table address 0x10000 | column byte offset
     // linear: destination of 16-byte chunk (it, lane): rows are dealt SK_J per lane
     const uint32_t cp_dst = region + (lane >> 3) * SK_REGION_BYTES + 32 + (lane & 7) * 16;
 
@@ -1234,7 +1249,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             // ---- between the passes: merge the warps' center lists, rank, plan (all in shared memory) -----------
             // every warp list is sorted and cta_thr <= the w-th key of some warp, i.e. an upper bound of the global
             // w-th key: only keys <= cta_thr can be in the global top-w
-            u64 *pool = reinterpret_cast<u64 *>(smem_raw + SK_LUT_BYTES);  // the regions are idle now
+            u64 *pool = reinterpret_cast<u64 *>(smem_raw + hi_reg0);  // the regions are idle now
             int *pool_n = s_plan + 2;
             if (threadIdx.x == 0) *pool_n = 0;
             __syncthreads();
@@ -1336,7 +1351,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         if (tot <= 256) {
             // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
             if (wid == 0) {
-                u64 *mk = reinterpret_cast<u64 *>(smem_raw);
+                u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
                 const int P = next_pow2(tot < 2 ? 2 : tot);
                 int o = 0;
                 for (int w2 = 0; w2 < NW; ++w2) {
@@ -1360,9 +1375,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         } else {
             BlockTopk tk;
             const int mcap = next_pow2(NW * a.k + 1);
-            tk.keys = reinterpret_cast<u64 *>(smem_raw);
-            tk.count = reinterpret_cast<int *>(smem_raw + (size_t)mcap * 8 + 8);
-            tk.thr = reinterpret_cast<u64 *>(smem_raw + (size_t)mcap * 8);
+            tk.keys = reinterpret_cast<u64 *>(smem_raw + lut_off);
+            tk.count = reinterpret_cast<int *>(smem_raw + lut_off + (size_t)mcap * 8 + 8);
+            tk.thr = reinterpret_cast<u64 *>(smem_raw + lut_off + (size_t)mcap * 8);
             tk.cap = mcap;
             tk.k = a.k;
             tk.init();
@@ -1374,6 +1389,18 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     if (dbg && threadIdx.x == 0) dbg[3] = clock64();
 }
 
+// Host-side sizing.  The kernel always gets the maximum dynamic shared memory; what varies is how many warp regions
+// fit below and above the 64 KB table pinned at absolute shared address 0x10000 (the window itself starts at
+// ~1 KB: reserved + static shared memory; both extremes are allowed for).
+#define SK_DYN_SMEM (227 * 1024 - 64)
+static inline int skew_regions_fit(bool ivf, int nw, int capw, int w_eff)
+{
+    const size_t meta = (((size_t)nw * capw * 8 + 16 + (ivf ? (size_t)w_eff * 24 + 32 : 0)) + 15) & ~(size_t)15;
+    const long long lut_off_min = 0x10000 - 2048, lut_off_max = 0x10000 - 1024;
+    const long long n_lo = (lut_off_min - (long long)meta) / SK_WARP_BYTES;
+    const long long n_hi = ((long long)SK_DYN_SMEM - (lut_off_max + SK_LUT_BYTES)) / SK_WARP_BYTES;
+    return (int)((n_lo < 0 ? 0 : n_lo) + (n_hi < 0 ? 0 : n_hi));
+}
 static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)
 {
     return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (size_t)nw * capw * 8 + 16 + 64 +

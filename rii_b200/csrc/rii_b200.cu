@@ -375,7 +375,7 @@ int grow_codes(rii_index *h, long long rows)
 int skew_pick_nw(bool ivf, int capw, int w_eff)
 {
     for (int nw : {16, 14, 12})
-        if (skew_smem_bytes(nw, ivf, capw, w_eff) <= SMEM_MAX) return nw;
+        if (skew_regions_fit(ivf, nw, capw, w_eff) >= nw) return nw;
     return 0;
 }
 
@@ -388,7 +388,7 @@ template <int NW, bool IVF> int launch_skew_t(const SkewArgs &a, int parts, int 
 
 int launch_skew(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
 {
-    const size_t smem = skew_smem_bytes(nw, ivf, a.cap, a.w_eff);
+    const size_t smem = SK_DYN_SMEM;
     if (ivf) {
         if (nw == 16) return launch_skew_t<16, true>(a, parts, B, smem, st);
         if (nw == 14) return launch_skew_t<14, true>(a, parts, B, smem, st);
@@ -470,6 +470,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
             Prof pr(h, st, PK_SCAN_LINEAR);
+            sa.smem_bytes = SK_DYN_SMEM;
             CKR(launch_skew(nw, false, sa, parts, B, st));
         } else {
             CKR(ensure_T());
@@ -606,6 +607,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         {
         Prof pr(h, st, PK_SCAN_IVF);
         if (use_v2) {
+            sa.smem_bytes = SK_DYN_SMEM;
             CKR(launch_skew(nw2, true, sa, parts, B, st));
         } else if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
