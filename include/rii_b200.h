@@ -139,8 +139,9 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 int rii_profile_enable(rii_index_t *h, int on);
 int rii_profile_reset(rii_index_t *h);
 int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches);
-/* With option "debug_clocks" = 1 the v2 scan kernel records clock64() per CTA at [start, table ready, scan done,
- * end]; this copies the (n_ctas, 4) values of the last launch to the host. */
+/* With option "debug_clocks" = 1 the v2 scan kernel records clock64() per CTA: [0] start, [1] ready to scan (table,
+ * and for the fused kernel coarse ranking + plan), [2] scan done, [3] end, [4] table built, [5] coarse pass done,
+ * [6] coarse pool sorted, [7] = pool size; this copies the (n_ctas, 8) values of the last launch to the host. */
 int rii_debug_clocks(rii_index_t *h, int64_t n_ctas, int64_t *out);
 
 #ifdef __cplusplus

@@ -952,30 +952,74 @@ struct SkewArgs {
 };
 
 struct WarpTopk {
-    u64 *keys;   // shared, this warp's buffer (cap keys)
-    int cap, k;
+    u64 *keys;   // shared, this warp's buffer (>= cap keys)
+    int cap, k;  // cap = next_pow2(k + 32): compaction threshold of the current pass
     int count;   // warp-uniform
 };
 
-__device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
+// Bitonic sort of 32*R keys held in registers (element e = r*32 + lane), ascending.  Exchanges at distance >= 32
+// are register-to-register inside a lane, smaller distances are warp shuffles: no shared memory, no barriers.
+// (The shared-memory version took ~145 cycles per compare-exchange round: 16 K cycles for 128 keys, measured with
+// the phase clocks -- profiles/r01_micro_ivf_phase_clocks_*.jsonl.)
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(u64 (&v)[R], int lane)
 {
-    __syncwarp();
-    int n = w.count;
-    int P = next_pow2(n < 2 ? 2 : n);
-    for (int i = n + lane; i < P; i += 32) w.keys[i] = RII_KEY_MAX;
-    __syncwarp();
-    for (int kk = 2; kk <= P; kk <<= 1)
+#pragma unroll
+    for (int kk = 2; kk <= 32 * R; kk <<= 1) {
+#pragma unroll
         for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < P; i += 32) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    u64 a = w.keys[i], b = w.keys[ixj];
-                    bool up = (i & kk) == 0;
-                    if ((a > b) == up) { w.keys[i] = b; w.keys[ixj] = a; }
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & jr) == 0) {
+                        const bool up = ((r * 32) & kk) == 0;  // kk > 32 here: bit of the register index
+                        const u64 x = v[r], y = v[r | jr];
+                        const bool sw = (x > y) == up;
+                        v[r] = sw ? y : x;
+                        v[r | jr] = sw ? x : y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const u64 x = v[r];
+                    const u64 y = __shfl_xor_sync(0xffffffffu, x, j);
+                    const bool up = (((r * 32 + lane) & kk) == 0);
+                    const bool lower = (lane & j) == 0;
+                    const bool take_min = lower == up;
+                    v[r] = take_min ? (x < y ? x : y) : (x < y ? y : x);
                 }
             }
-            __syncwarp();
         }
+    }
+}
+
+// sort the first n (<= 32*R) keys of a shared-memory buffer in place (one warp), pad with RII_KEY_MAX
+template <int R>
+__device__ __forceinline__ void warp_sort_buf(u64 *keys, int n, int lane)
+{
+    u64 v[R];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = (r * 32 + lane) < n ? keys[r * 32 + lane] : RII_KEY_MAX;
+    warp_sort_regs<R>(v, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) keys[r * 32 + lane] = v[r];
+    __syncwarp();
+}
+
+__device__ __noinline__ void warp_sort_any(u64 *keys, int n, int lane)  // n <= 256; buffer holds >= next_pow2-ish 32*R slots
+{
+    if (n <= 64) warp_sort_buf<2>(keys, n, lane);
+    else if (n <= 128) warp_sort_buf<4>(keys, n, lane);
+    else warp_sort_buf<8>(keys, n, lane);
+}
+
+__device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
+{
+    const int n = w.count;  // <= cap <= 256
+    warp_sort_any(w.keys, n, lane);
     w.count = n < w.k ? n : w.k;
     if (w.count == w.k && lane == 0) atomicMin(cta_thr, w.keys[w.k - 1]);
     __syncwarp();
@@ -1075,7 +1119,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     float *lut2 = reinterpret_cast<float *>(smem_raw + lut_off);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
-    long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 : nullptr;
+    long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     const uint32_t keys_off = 0;
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
@@ -1193,6 +1237,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         pc = a.centers;
         wt.k = a.w_eff;
         set_range(a.nlist, 1, 0);
+    }
+    wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
+    if (fused) {
     } else if (IVF) {
         set_range(J ? (long long)s_cum[J - 1] : 0, gridDim.x, blockIdx.x);
     } else {
@@ -1241,6 +1288,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     }
     __syncthreads();
     if (dbg && threadIdx.x == 0 && !fused) dbg[1] = clock64();
+    if (dbg && threadIdx.x == 0) dbg[4] = clock64();  // table ready
 
     const int npass = fused ? 2 : 1;
 #pragma unroll 1
@@ -1249,6 +1297,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             // ---- between the passes: merge the warps' center lists, rank, plan (all in shared memory) -----------
             // every warp list is sorted and cta_thr <= the w-th key of some warp, i.e. an upper bound of the global
             // w-th key: only keys <= cta_thr can be in the global top-w
+            if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // pass-0 engine + warp compaction done
             u64 *pool = reinterpret_cast<u64 *>(smem_raw + hi_reg0);  // the regions are idle now
             int *pool_n = s_plan + 2;
             if (threadIdx.x == 0) *pool_n = 0;
@@ -1263,9 +1312,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             __syncthreads();
             if (wid == 0) {
                 const int np = *pool_n;
-                const int P = next_pow2(np < 2 ? 2 : np);
-                for (int i = np + lane; i < P; i += 32) pool[i] = RII_KEY_MAX;
-                warp_sort_smem(pool, P, lane);
+                if (np <= 256) {
+                    warp_sort_any(pool, np, lane);
+                } else {
+                    const int P = next_pow2(np);
+                    for (int i = np + lane; i < P; i += 32) pool[i] = RII_KEY_MAX;
+                    warp_sort_smem(pool, P, lane);
+                }
+                if (dbg && lane == 0) { dbg[6] = clock64(); dbg[7] = np; }  // pool sorted; pool size
                 int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
                 for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist == number of pooled keys or more
                     const int no = (int)key_id(pool[j]);
@@ -1289,6 +1343,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             segm = true;
             segw = 0;
             wt.k = a.k;
+            wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
             wt.count = 0;
             set_range(J ? (long long)s_cum[J - 1] : 0, 1, 0);
             *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
@@ -1352,14 +1407,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
             if (wid == 0) {
                 u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
-                const int P = next_pow2(tot < 2 ? 2 : tot);
                 int o = 0;
                 for (int w2 = 0; w2 < NW; ++w2) {
                     for (int i = lane; i < s_cnt[w2]; i += 32) mk[o + i] = allkeys[(size_t)w2 * capw + i];
                     o += s_cnt[w2];
                 }
-                for (int i = tot + lane; i < P; i += 32) mk[i] = RII_KEY_MAX;
-                warp_sort_smem(mk, P, lane);
+                warp_sort_any(mk, tot, lane);
                 const int n = tot < a.k ? tot : a.k;
                 if (a.out.final) {
                     for (int i = lane; i < n; i += 32) {

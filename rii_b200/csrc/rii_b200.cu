@@ -468,7 +468,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             SkewArgs sa{};
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
-            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
             Prof pr(h, st, PK_SCAN_LINEAR);
             sa.smem_bytes = SK_DYN_SMEM;
             CKR(launch_skew(nw, false, sa, parts, B, st));
@@ -598,7 +598,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
             if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
-            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 32)); sa.dbg = h->dbg.as<long long>(); }
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         }
         if (!use_v2) {
             CKR(ensure_T());
@@ -912,13 +912,13 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
 
 int rii_debug_clocks(rii_index_t *h, int64_t n_ctas, int64_t *out)
 {
-    // out: (n_ctas, 4) clock64() values recorded by the last v2 scan launch (option "debug_clocks" = 1)
+    // out: (n_ctas, 8) clock64() values recorded by the last v2 scan launch (option "debug_clocks" = 1)
     if (!h || !out || n_ctas <= 0) return fail(RII_ERR_ARG, "bad arguments");
-    if ((size_t)n_ctas * 32 > h->dbg.cap) return fail(RII_ERR_ARG, "no debug clocks recorded for that many CTAs");
+    if ((size_t)n_ctas * 64 > h->dbg.cap) return fail(RII_ERR_ARG, "no debug clocks recorded for that many CTAs");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, h->dbg.p, (size_t)n_ctas * 32, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, h->dbg.p, (size_t)n_ctas * 64, cudaMemcpyDeviceToHost));
     return 0;
 }
 

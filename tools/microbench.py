@@ -91,24 +91,31 @@ def main_():
         oi = torch.empty((B, 1), dtype=torch.int64, device=dev)
         od = torch.empty((B, 1), dtype=torch.float32, device=dev)
         oc = torch.empty((B,), dtype=torch.int32, device=dev)
-        for it in range(5):
-            if it == 2:
-                torch.cuda.synchronize()
-                lib.rii_profile_reset(e3._h)
-            _capi.check(lib.rii_query_batch_dev(e3._h, C.c_void_p(Q.data_ptr()), B, 1, None, 0, L, 1,
-                                                C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()),
-                                                C.c_void_p(oc.data_ptr()), sp))
-        torch.cuda.synchronize()
-        clk = np.zeros((B, 4), np.int64)
-        _capi.check(lib.rii_debug_clocks(e3._h, B, clk.ctypes.data_as(C.POINTER(C.c_int64))))
-        d = np.diff(clk, axis=1)
-        out = {"what": "ivf_batch", "B": B, "L": L}
-        for name in ("coarse_rank", "scan_ivf", "dtable"):
-            ms, n = prof(lib, e3, name)
-            out[name + "_ms"] = round(ms / max(n, 1), 4)
-        out["cta_cycles_mean"] = {"table": float(d[:, 0].mean()), "scan": float(d[:, 1].mean()), "tail": float(d[:, 2].mean()),
-                                  "total": float((clk[:, 3] - clk[:, 0]).mean())}
-        print(json.dumps(out))
+        for fuse in (1, 0):
+            e3.set_option("fuse_coarse", fuse)
+            for it in range(5):
+                if it == 2:
+                    torch.cuda.synchronize()
+                    lib.rii_profile_reset(e3._h)
+                _capi.check(lib.rii_query_batch_dev(e3._h, C.c_void_p(Q.data_ptr()), B, 1, None, 0, L, 1,
+                                                    C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()),
+                                                    C.c_void_p(oc.data_ptr()), sp))
+            torch.cuda.synchronize()
+            clk = np.zeros((B, 8), np.int64)
+            _capi.check(lib.rii_debug_clocks(e3._h, B, clk.ctypes.data_as(C.POINTER(C.c_int64))))
+            out = {"what": "ivf_batch", "fuse_coarse": fuse, "B": B, "L": L}
+            for name in ("coarse_rank", "scan_ivf", "dtable"):
+                ms, n = prof(lib, e3, name)
+                out[name + "_ms"] = round(ms / max(n, 1), 4)
+            t0 = clk[:, 0]
+            out["cta_cycles_mean"] = {"table_built": float((clk[:, 4] - t0).mean()), "ready_to_scan": float((clk[:, 1] - t0).mean()),
+                                      "scan": float((clk[:, 2] - clk[:, 1]).mean()), "tail": float((clk[:, 3] - clk[:, 2]).mean()),
+                                      "total": float((clk[:, 3] - t0).mean())}
+            if fuse:
+                out["cta_cycles_mean"].update({"coarse_pass": float((clk[:, 5] - clk[:, 4]).mean()),
+                                               "pool_sort": float((clk[:, 6] - clk[:, 5]).mean()),
+                                               "plan": float((clk[:, 1] - clk[:, 6]).mean()), "pool_size": float(clk[:, 7].mean())})
+            print(json.dumps(out))
     if "assign" in a.what:
         n_as = min(N, 1000000)
         e2 = main.RiiCpp(cw, False, l2_variant=16)
