@@ -1073,7 +1073,11 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
 
 // end of a block: accumulator A holds the finished distance of local candidate `eloc` (id ID) in every lane
 #define SK_EMIT(ID)                                                                                           \
-    {                                                                                                         \
+    if (IVF && direct) { /* coarse pass of the fused kernel: keep every distance */                           \
+        if (eloc < (uint32_t)cnt) pool_d[(ID)] = __float_as_uint(accA);                                       \
+        accA = accB;                                                                                          \
+        accB = 0.f;                                                                                           \
+    } else {                                                                                                  \
         if constexpr (IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                        \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
@@ -1101,6 +1105,36 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
             }
             __syncwarp();
         }
+}
+
+// Coarse selection (fused kernel): the w smallest of np (distance bits, index) pairs, distances in shared memory.
+// Bisection on the 31 value bits of the non-negative float finds the w-th smallest distance d*; everything <= d*
+// (w keys, more only on exact ties at d*) is gathered as (dist, index) keys and sorted.  One warp, ~3 K cycles for
+// np = 1000 -- versus 13 K for sorting a thresholded pool and 14 K for per-warp top-w lists (phase clocks).
+// Returns the number of keys written to `out` (>= w when np >= w), or -1 if more than 256 tie (caller falls back).
+__device__ __noinline__ int warp_select_smallest(const uint32_t *d, int np, int w, u64 *out, int lane)
+{
+    uint32_t t = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t trial = t | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < np; i += 32) c += d[i] < trial;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c < w) t = trial;  // fewer than w values below trial: the w-th smallest is >= trial
+    }
+    // t == w-th smallest distance (bits)
+    int n = 0;
+    for (int i0 = 0; i0 < np; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < np && d[i] <= t;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (n + __popc(bal) > 256) return -1;
+        if (ok) out[n + __popc(bal & ((1u << lane) - 1u))] = ((u64)d[i] << 32) | (u64)(uint32_t)i;
+        n += __popc(bal);
+    }
+    warp_sort_any(out, n, lane);
+    return n;
 }
 
 // Phases: IVF launches with a.centers != null run TWO passes of the same engine in one CTA -- pass 0 ranks the
@@ -1233,13 +1267,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 
     // ---- pass setup: the first tile goes out before the table is built ---------------------------------
     bool segm = IVF && !fused;  // true: pass over planned posting-list segments; false: plain row range
-    if (fused) {
-        pc = a.centers;
-        wt.k = a.w_eff;
-        set_range(a.nlist, 1, 0);
-    }
+    bool direct = fused;         // coarse pass: every distance goes to pool_d[center]
+    // the warps' key buffers are idle during the coarse pass: they hold the nlist distances (host checks the size)
+    uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + keys_off);
     wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
     if (fused) {
+        pc = a.centers;
+        set_range(a.nlist, 1, 0);
     } else if (IVF) {
         set_range(J ? (long long)s_cum[J - 1] : 0, gridDim.x, blockIdx.x);
     } else {
@@ -1294,35 +1328,21 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 #pragma unroll 1
     for (int pass = 0; pass < npass; ++pass) {
         if (pass == 1) {
-            // ---- between the passes: merge the warps' center lists, rank, plan (all in shared memory) -----------
-            // every warp list is sorted and cta_thr <= the w-th key of some warp, i.e. an upper bound of the global
-            // w-th key: only keys <= cta_thr can be in the global top-w
-            if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // pass-0 engine + warp compaction done
-            u64 *pool = reinterpret_cast<u64 *>(smem_raw + hi_reg0);  // the regions are idle now
-            int *pool_n = s_plan + 2;
-            if (threadIdx.x == 0) *pool_n = 0;
-            __syncthreads();
-            {
-                const u64 thr = *cta_thr;
-                for (int i = lane; i < wt.count; i += 32) {
-                    const u64 key = wt.keys[i];
-                    if (key <= thr) pool[atomicAdd(pool_n, 1)] = key;
-                }
-            }
-            __syncthreads();
+            // ---- between the passes: select + rank the w_eff nearest centers, plan (all in shared memory) ----------
+            if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // coarse pass done (the pass loop ended with a barrier)
             if (wid == 0) {
-                const int np = *pool_n;
-                if (np <= 256) {
-                    warp_sort_any(pool, np, lane);
-                } else {
-                    const int P = next_pow2(np);
-                    for (int i = np + lane; i < P; i += 32) pool[i] = RII_KEY_MAX;
-                    warp_sort_smem(pool, P, lane);
+                u64 *sel = reinterpret_cast<u64 *>(smem_raw + hi_reg0);  // the regions are idle now
+                int np = warp_select_smallest(pool_d, a.nlist, a.w_eff, sel, lane);
+                if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
+                    const int P = next_pow2(a.nlist);
+                    for (int i = lane; i < P; i += 32) sel[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
+                    warp_sort_smem(sel, P, lane);
+                    np = a.nlist;
                 }
-                if (dbg && lane == 0) { dbg[6] = clock64(); dbg[7] = np; }  // pool sorted; pool size
+                if (dbg && lane == 0) { dbg[6] = clock64(); dbg[7] = np; }
                 int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
-                for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist == number of pooled keys or more
-                    const int no = (int)key_id(pool[j]);
+                for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist, np >= w_eff
+                    const int no = (int)key_id(sel[j]);
                     ranked_g[j] = no;
                     s_f[j] = a.plan.glob_len[no];
                     s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
@@ -1341,6 +1361,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             J = s_plan[0];
             pc = a.codes;
             segm = true;
+            direct = false;
             segw = 0;
             wt.k = a.k;
             wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
@@ -1392,7 +1413,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             SK_BLOCK(rbw)
             SK_EMIT((uint32_t)(base + eloc))
         }
-        warp_compact(wt, cta_thr, lane);
+        if (!(IVF && direct)) warp_compact(wt, cta_thr, lane);
         __syncthreads();
     }
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();

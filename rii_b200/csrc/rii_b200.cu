@@ -528,7 +528,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // v2 (skewed, bank-conflict-free) posting-list scan when it applies: M == 32, no target_ids, small topk, plan
     // fits shared memory.  With one CTA per query (parts == 1) the coarse ranking and the plan are fused into the
     // same kernel (two passes of one engine): no k_coarse_rank launch at all.
-    const int capw2 = std::max(64, next_pow2(std::max(c.topk, w_eff) + 32));
+    const int capw2 = std::max(64, next_pow2(c.topk + 32));
     const int nw2 = skew_pick_nw(true, capw2, w_eff);
     const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
@@ -536,7 +536,9 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse;
+    // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8 &&
+                      (size_t)next_pow2(h->nlist) * 8 <= (size_t)8 * SK_WARP_BYTES;
     if (!fuse) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
