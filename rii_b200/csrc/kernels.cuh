@@ -1114,11 +1114,18 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
 // Returns the number of keys written to `out` (>= w when np >= w), or -1 if more than 256 tie (caller falls back).
 __device__ __noinline__ int warp_select_smallest(const uint32_t *d, int np, int w, u64 *out, int lane)
 {
+    // np <= 1024: the lane keeps its (up to) 32 values in registers -- a shared-memory loop here is latency bound
+    // (measured: 88 K cycles for np = 1000 against ~3 K from registers)
+    uint32_t v[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = (r * 32 + lane) < np ? d[r * 32 + lane] : 0xffffffffu;
     uint32_t t = 0;
+#pragma unroll 1
     for (int bit = 30; bit >= 0; --bit) {
         const uint32_t trial = t | (1u << bit);
         int c = 0;
-        for (int i = lane; i < np; i += 32) c += d[i] < trial;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) c += v[r] < trial;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c < w) t = trial;  // fewer than w values below trial: the w-th smallest is >= trial

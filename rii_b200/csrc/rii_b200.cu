@@ -537,8 +537,8 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8 &&
-                      (size_t)next_pow2(h->nlist) * 8 <= (size_t)8 * SK_WARP_BYTES;
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && h->nlist <= 1024 &&
+                      (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8;
     if (!fuse) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
