@@ -961,42 +961,32 @@ struct WarpTopk {
 // are register-to-register inside a lane, smaller distances are warp shuffles: no shared memory, no barriers.
 // (The shared-memory version took ~145 cycles per compare-exchange round: 16 K cycles for 128 keys, measured with
 // the phase clocks -- profiles/r01_micro_ivf_phase_clocks_*.jsonl.)
-template <int R, int JR>
-__device__ __forceinline__ void sort_exch_inlane(u64 (&v)[R], int kk)  // partners r and r | JR inside the lane
-{
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if ((r & JR) == 0) {
-            const bool up = ((r * 32) & kk) == 0;
-            const u64 x = v[r], y = v[r | JR];
-            const bool sw = (x > y) == up;
-            v[r] = sw ? y : x;
-            v[r | JR] = sw ? x : y;
-        }
-    }
-}
-
-// The stage loops are deliberately NOT unrolled: a fully unrolled 256-key network is ~46 KB of code and, together with
-// the other once-per-CTA phases, thrashed the instruction cache (phase clocks: 60 K cycles for a 3 K-cycle select).
 template <int R>
 __device__ __forceinline__ void warp_sort_regs(u64 (&v)[R], int lane)
 {
-#pragma unroll 1
+#pragma unroll
     for (int kk = 2; kk <= 32 * R; kk <<= 1) {
-#pragma unroll 1
+#pragma unroll
         for (int j = kk >> 1; j > 0; j >>= 1) {
             if (j >= 32) {
                 const int jr = j >> 5;
-                if (R > 1 && jr == 1) sort_exch_inlane<R, (R > 1 ? 1 : 0)>(v, kk);
-                else if (R > 2 && jr == 2) sort_exch_inlane<R, (R > 2 ? 2 : 0)>(v, kk);
-                else if (R > 4 && jr == 4) sort_exch_inlane<R, (R > 4 ? 4 : 0)>(v, kk);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & jr) == 0) {
+                        const bool up = ((r * 32) & kk) == 0;  // kk > 32 here: bit of the register index
+                        const u64 x = v[r], y = v[r | jr];
+                        const bool sw = (x > y) == up;
+                        v[r] = sw ? y : x;
+                        v[r | jr] = sw ? x : y;
+                    }
+                }
             } else {
-                const bool lower = (lane & j) == 0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const u64 x = v[r];
                     const u64 y = __shfl_xor_sync(0xffffffffu, x, j);
                     const bool up = (((r * 32 + lane) & kk) == 0);
+                    const bool lower = (lane & j) == 0;
                     const bool take_min = lower == up;
                     v[r] = take_min ? (x < y ? x : y) : (x < y ? y : x);
                 }
@@ -1049,90 +1039,6 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
     if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
 }
 
-// ---- out-of-line pieces of the v2 engine.  The 4-block tile loop is ~900 instructions; everything that runs once
-// per tile or only for survivors is kept out of line so that the loop stays inside the instruction cache.
-__device__ __noinline__ void sk_issue_tile(const uint8_t *pc, long long base, long long end, int n, uint32_t dst, int lane)
-{
-    // rows [base + 128 n, +128) of the contiguous table pc -> this warp's regions (16-byte chunks dealt round-robin)
-    const long long r0 = base + (long long)n * SK_TILE_ROWS;
-    const uint8_t *g = pc + r0 * 32 + lane * 16;
-    if (r0 + SK_TILE_ROWS <= end) {  // full tile: 8 x 512 contiguous bytes per warp, immediates only
-#pragma unroll
-        for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
-    } else {                          // last tile: rows past the end are zero filled, their results masked
-#pragma unroll
-        for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
-            const int nbytes = r0 + it * 16 + (lane >> 1) < end ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
-                         "l"(nbytes ? g + it * 512 : pc), "r"(nbytes));
-        }
-    }
-    asm volatile("cp.async.commit_group;");
-}
-
-// IVF: tile n = flattened candidates [c0, c0 + 128) of the plan; segment j covers [cum[j-1], cum[j]) and starts at row
-// s_off[j] of the list-ordered code copy.  segw = segment of c0 (warp-uniform, carried along by the caller).
-__device__ __noinline__ int sk_issue_tile_seg(const uint8_t *pc, const int *s_cum, const long long *s_off, int J, int c0, int cend,
-                                              int segw, uint32_t dst, int lane)
-{
-    while (segw < J - 1 && s_cum[segw] <= c0) ++segw;
-    const int seg_lo = segw ? s_cum[segw - 1] : 0;
-    if (c0 + SK_TILE_ROWS <= cend && c0 + SK_TILE_ROWS <= s_cum[segw]) {  // one segment, full tile: pure stream
-        const uint8_t *g = pc + (size_t)(s_off[segw] + (c0 - seg_lo)) * 32 + lane * 16;
-#pragma unroll
-        for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
-    } else {                                                             // crosses a segment boundary / tail
-#pragma unroll 1
-        for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
-            const int c = c0 + it * 16 + (lane >> 1);
-            const bool ok = c < cend;
-            int seg = segw;
-            if (ok) while (s_cum[seg] <= c) ++seg;
-            const uint8_t *g = pc + (size_t)(s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) * 32 + (lane & 1) * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
-                         "l"(ok ? g : pc), "r"(ok ? 16 : 0));
-        }
-    }
-    asm volatile("cp.async.commit_group;");
-    return segw;
-}
-
-struct SkSeg {  // IVF candidate -> posting-list id mapping (shared-memory plan)
-    const int *s_cum;
-    const long long *s_off;
-    const int *ids;
-    int J;
-    uint32_t total;
-};
-
-// survivors of an emission: exact (distance, id) test against the live CTA threshold, append, compact when nearly full
-__device__ __noinline__ void sk_emit_slow(WarpTopk &w, u64 *cta_thr, int lane, float dist, uint32_t c, bool pre, bool segm,
-                                          const SkSeg &sg)
-{
-    uint32_t id = c;
-    if (segm) {  // posting-list id of flattened candidate c
-        id = 0u;
-        if (pre && c < sg.total) {
-            int lo = 0, hi = sg.J - 1;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (sg.s_cum[mid] > (int)c) hi = mid; else lo = mid + 1;
-            }
-            id = (uint32_t)__ldg(sg.ids + sg.s_off[lo] + ((int)c - (lo ? sg.s_cum[lo - 1] : 0)));
-        }
-    }
-    const u64 thr = *reinterpret_cast<volatile u64 *>(cta_thr);
-    const u64 key = pack_key(dist, id);
-    const bool pass = pre && key < thr;
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (!bal) return;
-    if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
-    w.count += __popc(bal);
-    if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
-}
-
 // one lookup step.  The table sits at the 64 KB-aligned ABSOLUTE shared address 0x10000, so the byte-permute of
 // (code word, colreg = 0x00010000 | lane column offset) IS the lookup address: 0x10000 | ks << 8 | col; the step
 // index goes into the load's immediate.  (t < l ? A : B) += v with a predicated add pair.
@@ -1175,7 +1081,8 @@ __device__ __noinline__ void sk_emit_slow(WarpTopk &w, u64 *cta_thr, int lane, f
         if constexpr (IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                        \
         const bool pre_ = eloc < (uint32_t)cnt && __float_as_uint(accA) <= thr_hi;                            \
         if (__any_sync(0xffffffffu, pre_)) {                                                                  \
-            sk_emit_slow(wt, cta_thr, lane, accA, (ID), pre_, segm, sg);                                      \
+            const uint32_t id_ = segm ? (pre_ ? cand_id(ID) : 0u) : (ID);                                     \
+            warp_push(wt, cta_thr, lane, accA, id_, pre_);                                                    \
             thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];                                       \
         }                                                                                                     \
         accA = accB;                                                                                          \
@@ -1201,40 +1108,75 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
 }
 
 // Coarse selection (fused kernel): the w smallest of np (distance bits, index) pairs, distances in shared memory.
-// Bisection on the 31 value bits of the non-negative float finds the w-th smallest distance d*; everything <= d*
-// (w keys, more only on exact ties at d*) is gathered as (dist, index) keys and sorted.  One warp, ~3 K cycles for
-// np = 1000 -- versus 13 K for sorting a thresholded pool and 14 K for per-warp top-w lists (phase clocks).
-// Returns the number of keys written to `out` (>= w when np >= w), or -1 if more than 256 tie (caller falls back).
-__device__ __noinline__ int warp_select_smallest(const uint32_t *d, int np, int w, u64 *out, int lane)
+// CTA-wide 8-bit radix select (4 passes over the 31 value bits of the non-negative float): every thread histograms its
+// share of the values that still match the prefix, every warp scans the 256 bins redundantly and reaches the same
+// decision.  Result: t = the w-th smallest distance; then one warp gathers everything <= t (w keys, more only on exact
+// ties at t) as (dist, index) keys and sorts them.  (Measured alternatives, phase clocks: per-warp top-w lists + pool
+// sort 27 K cycles; single-warp bisection 60 K cycles.)
+// Returns (in every thread) the number of keys in `out`, or -1 if more than 256 tie (caller falls back to a full sort).
+template <int NT>
+__device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist /* 256 + 2 ints */)
 {
-    // np <= 1024: the lane keeps its (up to) 32 values in registers -- a shared-memory loop here is latency bound
-    // (measured: 88 K cycles for np = 1000 against ~3 K from registers)
-    uint32_t v[32];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) v[r] = (r * 32 + lane) < np ? d[r * 32 + lane] : 0xffffffffu;
-    uint32_t t = 0;
+    const int lane = threadIdx.x & 31;
+    uint32_t prefix = 0, mask = 0;
+    int remaining = w;
 #pragma unroll 1
-    for (int bit = 30; bit >= 0; --bit) {
-        const uint32_t trial = t | (1u << bit);
-        int c = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += NT) hist[i] = 0;
+        __syncthreads();
+        const int sh = 8 * pass;
+        for (int i = threadIdx.x; i < np; i += NT) {
+            const uint32_t v = d[i];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> sh) & 255], 1);
+        }
+        __syncthreads();
+        // bins 8*lane .. 8*lane+7 -> inclusive prefix over lanes -> the bin holding the remaining-th value
+        int c[8], tot = 0;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) c += v[r] < trial;
+        for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; tot += c[j]; }
+        int incl = tot;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (c < w) t = trial;  // fewer than w values below trial: the w-th smallest is >= trial
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int excl = incl - tot;
+        const bool mine = excl < remaining && remaining <= incl;  // exactly one lane
+        int bin = 0, below = 0;
+        if (mine) {
+            int run = excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (run + c[j] >= remaining) { bin = 8 * lane + j; below = run; break; }
+                run += c[j];
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const int src = __ffs(who) - 1;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        prefix |= (uint32_t)bin << sh;
+        mask |= 0xffu << sh;
+        remaining -= below;
+        __syncthreads();  // histogram is cleared again
     }
-    // t == w-th smallest distance (bits)
-    int n = 0;
-    for (int i0 = 0; i0 < np; i0 += 32) {
-        const int i = i0 + lane;
-        const bool ok = i < np && d[i] <= t;
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (n + __popc(bal) > 256) return -1;
-        if (ok) out[n + __popc(bal & ((1u << lane) - 1u))] = ((u64)d[i] << 32) | (u64)(uint32_t)i;
-        n += __popc(bal);
+    const uint32_t t = prefix;  // the w-th smallest distance (bits)
+    int *cnt = hist + 256;
+    if (threadIdx.x < 32) {
+        int n = 0;
+        for (int i0 = 0; i0 < np; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i < np && d[i] <= t;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (n + __popc(bal) > 256) { n = -1; break; }
+            if (ok) out[n + __popc(bal & ((1u << lane) - 1u))] = ((u64)d[i] << 32) | (u64)(uint32_t)i;
+            n += __popc(bal);
+        }
+        if (n > 0) warp_sort_any(out, n, lane);
+        if (lane == 0) *cnt = n;
     }
-    warp_sort_any(out, n, lane);
-    return n;
+    __syncthreads();
+    return *cnt;
 }
 
 // Phases: IVF launches with a.centers != null run TWO passes of the same engine in one CTA -- pass 0 ranks the
@@ -1309,16 +1251,64 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         cnt = end > base ? (int)(end - base) : 0;
         ntiles = (cnt + SK_TILE_ROWS - 1) / SK_TILE_ROWS;
     };
-    bool segm = IVF && !fused;  // true: pass over planned posting-list segments; false: plain row range
-    SkSeg sg;
-    sg.s_cum = s_cum; sg.s_off = s_off; sg.ids = a.ids; sg.J = J; sg.total = 0;
-    auto issue = [&](int n) {  // stage tile n of the current pass into the half (n & 1) of this warp's regions
+    auto issue_tile = [&](int n) {  // rows [base + 128 n, +128) of the contiguous table pc
+        const long long r0 = base + (long long)n * SK_TILE_ROWS;
+        const uint8_t *g = pc + r0 * 32 + lane * 16;
         const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
-        if (segm) segw = sk_issue_tile_seg(pc, s_cum, s_off, sg.J, (int)base + n * SK_TILE_ROWS, (int)end, segw, dst, lane);
-        else sk_issue_tile(pc, base, end, n, dst, lane);
+        if (r0 + SK_TILE_ROWS <= end) {  // full tile: 8 x 512 contiguous bytes per warp, immediates only
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
+        } else {                          // last tile: rows past the end are zero filled, their results masked
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
+                const int nbytes = r0 + it * 16 + (lane >> 1) < end ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
+                             "l"(nbytes ? g + it * 512 : pc), "r"(nbytes));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    // IVF pass 1: tile n = flattened candidates [c0, c0 + 128) of the plan; segment j covers [cum[j-1], cum[j]) and
+    // starts at row s_off[j] of the list-ordered code copy.  segw = segment of c0 (warp-uniform, carried along).
+    auto issue_tile_seg = [&](int n) {
+        const int c0 = (int)base + n * SK_TILE_ROWS;
+        const int cend = (int)end;
+        while (segw < J - 1 && s_cum[segw] <= c0) ++segw;
+        const int seg_lo = segw ? s_cum[segw - 1] : 0;
+        const uint32_t dst = smem_base + cp_dst + ((n & 1) ? SK_J * 32 : 0);
+        if (c0 + SK_TILE_ROWS <= cend && c0 + SK_TILE_ROWS <= s_cum[segw]) {  // one segment, full tile: pure stream
+            const uint8_t *g = pc + (size_t)(s_off[segw] + (c0 - seg_lo)) * 32 + lane * 16;
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 4 * SK_REGION_BYTES), "l"(g + it * 512));
+        } else {                                                             // crosses a segment boundary / tail
+#pragma unroll
+            for (int it = 0; it < SK_TILE_ROWS / 16; ++it) {
+                const int c = c0 + it * 16 + (lane >> 1);
+                const bool ok = c < cend;
+                int seg = segw;
+                if (ok) while (s_cum[seg] <= c) ++seg;
+                const uint8_t *g = pc + (size_t)(s_off[seg] + (c - (seg ? s_cum[seg - 1] : 0))) * 32 + (lane & 1) * 16;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + it * 4 * SK_REGION_BYTES),
+                             "l"(ok ? g : pc), "r"(ok ? 16 : 0));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    // IVF pass 1: posting-list id of flattened candidate c (survivors only)
+    auto cand_id = [&](uint32_t c) -> uint32_t {
+        if (c >= (uint32_t)total) return 0u;
+        int lo = 0, hi = J - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_cum[mid] > (int)c) hi = mid; else lo = mid + 1;
+        }
+        return (uint32_t)__ldg(a.ids + s_off[lo] + ((int)c - (lo ? s_cum[lo - 1] : 0)));
     };
 
     // ---- pass setup: the first tile goes out before the table is built ---------------------------------
+    bool segm = IVF && !fused;  // true: pass over planned posting-list segments; false: plain row range
     bool direct = fused;         // coarse pass: every distance goes to pool_d[center]
     // the warps' key buffers are idle during the coarse pass: they hold the nlist distances (host checks the size)
     uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + keys_off);
@@ -1328,7 +1318,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         set_range(a.nlist, 1, 0);
     } else if (IVF) {
         set_range(J ? (long long)s_cum[J - 1] : 0, gridDim.x, blockIdx.x);
-        sg.total = (uint32_t)total;
     } else {
         set_range(a.N, gridDim.x, blockIdx.x);
     }
@@ -1336,7 +1325,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
     if (ntiles > 0) {
-        issue(0);
+        if (segm) issue_tile_seg(0);
+        else issue_tile(0);
     }
     {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (zero-filled padding rows index row 0 only)
         if (a.T) {
@@ -1382,9 +1372,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         if (pass == 1) {
             // ---- between the passes: select + rank the w_eff nearest centers, plan (all in shared memory) ----------
             if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // coarse pass done (the pass loop ended with a barrier)
+            u64 *sel = reinterpret_cast<u64 *>(smem_raw + hi_reg0);          // the regions are idle now
+            int *hist = reinterpret_cast<int *>(smem_raw + hi_reg0 + 4096);  // 256 keys above `sel`
+            int np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, sel, hist);
             if (wid == 0) {
-                u64 *sel = reinterpret_cast<u64 *>(smem_raw + hi_reg0);  // the regions are idle now
-                int np = warp_select_smallest(pool_d, a.nlist, a.w_eff, sel, lane);
                 if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
                     const int P = next_pow2(a.nlist);
                     for (int i = lane; i < P; i += 32) sel[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
@@ -1421,9 +1412,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             set_range(J ? (long long)s_cum[J - 1] : 0, 1, 0);
             *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4 *>(smem_raw + myreg + 16) = make_uint4(0, 0, 0, 0);
-            sg.J = J;
-            sg.total = (uint32_t)total;
-            if (ntiles > 0) issue(0);
+            if (ntiles > 0) issue_tile_seg(0);
         }
 
         float accA = 0.f, accB = 0.f;
@@ -1452,7 +1441,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             eloc += SK_TILE_ROWS - SK_J + 1;
             __syncwarp();  // the other half's last reader finished with this block
             if (n + 1 < ntiles) {
-                issue(n + 1);
+                if (segm) issue_tile_seg(n + 1);
+                else issue_tile(n + 1);
             }
 #pragma unroll
             for (int i = 1; i < SK_J; ++i) {
