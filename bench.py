@@ -14,8 +14,12 @@ scan -> top-k).
           its own single-query API on this box's host cores (one process per core, each a loop of
           main.RiiCpp.query_ivf calls like examples/benchmark/run_sift1m.py:26-30)
 
-Multi-GPU (torchrun, one rank per GPU): the index is partitioned by contiguous id range; every
-rank scans its shard for every query; per-shard top-k are all-gathered over NCCL and merged -> "strong".
+Multi-GPU (torchrun, one rank per GPU), total work per step fixed -> "strong":
+  default  : N = 1M fits every GPU many times over, so the index is REPLICATED and each rank answers B/G of the step's
+             queries; the per-rank results are all-gathered over NCCL so that every rank holds the whole batch.
+  --shard  : the index is partitioned by contiguous id range (what C4/C5-sized indexes need): every rank
+             scans its shard for every query, per-shard top-k are all-gathered and merged (k_merge_shards).  At
+             N = 1M this divides only the scan, not the per-query table / coarse work: measured in profiles/.
 """
 import argparse
 import ctypes as C
@@ -132,7 +136,8 @@ def run_ours(args):
     # ---- index: id-range shard per rank -----------------------------------------------------------
     e = main.RiiCpp(cw, False, device=local, l2_variant=16)
     t_build = time.time()
-    if world == 1:
+    shard = bool(args.shard) and world > 1
+    if not shard:
         e.add_codes(codes, False)
         e.reconfigure(CFG["nlist"], CFG["iter"])
     else:
@@ -149,22 +154,28 @@ def run_ours(args):
     o_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
     o_d = torch.empty((B, k), dtype=torch.float32, device=dev)
     o_c = torch.empty((B,), dtype=torch.int32, device=dev)
+    Bl = B if (world == 1 or shard) else B // world  # queries this rank answers per step
+    assert B % world == 0
     if world > 1:
-        g_ids = torch.empty((world, B, k), dtype=torch.int64, device=dev)
-        g_d = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-        g_c = torch.empty((world, B), dtype=torch.int32, device=dev)
+        g_ids = torch.empty((world, Bl, k), dtype=torch.int64, device=dev)
+        g_d = torch.empty((world, Bl, k), dtype=torch.float32, device=dev)
+        g_c = torch.empty((world, Bl), dtype=torch.int32, device=dev)
         f_ids, f_d, f_c = torch.empty_like(o_ids), torch.empty_like(o_d), torch.empty_like(o_c)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_dev(i):
         q = dQ[(i % (nq // B)) * B:(i % (nq // B) + 1) * B]
-        _capi.check(lib.rii_query_batch_dev(e._h, C.c_void_p(q.data_ptr()), B, k, None, 0, L, 1,
+        if world > 1 and not shard:  # replicas: this rank's slice of the batch, then all-gather of the results
+            q = q[rank * Bl:(rank + 1) * Bl]
+        _capi.check(lib.rii_query_batch_dev(e._h, C.c_void_p(q.data_ptr()), Bl, k, None, 0, L, 1,
                                             C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_d.data_ptr()),
                                             C.c_void_p(o_c.data_ptr()), sp))
         if world > 1:
-            dist.all_gather_into_tensor(g_ids.view(-1), o_ids.view(-1))
-            dist.all_gather_into_tensor(g_d.view(-1), o_d.view(-1))
-            dist.all_gather_into_tensor(g_c.view(-1), o_c)
+            dist.all_gather_into_tensor(g_ids.view(-1), o_ids[:Bl].reshape(-1))
+            dist.all_gather_into_tensor(g_d.view(-1), o_d[:Bl].reshape(-1))
+            dist.all_gather_into_tensor(g_c.view(-1), o_c[:Bl])
+            if not shard:
+                return g_ids.view(B, k)
             _capi.check(lib.rii_merge_shards_dev(e._h, C.c_void_p(g_ids.data_ptr()), C.c_void_p(g_d.data_ptr()),
                                                  C.c_void_p(g_c.data_ptr()), world, B, k,
                                                  C.c_void_p(f_ids.data_ptr()), C.c_void_p(f_d.data_ptr()),
@@ -264,9 +275,9 @@ def run_ours(args):
     # algorithmic bytes of the dominant kernel (posting-list scan), per launch: per query C*M code bytes
     # (C = L candidates) + 4*M*Ks (its distance table).  SURVEY's V*4 bytes of visited ids are NOT counted: the
     # kernel streams a list-ordered code copy and reads ids only for survivors.
-    shard = 1.0 / world
-    q_per_launch = K * B / max(scan_n.value, 1)  # the library processes a step in chunks of <= 2048 queries
-    alg = q_per_launch * (L * shard * M + 4 * M * CFG["Ks"])
+    frac_scanned = 1.0 / world if shard else 1.0
+    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 2048 queries
+    alg = q_per_launch * (L * frac_scanned * M + 4 * M * CFG["Ks"])
     launch_ms = scan_ms.value / max(scan_n.value, 1)
     achieved = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
     line = {
@@ -276,7 +287,9 @@ def run_ours(args):
         "data": "synthetic U[0,1)^128 float32 vectors, PQ trained on a 20k sample; ground truth exact L2",
         "config": {"workload": "C2: N=1M D=128 M=32 Ks=256 IVF nlist=1000 L=32000 (w=35 lists) topk=1",
                    "batch_queries_per_step": B, "l2": "flushed between steps (256 MB write)",
-                   "parallelism": "1 GPU" if world == 1 else "id-range shards x%d + NCCL all-gather of top-k" % world,
+                   "parallelism": "1 GPU" if world == 1 else
+                   ("id-range shards x%d + NCCL all-gather of per-shard top-k + merge" % world if shard else
+                    "index replicated x%d, queries split, NCCL all-gather of results" % world),
                    "index_build_s": round(t_build, 2)},
         "recall_at_1": round(recall, 4),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
@@ -289,8 +302,14 @@ def run_ours(args):
                              "binding resource is the shared-memory lookup rate (DESIGN.md)"},
         "kernel_ms": prof,
     }
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(cw, codes, Q)
+    try:  # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (tools/ncu_summary.py)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        line["roofline"]["traffic"] = tr.get("k_scan_skew32_ivf_fused_bytes_per_launch")
+        line["roofline"]["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -366,6 +385,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="queries per step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--shard", action="store_true", help="multi-GPU: partition the index by id range instead of replicating it")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
