@@ -955,6 +955,8 @@ struct WarpTopk {
     u64 *keys;   // shared, this warp's buffer (>= cap keys)
     int cap, k;  // cap = next_pow2(k + 32): compaction threshold of the current pass
     int count;   // warp-uniform
+    u64 *thr_w;  // shared [nw]: every warp's ceil(k/nw)-th smallest key (RII_KEY_MAX until it has that many)
+    int nw, wid;
 };
 
 // Bitonic sort of 32*R keys held in registers (element e = r*32 + lane), ascending.  Exchanges at distance >= 32
@@ -1021,7 +1023,23 @@ __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
     const int n = w.count;  // <= cap <= 256
     warp_sort_any(w.keys, n, lane);
     w.count = n < w.k ? n : w.k;
-    if (w.count == w.k && lane == 0) atomicMin(cta_thr, w.keys[w.k - 1]);
+    // Two valid upper bounds of the CTA's k-th key tighten the shared threshold:
+    //  (1) this warp's own k-th key;
+    //  (2) the LARGEST, over all warps, of the warps' ceil(k/nw)-th keys: at least nw * ceil(k/nw) >= k keys lie below
+    //      it.  With the candidates spread evenly over the warps (2) is ~nw times tighter than (1) for k >= nw.
+    const int kq = (w.k + w.nw - 1) / w.nw;
+    if (lane == 0) {
+        if (w.count == w.k) atomicMin(cta_thr, w.keys[w.k - 1]);
+        if (w.count >= kq) w.thr_w[w.wid] = w.keys[kq - 1];
+    }
+    __syncwarp();
+    u64 t = lane < w.nw ? *reinterpret_cast<volatile u64 *>(w.thr_w + lane) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 y = __shfl_xor_sync(0xffffffffu, t, o);
+        t = t > y ? t : y;
+    }
+    if (lane == 0 && t != RII_KEY_MAX) atomicMin(cta_thr, t);
     __syncwarp();
 }
 
@@ -1062,6 +1080,26 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
         SK_STEP(wd_, 1, 4 * (Q) + 1)                                                                          \
         SK_STEP(wd_, 2, 4 * (Q) + 2)                                                                          \
         SK_STEP(wd_, 3, 4 * (Q) + 3)                                                                          \
+    }
+
+// drain variant: the 32 steps after a lane's last row.  Only the lagging steps (t < l) carry real data (the tail of the
+// last row); the rest would read past the lane's region -- into the next lane's / warp's carry row, harmless for the
+// results but a data race (racecheck) -- so the word address is clamped to the lane's own last word.
+#define SK_WORD_CLAMP(WOFF, Q, LIM)                                                                           \
+    {                                                                                                         \
+        const uint32_t wa_ = (WOFF) + 4 * (Q) < (LIM) ? (WOFF) + 4 * (Q) : (LIM);                             \
+        const uint32_t x_ = *reinterpret_cast<const uint32_t *>(smem_raw + wa_);                              \
+        const uint32_t wd_ = __funnelshift_rc(xprev, x_, shift);                                              \
+        xprev = x_;                                                                                           \
+        SK_STEP(wd_, 0, 4 * (Q) + 0)                                                                          \
+        SK_STEP(wd_, 1, 4 * (Q) + 1)                                                                          \
+        SK_STEP(wd_, 2, 4 * (Q) + 2)                                                                          \
+        SK_STEP(wd_, 3, 4 * (Q) + 3)                                                                          \
+    }
+#define SK_BLOCK_CLAMP(WOFF, LIM)                                                                             \
+    {                                                                                                         \
+        SK_WORD_CLAMP(WOFF, 0, LIM) SK_WORD_CLAMP(WOFF, 1, LIM) SK_WORD_CLAMP(WOFF, 2, LIM) SK_WORD_CLAMP(WOFF, 3, LIM) \
+        SK_WORD_CLAMP(WOFF, 4, LIM) SK_WORD_CLAMP(WOFF, 5, LIM) SK_WORD_CLAMP(WOFF, 6, LIM) SK_WORD_CLAMP(WOFF, 7, LIM) \
     }
 
 // one block = 32 steps = 8 code words starting at byte offset WOFF of the dynamic shared memory
@@ -1108,75 +1146,78 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
 }
 
 // Coarse selection (fused kernel): the w smallest of np (distance bits, index) pairs, distances in shared memory.
-// CTA-wide 8-bit radix select (4 passes over the 31 value bits of the non-negative float): every thread histograms its
-// share of the values that still match the prefix, every warp scans the 256 bins redundantly and reaches the same
-// decision.  Result: t = the w-th smallest distance; then one warp gathers everything <= t (w keys, more only on exact
-// ties at t) as (dist, index) keys and sorts them.  (Measured alternatives, phase clocks: per-warp top-w lists + pool
-// sort 27 K cycles; single-warp bisection 60 K cycles.)
-// Returns (in every thread) the number of keys in `out`, or -1 if more than 256 tie (caller falls back to a full sort).
+// One CTA-wide histogram pass: 256 equal-width buckets over [min, max] of the (non-negative float) distance bits, a
+// redundant per-warp scan finds the bucket b* holding the w-th smallest; everything in buckets <= b* (w keys plus the
+// few extra of bucket b*) is gathered as (dist, index) keys by one warp and sorted in registers.
+// (Measured alternatives, phase clocks: per-warp top-w lists + pool sort 27 K cycles; single-warp bisection 60 K; four
+// 8-bit radix passes 13 K.)
+// Returns (in every thread) the number of keys in `out` (>= w), or -1 if more than 256 qualify (heavily tied
+// distances: the caller falls back to a full sort).
 template <int NT>
-__device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist /* 256 + 2 ints */)
+__device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist /* 256 + 4 ints */)
 {
     const int lane = threadIdx.x & 31;
-    uint32_t prefix = 0, mask = 0;
-    int remaining = w;
-#pragma unroll 1
-    for (int pass = 3; pass >= 0; --pass) {
-        for (int i = threadIdx.x; i < 256; i += NT) hist[i] = 0;
-        __syncthreads();
-        const int sh = 8 * pass;
+    uint32_t *mm = reinterpret_cast<uint32_t *>(hist + 256);  // [0] min, [1] max, [2] result count
+    for (int i = threadIdx.x; i < 256; i += NT) hist[i] = 0;
+    if (threadIdx.x == 0) { mm[0] = 0xffffffffu; mm[1] = 0u; }
+    __syncthreads();
+    {
+        uint32_t lo = 0xffffffffu, hi = 0u;
         for (int i = threadIdx.x; i < np; i += NT) {
             const uint32_t v = d[i];
-            if ((v & mask) == prefix) atomicAdd(&hist[(v >> sh) & 255], 1);
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
         }
-        __syncthreads();
-        // bins 8*lane .. 8*lane+7 -> inclusive prefix over lanes -> the bin holding the remaining-th value
-        int c[8], tot = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; tot += c[j]; }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t a = __shfl_xor_sync(0xffffffffu, lo, o), c = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = a < lo ? a : lo;
+            hi = c > hi ? c : hi;
         }
-        const int excl = incl - tot;
-        const bool mine = excl < remaining && remaining <= incl;  // exactly one lane
-        int bin = 0, below = 0;
-        if (mine) {
-            int run = excl;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (run + c[j] >= remaining) { bin = 8 * lane + j; below = run; break; }
-                run += c[j];
-            }
-        }
-        const unsigned who = __ballot_sync(0xffffffffu, mine);
-        const int src = __ffs(who) - 1;
-        bin = __shfl_sync(0xffffffffu, bin, src);
-        below = __shfl_sync(0xffffffffu, below, src);
-        prefix |= (uint32_t)bin << sh;
-        mask |= 0xffu << sh;
-        remaining -= below;
-        __syncthreads();  // histogram is cleared again
+        if (lane == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
     }
-    const uint32_t t = prefix;  // the w-th smallest distance (bits)
-    int *cnt = hist + 256;
+    __syncthreads();
+    const uint32_t mn = mm[0], range = mm[1] - mn;
+    const int sh = range >= 256u ? (32 - __clz(range)) - 8 : 0;  // (v - mn) >> sh is in [0, 255]
+    for (int i = threadIdx.x; i < np; i += NT) atomicAdd(&hist[(d[i] - mn) >> sh], 1);
+    __syncthreads();
+    // bins 8*lane .. 8*lane+7 -> inclusive prefix over lanes -> the bin holding the w-th smallest value
+    int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; tot += c[j]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int excl = incl - tot;
+    const bool mine = excl < w && w <= incl;  // exactly one lane (w <= np)
+    int bin = 0;
+    if (mine) {
+        int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (run + c[j] >= w) { bin = 8 * lane + j; break; }
+            run += c[j];
+        }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, __ffs(__ballot_sync(0xffffffffu, mine)) - 1);
     if (threadIdx.x < 32) {
         int n = 0;
         for (int i0 = 0; i0 < np; i0 += 32) {
             const int i = i0 + lane;
-            const bool ok = i < np && d[i] <= t;
+            const bool ok = i < np && (int)((d[i] - mn) >> sh) <= bin;
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
             if (n + __popc(bal) > 256) { n = -1; break; }
             if (ok) out[n + __popc(bal & ((1u << lane) - 1u))] = ((u64)d[i] << 32) | (u64)(uint32_t)i;
             n += __popc(bal);
         }
         if (n > 0) warp_sort_any(out, n, lane);
-        if (lane == 0) *cnt = n;
+        if (lane == 0) mm[2] = (uint32_t)n;
     }
     __syncthreads();
-    return *cnt;
+    return (int)mm[2];
 }
 
 // Phases: IVF launches with a.centers != null run TWO passes of the same engine in one CTA -- pass 0 ranks the
@@ -1200,7 +1241,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     const uint32_t keys_off = 0;
     u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
     u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
-    long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8);
+    u64 *thr_w = cta_thr + 1;  // [NW]
+    long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8 + NW * 8);
     const int wq = IVF ? a.w_eff : 0;
     int *s_cum = reinterpret_cast<int *>(s_off + wq);
     int *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;  // s_plan: [J, flags]
@@ -1217,9 +1259,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
     }
     if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+    if (threadIdx.x < NW) thr_w[threadIdx.x] = RII_KEY_MAX;
     __syncthreads();  // plan (unfused IVF) and threshold are visible; the table is built after the first tile is in flight
 
-    const uint32_t lo_reg0 = (uint32_t)(((size_t)NW * capw * 8 + 16 + (IVF ? (size_t)a.w_eff * 24 + 32 : 0) + 15) & ~(size_t)15);
+    const uint32_t lo_reg0 = (uint32_t)(((size_t)NW * capw * 8 + 16 + NW * 8 + (IVF ? (size_t)a.w_eff * 24 + 32 : 0) + 15) & ~(size_t)15);
     const uint32_t hi_reg0 = lut_off + SK_LUT_BYTES;
     const int n_lo = (int)((lut_off - lo_reg0) / SK_WARP_BYTES);
     if (n_lo + (int)((a.smem_bytes - hi_reg0) / SK_WARP_BYTES) < NW) __trap();  // host sized the launch wrongly
@@ -1241,6 +1284,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     wt.cap = capw;
     wt.k = a.k;
     wt.count = 0;
+    wt.thr_w = thr_w;
+    wt.nw = NW;
+    wt.wid = wid;
 
     auto set_range = [&](long long tot, int nsplit, int split) {  // this warp's slice [base, base + cnt) of [0, tot)
         total = tot;
@@ -1396,7 +1442,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
                 if (lane == 0) {
                     make_plan(a.plan, b, s_f, s_pre, s_loc, s_cum);
                     s_plan[0] = a.plan.flags[b] != 0 ? 0 : a.plan.J[b];
-                    *cta_thr = RII_KEY_MAX;
+                    *cta_thr = RII_KEY_MAX;  // (thr_w is still all-MAX: the coarse pass does not use the warp lists)
                 }
             }
             __syncthreads();
@@ -1453,7 +1499,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
         }
         if (ntiles > 0) {  // drain: 32 more steps complete the last row of every lane
             const uint32_t rbw = rb + 4 * (((ntiles - 1) & 1) * SK_HALF_WORDS + SK_HALF_WORDS);
-            SK_BLOCK(rbw)
+            SK_BLOCK_CLAMP(rbw, myreg + SK_REGION_BYTES - 4)
             SK_EMIT((uint32_t)(base + eloc))
         }
         if (!(IVF && direct)) warp_compact(wt, cta_thr, lane);
@@ -1512,7 +1558,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 #define SK_DYN_SMEM (227 * 1024 - 64)
 static inline int skew_regions_fit(bool ivf, int nw, int capw, int w_eff)
 {
-    const size_t meta = (((size_t)nw * capw * 8 + 16 + (ivf ? (size_t)w_eff * 24 + 32 : 0)) + 15) & ~(size_t)15;
+    const size_t meta = (((size_t)nw * capw * 8 + 16 + (size_t)nw * 8 + (ivf ? (size_t)w_eff * 24 + 32 : 0)) + 15) & ~(size_t)15;
     const long long lut_off_min = 0x10000 - 2048, lut_off_max = 0x10000 - 1024;
     const long long n_lo = (lut_off_min - (long long)meta) / SK_WARP_BYTES;
     const long long n_hi = ((long long)SK_DYN_SMEM - (lut_off_max + SK_LUT_BYTES)) / SK_WARP_BYTES;

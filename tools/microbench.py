@@ -116,6 +116,21 @@ def main_():
                                                "pool_sort": float((clk[:, 6] - clk[:, 5]).mean()),
                                                "plan": float((clk[:, 1] - clk[:, 6]).mean()), "pool_size": float(clk[:, 7].mean())})
             print(json.dumps(out))
+        e3.set_option("fuse_coarse", 1)
+        e3.set_option("debug_clocks", 0)
+        for topk in (10, 100):
+            oi2 = torch.empty((B, topk), dtype=torch.int64, device=dev)
+            od2 = torch.empty((B, topk), dtype=torch.float32, device=dev)
+            for it in range(5):
+                if it == 2:
+                    torch.cuda.synchronize()
+                    lib.rii_profile_reset(e3._h)
+                _capi.check(lib.rii_query_batch_dev(e3._h, C.c_void_p(Q.data_ptr()), B, topk, None, 0, L, 1,
+                                                    C.c_void_p(oi2.data_ptr()), C.c_void_p(od2.data_ptr()),
+                                                    C.c_void_p(oc.data_ptr()), sp))
+            torch.cuda.synchronize()
+            ms, n = prof(lib, e3, "scan_ivf")
+            print(json.dumps({"what": "ivf_batch_topk", "topk": topk, "B": B, "L": L, "scan_ivf_ms": round(ms / max(n, 1), 4)}))
     if "assign" in a.what:
         n_as = min(N, 1000000)
         e2 = main.RiiCpp(cw, False, l2_variant=16)
