@@ -1030,10 +1030,10 @@ __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
     const int kq = (w.k + w.nw - 1) / w.nw;
     if (lane == 0) {
         if (w.count == w.k) atomicMin(cta_thr, w.keys[w.k - 1]);
-        if (w.count >= kq) w.thr_w[w.wid] = w.keys[kq - 1];
+        if (w.count >= kq) atomicMin(w.thr_w + w.wid, w.keys[kq - 1]);  // (atomics: other warps read this slot concurrently)
     }
     __syncwarp();
-    u64 t = lane < w.nw ? *reinterpret_cast<volatile u64 *>(w.thr_w + lane) : 0ull;
+    u64 t = lane < w.nw ? atomicMin(w.thr_w + lane, RII_KEY_MAX) : 0ull;   // atomic read
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const u64 y = __shfl_xor_sync(0xffffffffu, t, o);
