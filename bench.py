@@ -269,6 +269,41 @@ def run_ours(args):
         e2e = {"value": round(K * B / dt, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
                "d2h_bytes_per_step": B * k * 12 + B * 4, "single_query_call_us": round(lat * 1e6, 1)}
 
+    # ---- the HBM-bound side of the same engine: linear PQ-code scan over N >> L2 (north_star's ">= 70 % of the HBM
+    # roofline on the code scan"); random codes (throughput only), 1 query per launch, CUDA events inside the library
+    lin = None
+    if world == 1 and args.linear_n > 0:
+        try:
+            e.set_option("fuse_coarse", 1)
+            el = main.RiiCpp(cw, False, device=local, l2_variant=16)
+            nl, chunk = int(args.linear_n), 8000000
+            gen = torch.Generator(device=dev).manual_seed(7)
+            for s0 in range(0, nl, chunk):
+                c = min(chunk, nl - s0)
+                el.add_codes(torch.randint(0, 256, (c, M), dtype=torch.uint8, device=dev, generator=gen).cpu().numpy(), False)
+            lib.rii_profile_enable(el._h, 1)
+            q1 = dQ[:1]
+            li = torch.empty((1, 1), dtype=torch.int64, device=dev)
+            ld = torch.empty((1, 1), dtype=torch.float32, device=dev)
+            lc = torch.empty((1,), dtype=torch.int32, device=dev)
+            for it in range(13):
+                if it == 3:
+                    torch.cuda.synchronize()
+                    lib.rii_profile_reset(el._h)
+                flush.zero_()
+                _capi.check(lib.rii_query_batch_dev(el._h, C.c_void_p(q1.data_ptr()), 1, 1, None, 0, 0, 0,
+                                                    C.c_void_p(li.data_ptr()), C.c_void_p(ld.data_ptr()),
+                                                    C.c_void_p(lc.data_ptr()), sp))
+            torch.cuda.synchronize()
+            m_, n_ = C.c_double(0), C.c_int64(0)
+            lib.rii_profile_get(el._h, b"scan_linear", C.byref(m_), C.byref(n_))
+            lms = m_.value / max(n_.value, 1)
+            lin = {"kernel": "k_scan_skew32<NW=16, linear>", "workload": "linear scan, N=%d M=32 (random codes), topk=1, 1 query/launch" % nl,
+                   "bound": "hbm", "launch_ms": round(lms, 4), "algorithmic_bytes_per_launch": nl * M + 4 * M * CFG["Ks"],
+                   "achieved": round((nl * M + 4 * M * CFG["Ks"]) / (lms * 1e-3) / 1e9, 1), "unit": "GB/s"}
+            del el
+        except Exception as ex:  # never lose the headline line over the side measurement
+            lin = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -304,12 +339,18 @@ def run_ours(args):
                              "binding resource is the shared-memory lookup rate (DESIGN.md)"},
         "kernel_ms": prof,
     }
+    if lin is not None:
+        if "achieved" in lin:
+            lin.update({"peak": peak, "frac": round(lin["achieved"] / peak, 4)})
+        line["roofline_linear_scan"] = lin
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(cw, codes, Q)
     try:  # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (tools/ncu_summary.py)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         line["roofline"]["traffic"] = tr.get("k_scan_skew32_ivf_fused_bytes_per_launch")
         line["roofline"]["traffic_source"] = tr.get("source")
+        if lin is not None and "achieved" in lin:
+            lin["traffic"] = tr.get("k_scan_skew32_linear_N64M_bytes_per_launch") if int(args.linear_n) == 64000000 else None
     except Exception:
         pass
     print(json.dumps(line))
@@ -387,6 +428,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="queries per step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--linear-n", type=int, default=64000000,
+                    help="also time the HBM-bound linear scan over this many random codes (0 = skip); 1 GPU only")
     ap.add_argument("--shard", action="store_true", help="multi-GPU: partition the index by id range instead of replicating it")
     a = ap.parse_args()
     if a.warmup < 3:
