@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(RII_THREADS) k_adc_all(const float *__restrict
 #define SK_REGION_BYTES (SK_REGION_WORDS * 4)    // 288
 #define SK_WARP_BYTES (32 * SK_REGION_BYTES)     // 9216
 #define SK_LUT_BYTES 65536
-#define SK_MAX_K 192   // CTA list (<= k) + one warp buffer (64) are merged in registers: <= 256 keys
+#define SK_MAX_K 224
 
 struct SkewArgs {
     const float *T;            // (B, 32*Ks), or null: build the table in-kernel from Q / cw (K1 fused)
@@ -951,20 +951,12 @@ struct SkewArgs {
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)
 };
 
-// Top-k state of the v2 engine.  Each warp appends survivors to its own small buffer (SK_WCAP keys, ballot-compacted);
-// when the buffer is nearly full the warp MERGES it into the CTA's shared sorted list `gl` (<= k keys) under a lock:
-// list + buffer are sorted together in registers, the k smallest go back to the list, the shared threshold becomes
-// the list's k-th key -- the exact k-th best of everything merged so far -- and the buffer is empty again.  So every
-// warp filters with a CTA-wide threshold (pass rate ~k/n_cta instead of ~k/n_warp), buffers stay 64 keys for any k,
-// and at the end of a pass the list IS the CTA's result.
-#define SK_WCAP 64
 struct WarpTopk {
-    u64 *keys;   // shared, this warp's buffer (SK_WCAP keys)
-    int k;
+    u64 *keys;   // shared, this warp's buffer (>= cap keys)
+    int cap, k;  // cap = next_pow2(k + 32): compaction threshold of the current pass
     int count;   // warp-uniform
-    u64 *gl;     // shared, CTA list (256 slots)
-    int *gl_n;   // shared, number of valid keys in gl
-    int *lock;   // shared
+    u64 *thr_w;  // shared [nw]: every warp's ceil(k/nw)-th smallest key (RII_KEY_MAX until it has that many)
+    int nw, wid;
 };
 
 // Bitonic sort of 32*R keys held in registers (element e = r*32 + lane), ascending.  Exchanges at distance >= 32
@@ -1026,47 +1018,28 @@ __device__ __noinline__ void warp_sort_any(u64 *keys, int n, int lane)  // n <= 
     else warp_sort_buf<8>(keys, n, lane);
 }
 
-template <int R>
-__device__ __forceinline__ void merge_regs(WarpTopk &w, int lane, int ng)
+__device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
 {
-    u64 v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int e = r * 32 + lane;
-        // (atomic reads/writes of the list: it is touched by one warp at a time, under the lock, but by different warps)
-        v[r] = e < ng ? atomicMin(w.gl + e, RII_KEY_MAX) : (e - ng < w.count ? w.keys[e - ng] : RII_KEY_MAX);
-    }
-    warp_sort_regs<R>(v, lane);
-    const int keep = ng + w.count < w.k ? ng + w.count : w.k;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int e = r * 32 + lane;
-        if (e < keep) atomicExch(w.gl + e, v[r]);
-    }
-}
-
-__device__ __noinline__ void warp_merge(WarpTopk &w, u64 *cta_thr, int lane)
-{
-    if (w.count == 0) return;  // warp-uniform
-    if (lane == 0)
-        while (atomicCAS(w.lock, 0, 1) != 0) __nanosleep(32);
-    __syncwarp();
-    __threadfence_block();
-    const int ng = atomicAdd(w.gl_n, 0);
-    const int tot = ng + w.count;  // <= k + SK_WCAP <= 256
-    if (tot <= 64) merge_regs<2>(w, lane, ng);
-    else if (tot <= 128) merge_regs<4>(w, lane, ng);
-    else merge_regs<8>(w, lane, ng);
-    __threadfence_block();
-    __syncwarp();
+    const int n = w.count;  // <= cap <= 256
+    warp_sort_any(w.keys, n, lane);
+    w.count = n < w.k ? n : w.k;
+    // Two valid upper bounds of the CTA's k-th key tighten the shared threshold:
+    //  (1) this warp's own k-th key;
+    //  (2) the LARGEST, over all warps, of the warps' ceil(k/nw)-th keys: at least nw * ceil(k/nw) >= k keys lie below
+    //      it.  With the candidates spread evenly over the warps (2) is ~nw times tighter than (1) for k >= nw.
+    const int kq = (w.k + w.nw - 1) / w.nw;
     if (lane == 0) {
-        const int keep = tot < w.k ? tot : w.k;
-        atomicExch(w.gl_n, keep);
-        if (keep == w.k) atomicExch(cta_thr, atomicMin(w.gl + (w.k - 1), RII_KEY_MAX));  // exact k-th best so far
-        __threadfence_block();
-        atomicExch(w.lock, 0);
+        if (w.count == w.k) atomicMin(cta_thr, w.keys[w.k - 1]);
+        if (w.count >= kq) atomicMin(w.thr_w + w.wid, w.keys[kq - 1]);  // (atomics: other warps read this slot concurrently)
     }
-    w.count = 0;
+    __syncwarp();
+    u64 t = lane < w.nw ? atomicMin(w.thr_w + lane, RII_KEY_MAX) : 0ull;   // atomic read
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 y = __shfl_xor_sync(0xffffffffu, t, o);
+        t = t > y ? t : y;
+    }
+    if (lane == 0 && t != RII_KEY_MAX) atomicMin(cta_thr, t);
     __syncwarp();
 }
 
@@ -1081,7 +1054,7 @@ __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lane, floa
     if (!bal) return;
     if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;
     w.count += __popc(bal);
-    if (w.count + 32 > SK_WCAP) warp_merge(w, cta_thr, lane);
+    if (w.count + 32 > w.cap) warp_compact(w, cta_thr, lane);
 }
 
 // one lookup step.  The table sits at the 64 KB-aligned ABSOLUTE shared address 0x10000, so the byte-permute of
@@ -1262,16 +1235,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     const uint32_t lut_off = 0x10000u - smem_base;
     float *lut2 = reinterpret_cast<float *>(smem_raw + lut_off);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int capw = a.cap;
     long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     const uint32_t keys_off = 0;
-    // [NW warp buffers of SK_WCAP keys][CTA list gl: 256 keys][cta_thr][gl_n, lock][IVF plan arrays]
-    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * SK_WCAP;
-    u64 *gl = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * SK_WCAP;
-    u64 *cta_thr = gl + 256;
-    int *gl_n = reinterpret_cast<int *>(cta_thr + 1);
-    int *lock = gl_n + 1;
-    long long *s_off = reinterpret_cast<long long *>(cta_thr + 2);
+    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)wid * capw;
+    u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw + keys_off) + (size_t)NW * capw;
+    u64 *thr_w = cta_thr + 1;  // [NW]
+    long long *s_off = reinterpret_cast<long long *>(smem_raw + keys_off + (size_t)NW * capw * 8 + 8 + NW * 8);
     const int wq = IVF ? a.w_eff : 0;
     int *s_cum = reinterpret_cast<int *>(s_off + wq);
     int *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;  // s_plan: [J, flags]
@@ -1287,10 +1258,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             }
         }
     }
-    if (threadIdx.x == 0) { *cta_thr = RII_KEY_MAX; *gl_n = 0; *lock = 0; }
+    if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+    if (threadIdx.x < NW) thr_w[threadIdx.x] = RII_KEY_MAX;
     __syncthreads();  // plan (unfused IVF) and threshold are visible; the table is built after the first tile is in flight
 
-    const uint32_t lo_reg0 = (uint32_t)(((size_t)NW * SK_WCAP * 8 + 2048 + 16 + (IVF ? (size_t)a.w_eff * 24 + 32 : 0) + 15) & ~(size_t)15);
+    const uint32_t lo_reg0 = (uint32_t)(((size_t)NW * capw * 8 + 16 + NW * 8 + (IVF ? (size_t)a.w_eff * 24 + 32 : 0) + 15) & ~(size_t)15);
     const uint32_t hi_reg0 = lut_off + SK_LUT_BYTES;
     const int n_lo = (int)((lut_off - lo_reg0) / SK_WARP_BYTES);
     if (n_lo + (int)((a.smem_bytes - hi_reg0) / SK_WARP_BYTES) < NW) __trap();  // host sized the launch wrongly
@@ -1309,11 +1281,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     int segw = 0;
     WarpTopk wt;
     wt.keys = wkeys;
+    wt.cap = capw;
     wt.k = a.k;
     wt.count = 0;
-    wt.gl = gl;
-    wt.gl_n = gl_n;
-    wt.lock = lock;
+    wt.thr_w = thr_w;
+    wt.nw = NW;
+    wt.wid = wid;
 
     auto set_range = [&](long long tot, int nsplit, int split) {  // this warp's slice [base, base + cnt) of [0, tot)
         total = tot;
@@ -1385,6 +1358,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
     bool direct = fused;         // coarse pass: every distance goes to pool_d[center]
     // the warps' key buffers are idle during the coarse pass: they hold the nlist distances (host checks the size)
     uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + keys_off);
+    wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
     if (fused) {
         pc = a.centers;
         set_range(a.nlist, 1, 0);
@@ -1468,7 +1442,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
                 if (lane == 0) {
                     make_plan(a.plan, b, s_f, s_pre, s_loc, s_cum);
                     s_plan[0] = a.plan.flags[b] != 0 ? 0 : a.plan.J[b];
-                    *cta_thr = RII_KEY_MAX;  // (gl_n == 0, lock == 0: the coarse pass does not use the top-k lists)
+                    *cta_thr = RII_KEY_MAX;  // (thr_w is still all-MAX: the coarse pass does not use the warp lists)
                 }
             }
             __syncthreads();
@@ -1479,6 +1453,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             direct = false;
             segw = 0;
             wt.k = a.k;
+            wt.cap = next_pow2(wt.k + 32) < 64 ? 64 : next_pow2(wt.k + 32);
             wt.count = 0;
             set_range(J ? (long long)s_cum[J - 1] : 0, 1, 0);
             *reinterpret_cast<uint4 *>(smem_raw + myreg) = make_uint4(0, 0, 0, 0);
@@ -1527,22 +1502,51 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
             SK_BLOCK_CLAMP(rbw, myreg + SK_REGION_BYTES - 4)
             SK_EMIT((uint32_t)(base + eloc))
         }
-        if (!(IVF && direct)) warp_merge(wt, cta_thr, lane);
+        if (!(IVF && direct)) warp_compact(wt, cta_thr, lane);
         __syncthreads();
     }
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();
-    if (wid == 0) {  // the CTA list is the (sorted) result of the pass
-        const int n = *gl_n;
-        if (a.out.final) {
-            for (int i = lane; i < n; i += 32) {
-                const u64 key = gl[i];
-                a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(key);
-                a.out.out_dists[(size_t)b * a.k + i] = key_dist(key);
+    {   // CTA merge of the (sorted) warp lists, reusing the lut2 area for the keys
+        __shared__ int s_cnt[NW];
+        if (lane == 0) s_cnt[wid] = wt.count;
+        __syncthreads();
+        int tot = 0;
+        for (int w2 = 0; w2 < NW; ++w2) tot += s_cnt[w2];
+        const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw + keys_off);
+        if (tot <= 256) {
+            // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
+            if (wid == 0) {
+                u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
+                int o = 0;
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    for (int i = lane; i < s_cnt[w2]; i += 32) mk[o + i] = allkeys[(size_t)w2 * capw + i];
+                    o += s_cnt[w2];
+                }
+                warp_sort_any(mk, tot, lane);
+                const int n = tot < a.k ? tot : a.k;
+                if (a.out.final) {
+                    for (int i = lane; i < n; i += 32) {
+                        a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(mk[i]);
+                        a.out.out_dists[(size_t)b * a.k + i] = key_dist(mk[i]);
+                    }
+                    if (lane == 0) a.out.out_counts[b] = n;
+                } else {
+                    u64 *dst = a.out.partial + ((size_t)b * gridDim.x + blockIdx.x) * a.k;
+                    for (int i = lane; i < a.k; i += 32) dst[i] = i < n ? mk[i] : RII_KEY_MAX;
+                }
             }
-            if (lane == 0) a.out.out_counts[b] = n;
         } else {
-            u64 *dst = a.out.partial + ((size_t)b * gridDim.x + blockIdx.x) * a.k;
-            for (int i = lane; i < a.k; i += 32) dst[i] = i < n ? gl[i] : RII_KEY_MAX;
+            BlockTopk tk;
+            const int mcap = next_pow2(NW * a.k + 1);
+            tk.keys = reinterpret_cast<u64 *>(smem_raw + lut_off);
+            tk.count = reinterpret_cast<int *>(smem_raw + lut_off + (size_t)mcap * 8 + 8);
+            tk.thr = reinterpret_cast<u64 *>(smem_raw + lut_off + (size_t)mcap * 8);
+            tk.cap = mcap;
+            tk.k = a.k;
+            tk.init();
+            for (int w2 = 0; w2 < NW; ++w2)
+                for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
+            emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
         }
     }
     if (dbg && threadIdx.x == 0) dbg[3] = clock64();
@@ -1554,8 +1558,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_skew32(SkewArgs a)
 #define SK_DYN_SMEM (227 * 1024 - 64)
 static inline int skew_regions_fit(bool ivf, int nw, int capw, int w_eff)
 {
-    (void)capw;
-    const size_t meta = (((size_t)nw * SK_WCAP * 8 + 2048 + 16 + (ivf ? (size_t)w_eff * 24 + 32 : 0)) + 15) & ~(size_t)15;
+    const size_t meta = (((size_t)nw * capw * 8 + 16 + (size_t)nw * 8 + (ivf ? (size_t)w_eff * 24 + 32 : 0)) + 15) & ~(size_t)15;
     const long long lut_off_min = 0x10000 - 2048, lut_off_max = 0x10000 - 1024;
     const long long n_lo = (lut_off_min - (long long)meta) / SK_WARP_BYTES;
     const long long n_hi = ((long long)SK_DYN_SMEM - (lut_off_max + SK_LUT_BYTES)) / SK_WARP_BYTES;

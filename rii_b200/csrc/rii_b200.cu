@@ -456,7 +456,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         const int nw = skew_pick_nw(false, capw, 0);
         const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
         const bool use_v2 = v2_ok && (h->opt_scan_kernel == 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
-        if (h->opt_scan_kernel == 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2 needs M == 32, no target_ids and topk <= 192");
+        if (h->opt_scan_kernel == 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2 needs M == 32, no target_ids and topk <= 224");
         if (use_v2) {
             parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                              std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
@@ -532,12 +532,13 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     const int nw2 = skew_pick_nw(true, capw2, w_eff);
     const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-    if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 192 and a short list plan");
+    if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && (size_t)h->nlist * 4 <= (size_t)nw2 * SK_WCAP * 8;
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && h->nlist <= 1024 &&
+                      (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8;
     if (!fuse) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;

@@ -325,7 +325,7 @@ def test_skew_kernel_matches_oracle(N):
     e.set_option("scan_kernel", 2)
     for q in Q:
         T = O.dtable(q, cw, 16)
-        for topk in (1, 10, 192):
+        for topk in (1, 10, 224):
             if topk > N:
                 continue
             ids, d = e.query_linear(q, topk, EMPTY)
@@ -348,7 +348,7 @@ def test_skew_kernel_small_ks_and_ties():
     e2.set_option("scan_kernel", 2)
     for q in Q:
         T = O.dtable(q, cw, 16)
-        for topk in (1, 50, 190):
+        for topk in (1, 50, 200):
             r1, r2 = e1.query_linear(q, topk, EMPTY), e2.query_linear(q, topk, EMPTY)
             assert r1 == r2
             assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(T, codes, topk), "ties")
