@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rii_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "topk.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "topk.cuh"), os.path.join(HERE, "csrc", "scan_dual.cuh"), os.path.join(HERE, "csrc", "scan_stream.cuh"),
         os.path.join(HERE, "..", "include", "rii_b200.h")]
 OUT = os.path.join(HERE, "librii_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

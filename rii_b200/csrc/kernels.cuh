@@ -940,6 +940,7 @@ struct SkewArgs {
     long long N;               // linear: rows of the shard
     const long long *offsets;  // IVF: CSR
     const int *ids;
+    const long long *skew_off; // v4 (scan_stream.cuh): first physical row of every posting list in the skew64 table
     const int *ranked, *cum, *J, *flags;  // IVF plan
     int w_eff;
     int Ks, k, cap;            // cap = per-warp key capacity (power of two >= max(k, w_eff) + 32)
@@ -1569,3 +1570,6 @@ static inline size_t skew_smem_bytes(int nw, bool ivf, int capw, int w_eff)
     return (size_t)SK_LUT_BYTES + (size_t)nw * SK_WARP_BYTES + (size_t)nw * capw * 8 + 16 + 64 +
            (ivf ? (size_t)w_eff * 24 + 32 : 0);
 }
+
+#include "scan_dual.cuh"
+#include "scan_stream.cuh"

@@ -112,7 +112,13 @@ struct rii_index {
     float *d_Dm = nullptr;
     uint8_t *d_codes = nullptr;
     DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
-    DevBuf codes_list;  // (N, 32) list-ordered copy of the codes (row p <-> ids[p]); M == 32 only
+    DevBuf codes_list;  // (N, 32) list-ordered copy of the codes (row p <-> ids[p]); M == 32, v2 / v3 engines only (lazy)
+    bool codes_list_valid = false;
+    // skew64 copies (scan_stream.cuh; M == 32, built lazily on the query stream): the codes by id, every local posting
+    // list (segment i at physical row skew_off[i]) and the coarse centers
+    DevBuf skew_lin, skew_lists, skew_off, centers_skew, skew_misc_off;
+    long long skew_lin_rows = -1;  // rows covered by skew_lin (-1: stale)
+    bool skew_lists_valid = false, centers_skew_valid = false;
     bool has_global = false;
 
     std::vector<uint8_t> h_centers;      // (nlist, M)
@@ -126,8 +132,11 @@ struct rii_index {
 
     DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
     int opt_debug_clocks = 0;
+    int opt_stream_warps = 12; // warps per CTA of the v4 engine (8 or 12)
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
-    int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernel, 2 skewed conflict-free kernel (M == 32 only)
+    int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
+                              // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
+                              // when it applies).  v2 / v3 / v4: M == 32 only
 
     long long n_total() const { return N_total >= 0 ? N_total : N; }
 };
@@ -244,14 +253,8 @@ int upload_lists(rii_index *h)
     std::vector<int> len(nlist);
     for (int i = 0; i < nlist; ++i) len[i] = (int)(h->h_offsets[i + 1] - h->h_offsets[i]);
     if (nlist) CK(cudaMemcpyAsync(h->loc_len.p, len.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, h->stream));
-    if (h->M == 32 && !h->h_ids.empty()) {  // list-ordered code copy for the streaming posting-list scan (kernels.cuh, K5 v2)
-        const long long n = (long long)h->h_ids.size();
-        CKR(h->codes_list.ensure((size_t)n * 32));
-        k_gather_rows32_by_list<<<(unsigned)((n * 2 + 255) / 256), 256, 0, h->stream>>>(h->d_codes, h->ids.as<int>(), n,
-                                                                                       h->codes_list.as<uint8_t>());
-        LAUNCHED();
-        CK(cudaGetLastError());
-    }
+    h->codes_list_valid = false;  // derived copies are rebuilt lazily by the first query that needs them
+    h->skew_lists_valid = false;
     CK(cudaStreamSynchronize(h->stream));
     if (!h->has_global) {
         std::sort(len.begin(), len.end());
@@ -294,6 +297,7 @@ int update_posting_lists(rii_index *h, long long start, long long num)
 int set_centers(rii_index *h, const uint8_t *centers_host, int nlist)
 {
     h->nlist = nlist;
+    h->centers_skew_valid = false;
     h->h_centers.assign(centers_host, centers_host + (size_t)nlist * h->M);
     CKR(h->centers.ensure((size_t)nlist * h->M));
     CK(cudaMemcpyAsync(h->centers.p, h->h_centers.data(), (size_t)nlist * h->M, cudaMemcpyHostToDevice, h->stream));
@@ -371,6 +375,93 @@ int grow_codes(rii_index *h, long long rows)
     return 0;
 }
 
+// ---- derived code layouts (M == 32), built lazily on the query stream ------------------------------------
+int ensure_codes_list(rii_index *h, cudaStream_t st)  // list-ordered copy for the v2 / v3 posting-list scans
+{
+    if (h->codes_list_valid || h->h_ids.empty()) return 0;
+    const long long n = (long long)h->h_ids.size();
+    CKR(h->codes_list.ensure((size_t)n * 32));
+    k_gather_rows32_by_list<<<(unsigned)((n * 2 + 255) / 256), 256, 0, st>>>(h->d_codes, h->ids.as<int>(), n, h->codes_list.as<uint8_t>());
+    LAUNCHED();
+    CK(cudaGetLastError());
+    h->codes_list_valid = true;
+    return 0;
+}
+
+int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
+               long long prows, uint8_t *out, cudaStream_t st)
+{
+    if (prows <= 0) return 0;
+    const long long thr = prows * 2;
+    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(codes, ids, offsets, d_skew_off, nseg, n_single, 0, prows, out);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id (linear scan, scan_stream.cuh)
+{
+    if (h->skew_lin_rows == h->N) return 0;
+    const long long prows = skew64_rows(h->N);
+    CKR(h->skew_lin.ensure((size_t)prows * 32));
+    CKR(h->skew_misc_off.ensure(32));
+    const long long off[2] = {0, prows};
+    CK(cudaMemcpyAsync(h->skew_misc_off.p, off, 16, cudaMemcpyHostToDevice, st));
+    CKR(skew_build(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N, prows, h->skew_lin.as<uint8_t>(), st));
+    h->skew_lin_rows = h->N;
+    return 0;
+}
+
+int ensure_centers_skew(rii_index *h, cudaStream_t st)  // skew64 of the coarse centers (fused coarse pass)
+{
+    if (h->centers_skew_valid) return 0;
+    const long long prows = skew64_rows(h->nlist);
+    CKR(h->centers_skew.ensure((size_t)prows * 32));
+    CKR(h->skew_misc_off.ensure(32));
+    const long long off[2] = {0, prows};
+    CK(cudaMemcpyAsync(h->skew_misc_off.as<long long>() + 2, off, 16, cudaMemcpyHostToDevice, st));
+    CKR(skew_build(h->centers.as<uint8_t>(), nullptr, nullptr, h->skew_misc_off.as<long long>() + 2, 1, h->nlist, prows,
+                   h->centers_skew.as<uint8_t>(), st));
+    h->centers_skew_valid = true;
+    return 0;
+}
+
+int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local posting list
+{
+    if (h->skew_lists_valid) return 0;
+    const int nlist = h->nlist;
+    std::vector<long long> off((size_t)nlist + 1, 0);
+    for (int i = 0; i < nlist; ++i) off[i + 1] = off[i] + skew64_rows(h->h_offsets[i + 1] - h->h_offsets[i]);
+    CKR(h->skew_off.ensure((size_t)(nlist + 1) * 8));
+    CKR(h->skew_lists.ensure((size_t)std::max<long long>(1, off[nlist]) * 32));
+    CK(cudaMemcpyAsync(h->skew_off.p, off.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, st));
+    CKR(skew_build(h->d_codes, h->ids.as<int>(), h->offsets.as<long long>(), h->skew_off.as<long long>(), nlist, 0, off[nlist],
+                   h->skew_lists.as<uint8_t>(), st));
+    h->skew_lists_valid = true;
+    return 0;
+}
+
+// ---- v4 (register-streaming over skew64) scan launcher --------------------------------------------------
+int stream_pick_nw(const rii_index *h, bool ivf, int capw, int w_eff)
+{
+    const int nw = h->opt_stream_warps == 8 ? 8 : 12;
+    return stream_fits(ivf, nw, capw, w_eff) ? nw : (stream_fits(ivf, 8, capw, w_eff) ? 8 : 0);
+}
+
+template <int NW, bool IVF> int launch_stream_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
+{
+    CKR(set_smem(k_scan_stream32<NW, IVF>, smem));
+    k_scan_stream32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
+    return 0;
+}
+
+int launch_stream(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
+{
+    const size_t smem = SK_DYN_SMEM;
+    if (ivf) return nw == 12 ? launch_stream_t<12, true>(a, parts, B, smem, st) : launch_stream_t<8, true>(a, parts, B, smem, st);
+    return nw == 12 ? launch_stream_t<12, false>(a, parts, B, smem, st) : launch_stream_t<8, false>(a, parts, B, smem, st);
+}
+
 // ---- v2 (skewed) scan launcher: the most warps per SM whose shared-memory footprint fits ---------------
 int skew_pick_nw(bool ivf, int capw, int w_eff)
 {
@@ -384,6 +475,34 @@ template <int NW, bool IVF> int launch_skew_t(const SkewArgs &a, int parts, int 
     CKR(set_smem(k_scan_skew32<NW, IVF>, smem));
     k_scan_skew32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
     return 0;
+}
+
+// ---- v3 (dual-stream FFMA2) scan launcher -------------------------------------------------------------
+int dual_pick_nw(bool ivf, int capw, int w_eff)
+{
+    for (int nw : {11, 10, 8})
+        if (dual_regions_fit(ivf, nw, capw, w_eff) >= nw) return nw;
+    return 0;
+}
+
+template <int NW, bool IVF> int launch_dual_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
+{
+    CKR(set_smem(k_scan_dual32<NW, IVF>, smem));
+    k_scan_dual32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
+    return 0;
+}
+
+int launch_dual(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
+{
+    const size_t smem = SK_DYN_SMEM;
+    if (ivf) {
+        if (nw == 11) return launch_dual_t<11, true>(a, parts, B, smem, st);
+        if (nw == 10) return launch_dual_t<10, true>(a, parts, B, smem, st);
+        return launch_dual_t<8, true>(a, parts, B, smem, st);
+    }
+    if (nw == 11) return launch_dual_t<11, false>(a, parts, B, smem, st);
+    if (nw == 10) return launch_dual_t<10, false>(a, parts, B, smem, st);
+    return launch_dual_t<8, false>(a, parts, B, smem, st);
 }
 
 int launch_skew(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
@@ -453,10 +572,11 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         const size_t smem = scan_smem_bytes(lutf, cap, 0);
         // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
         const int capw = std::max(64, next_pow2(c.topk + 32));
-        const int nw = skew_pick_nw(false, capw, 0);
+        const int eng = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;  // v4 unless v2 / v3 is asked for
+        const int nw = eng == 4 ? stream_pick_nw(h, false, capw, 0) : eng == 3 ? dual_pick_nw(false, capw, 0) : skew_pick_nw(false, capw, 0);
         const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
-        const bool use_v2 = v2_ok && (h->opt_scan_kernel == 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
-        if (h->opt_scan_kernel == 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2 needs M == 32, no target_ids and topk <= 224");
+        const bool use_v2 = v2_ok && (h->opt_scan_kernel >= 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
+        if (h->opt_scan_kernel >= 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 needs M == 32, no target_ids and topk <= 224");
         if (use_v2) {
             parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                              std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
@@ -469,9 +589,14 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
-            Prof pr(h, st, PK_SCAN_LINEAR);
             sa.smem_bytes = SK_DYN_SMEM;
-            CKR(launch_skew(nw, false, sa, parts, B, st));
+            if (eng == 4) {
+                CKR(ensure_skew_lin(h, st));
+                sa.codes = h->skew_lin.as<uint8_t>();
+            }
+            Prof pr(h, st, PK_SCAN_LINEAR);
+            CKR(eng == 4 ? launch_stream(nw, false, sa, parts, B, st)
+                         : eng == 3 ? launch_dual(nw, false, sa, parts, B, st) : launch_skew(nw, false, sa, parts, B, st));
         } else {
             CKR(ensure_T());
             a.T = h->T.as<float>();
@@ -529,16 +654,25 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // fits shared memory.  With one CTA per query (parts == 1) the coarse ranking and the plan are fused into the
     // same kernel (two passes of one engine): no k_coarse_rank launch at all.
     const int capw2 = std::max(64, next_pow2(c.topk + 32));
-    const int nw2 = skew_pick_nw(true, capw2, w_eff);
-    const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && h->codes_list.p != nullptr;
+    const int eng2 = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;
+    const int nw2 = eng2 == 4 ? stream_pick_nw(h, true, capw2, w_eff) : eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
+    const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-    if (h->opt_scan_kernel == 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2 (ivf) needs M == 32, topk <= 224 and a short list plan");
+    if (h->opt_scan_kernel >= 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 (ivf) needs M == 32, topk <= 224 and a short list plan");
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
     const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && h->nlist <= 1024 &&
                       (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8;
+    if (use_v2) {
+        if (eng2 == 4) {
+            CKR(ensure_skew_lists(h, st));
+            if (fuse) CKR(ensure_centers_skew(h, st));
+        } else {
+            CKR(ensure_codes_list(h, st));
+        }
+    }
     if (!fuse) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
@@ -600,6 +734,11 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
             if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
+            if (eng2 == 4) {
+                sa.codes = h->skew_lists.as<uint8_t>();
+                sa.skew_off = h->skew_off.as<long long>();
+                if (fuse) sa.centers = h->centers_skew.as<uint8_t>();
+            }
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         }
         if (!use_v2) {
@@ -610,7 +749,8 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         Prof pr(h, st, PK_SCAN_IVF);
         if (use_v2) {
             sa.smem_bytes = SK_DYN_SMEM;
-            CKR(launch_skew(nw2, true, sa, parts, B, st));
+            CKR(eng2 == 4 ? launch_stream(nw2, true, sa, parts, B, st)
+                          : eng2 == 3 ? launch_dual(nw2, true, sa, parts, B, st) : launch_skew(nw2, true, sa, parts, B, st));
         } else if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
             DISPATCH_M(M, {
@@ -771,7 +911,7 @@ int rii_destroy(rii_index_t *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->dbg, &h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
+    for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
         b->release();
@@ -797,6 +937,7 @@ int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_fl
     if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->N = N0 + n;
+    h->skew_lin_rows = -1;
     if (h->verbose) printf("%lld new vectors are added.\nTotal number of codes is %lld\n", (long long)n, h->N);
     if (update_flag) {
         if (h->verbose) printf("Start to update posting lists\n");
@@ -850,6 +991,8 @@ int rii_clear(rii_index_t *h)
     if (!h) return fail(RII_ERR_ARG, "null index");
     h->N = 0;
     h->nlist = 0;
+    h->skew_lin_rows = -1;
+    h->skew_lists_valid = h->centers_skew_valid = h->codes_list_valid = false;
     h->h_centers.clear();
     h->h_offsets.assign(1, 0);
     h->h_ids.clear();
@@ -896,8 +1039,14 @@ int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk,
 int rii_set_option(rii_index_t *h, const char *name, int64_t value)
 {
     if (!h || !name) return fail(RII_ERR_ARG, "bad arguments");
+    if (!strcmp(name, "stream_warps")) {
+        if (value != 8 && value != 12) return fail(RII_ERR_ARG, "stream_warps must be 8 or 12");
+        h->opt_stream_warps = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "scan_kernel")) {
-        if (value < 0 || value > 2) return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 or 2");
+        if (value < 0 || value > 4)
+            return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural layout), 2 (skewed), 3 (dual-stream skewed) or 4 (register streaming)");
         h->opt_scan_kernel = (int)value;
         return 0;
     }

@@ -1,0 +1,496 @@
+// ===================================================================================================
+// K2/K5 v4 ("stream"): the skewed scan engine over a PRE-SKEWED copy of the codes.
+//
+// What v2 / v3 taught (profiles/r01_*): the lookup loop is bound by the shared-memory pipe, not by issue slots.  Every
+// code byte went global -> shared (LDGSTS into per-lane padded regions) -> register (one LDS.32 + funnel shift per
+// 4 bytes) just so that lane l could read its stream l bytes late, with warp barriers around every tile.
+//
+// Here the lag is applied ONCE, when the index is built: the "skew64" layout stores, for every 64 consecutive rows of
+// a segment (the whole table for the linear scan, one posting list for the IVF scan), 64 byte streams -- stream s =
+// rows s, 64 + s, 128 + s, ... back to back -- each delayed by (s & 31) bytes and cut into 32-byte windows:
+//        window[b][s][i] = stream_s[32 b - (s & 31) + i]          (zeros before the first / after the last row)
+// Same size as the codes (+ one block of 64 rows per segment).  Lane l of a warp owns streams l (x) and 32 + l (y); a
+// 2 KB block b holds the 64 windows as four 512-byte quarters [x bytes 0-15 | x 16-31 | y 0-15 | y 16-31] x 32 lanes,
+// so a lane copies exactly the four 16-byte chunks it will consume itself (cp.async, 512 contiguous bytes per warp
+// instruction, conflict free) into a private 4-stage ring and reads them back with four LDS.128: no cross-lane
+// traffic, hence NO warp barrier and no funnel shifts -- the lookup address is one PRMT of a register.  Per pair of
+// lookups:       2 PRMT + 2 LDS + 2 FFMA2            (+ 4 LDGSTS + 4 LDS.128 per 64 lookups)
+// with the predicate-free accumulation of scan_dual.cuh (acc = acc * keep_t + v, out = acc * sel_t + out).  Distances
+// are still the sequential fp32 sums of src/rii.h:386-394, bit for bit.  Three blocks (6 KB per warp, 72 KB per SM)
+// are in flight while one is scanned.  Feeding variants measured in isolation (tools/ubench_feed.cu,
+// profiles/r01_ubench_feed.jsonl; lookups/clk/SM, HBM source): this ring 20.9, LDG.256 into registers 19.3 (and the
+// real kernel lost much more to scoreboard sharing between its 8 outstanding LDG.256 and the table LDS), TMA bulk 19.7.
+//
+// Work is split by GROUPS of 64 rows.  A warp walks a contiguous range of the pass's flattened group list; at the end
+// of a segment (or of its range) one extra "drain" block finishes the lagging rows.  Rows past a segment's take
+// count are masked when their distance completes.
+// ===================================================================================================
+#pragma once
+
+#define ST_D 3                      // blocks in flight ahead of the one being scanned
+#define ST_R (ST_D + 1)             // ring stages per warp
+#define ST_BLOCK_BYTES 2048         // 64 windows of 32 bytes
+#define ST_RING_BYTES (ST_R * ST_BLOCK_BYTES)
+#define ST_TABLE_LIMIT 1e37f        // 32 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
+
+// physical rows of a skew64 segment holding `len` code rows
+static __host__ __device__ inline long long skew64_rows(long long len) { return 64 * ((len + 63) / 64 + 1); }
+
+// Build (a range of) skew64 segments.  codes: (rows, 32) by id; ids / offsets: CSR of the segments (null: ONE segment
+// = rows [0, n_single) in id order); skew_off: (nseg + 1) first physical row (32-byte unit) of every segment, a
+// multiple of 64.  One thread per 16-byte chunk.
+__global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__restrict__ ids, const long long *__restrict__ offsets,
+                               const long long *__restrict__ skew_off, int nseg, long long n_single, long long prow0,
+                               long long prow1, uint8_t *__restrict__ out)
+{
+    const long long i = prow0 * 2 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the table
+    const long long prow = i >> 1;
+    if (prow >= prow1) return;
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (skew_off[mid] <= prow) lo = mid; else hi = mid - 1;
+    }
+    const long long c16 = i - skew_off[lo] * 2;  // chunk within the segment: block b, quarter q, lane l
+    const long long b = c16 >> 7;
+    const int q = (int)(c16 >> 5) & 3, l = (int)(c16 & 31);
+    const int s = (q >> 1) * 32 + l, half = q & 1, lag = l;
+    const long long len = offsets ? offsets[lo + 1] - offsets[lo] : n_single;
+    const long long ioff = offsets ? offsets[lo] : 0;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const long long x = 32 * b - lag + 16 * half + j;  // byte of stream s
+        if (x >= 0) {
+            const long long r = 64 * (x >> 5) + s;         // row of the segment
+            if (r < len) {
+                const long long id = ids ? (long long)ids[ioff + r] : r;
+                w[j >> 2] |= (uint32_t)__ldg(codes + id * 32 + (x & 31)) << (8 * (j & 3));
+            }
+        }
+    }
+    reinterpret_cast<uint4 *>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+#define ST_LDS128(W, A)                                                                                       \
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"((W)[0]), "=r"((W)[1]), "=r"((W)[2]), "=r"((W)[3]) : "r"(A))
+// issue the copy of the next block of this warp's walk (data block or drain block) into ring stage S and describe
+// it: D = flattened group << 2 | y row valid << 1 | x row valid   (0 for a drain block).  Past the end of the walk
+// only an (empty) group is committed, so that "wait_group ST_D" always means "the block of this stage has landed".
+#define ST_ISSUE(S, D, ACTIVE)                                                                                \
+    {                                                                                                         \
+        if (ACTIVE) {                                                                                         \
+            const int g_ = cur_f - seg_g0;                                                                    \
+            const uint8_t *p_ = pc + ((size_t)(seg_prow + (long long)g_ * 64)) * 32 + lane * 16;              \
+            if (!drain_next) {                                                                                \
+                const int r_ = g_ * 64 + lane;                                                                \
+                D = ((uint32_t)cur_f << 2) | (r_ < seg_take ? 1u : 0u) | (r_ + 32 < seg_take ? 2u : 0u);      \
+                ++cur_f;                                                                                      \
+                drain_next = cur_f == f_end || cur_f == seg_gend;                                             \
+            } else { /* the block after the segment's (or the range's) last group: only the lagging bytes matter */ \
+                D = 0u;                                                                                       \
+                drain_next = false;                                                                           \
+                if (cur_f < f_end) load_seg(seg + 1);                                                         \
+            }                                                                                                 \
+            const uint32_t dst_ = ring + (S) * ST_BLOCK_BYTES;                                                \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_), "l"(p_));                   \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 512), "l"(p_ + 512));       \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1024), "l"(p_ + 1024));     \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1536), "l"(p_ + 1536));     \
+        }                                                                                                     \
+        asm volatile("cp.async.commit_group;");                                                               \
+    }
+#define ST_WORD(BX, BY, Q)                                                                                    \
+    DU_STEP(BX[Q], BY[Q], 0, 4 * (Q) + 0)                                                                     \
+    DU_STEP(BX[Q], BY[Q], 1, 4 * (Q) + 1)                                                                     \
+    DU_STEP(BX[Q], BY[Q], 2, 4 * (Q) + 2)                                                                     \
+    DU_STEP(BX[Q], BY[Q], 3, 4 * (Q) + 3)
+#define ST_BLOCK(BX, BY)                                                                                      \
+    {                                                                                                         \
+        ST_WORD(BX, BY, 0) ST_WORD(BX, BY, 1) ST_WORD(BX, BY, 2) ST_WORD(BX, BY, 3)                           \
+        ST_WORD(BX, BY, 4) ST_WORD(BX, BY, 5) ST_WORD(BX, BY, 6) ST_WORD(BX, BY, 7)                           \
+    }
+// one pipeline stage: block m + S lives in ring stage S; the stage of block m + S - 1 takes block m + S + ST_D
+#define ST_STAGE(S)                                                                                           \
+    if (m + (S) < nblk) {                                                                                     \
+        const uint32_t dprev_ = dsc[((S) + ST_D) % ST_R];                                                     \
+        ST_ISSUE(((S) + ST_D) % ST_R, dsc[((S) + ST_D) % ST_R], m + (S) + ST_D < nblk)                        \
+        asm volatile("cp.async.wait_group 3;" ::: "memory");                                                  \
+        uint32_t wx_[8], wy_[8];                                                                              \
+        ST_LDS128(wx_, ring + (S) * ST_BLOCK_BYTES);                                                          \
+        ST_LDS128(wx_ + 4, ring + (S) * ST_BLOCK_BYTES + 512);                                                \
+        ST_LDS128(wy_, ring + (S) * ST_BLOCK_BYTES + 1024);                                                   \
+        ST_LDS128(wy_ + 4, ring + (S) * ST_BLOCK_BYTES + 1536);                                               \
+        ST_BLOCK(wx_, wy_)                                                                                    \
+        float dx_, dy_;                                                                                       \
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(dx_), "=f"(dy_) : "l"(out2));                                      \
+        out2 = 0ull;                                                                                          \
+        emit2(dx_, dy_, dprev_);                                                                              \
+    }
+
+// Args: SkewArgs (kernels.cuh) with `codes` = skew64 table of the pass-1 rows (linear: the codes by id, one segment;
+// IVF: every local posting list, segment i at physical row skew_off[i]) and `centers` = skew64 of the coarse centers.
+template <int NW, bool IVF>
+__global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout (dynamic shared memory; the window starts at absolute shared address ~1 KB):
+    //   [NW key buffers][cta_thr][thr_w][segments: s_off, s_prow i64[wq] | s_gcum, s_take, s_cum, s_f, s_pre, s_loc i32[wq] | s_plan]
+    //   ... lut2 (64 KB) at ABSOLUTE shared address 0x10000 ... [NW rings of 8 KB; between the passes: selection scratch]
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t lut_off = 0x10000u - smem_base;
+    float *lut2 = reinterpret_cast<float *>(smem_raw + lut_off);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int capw = a.cap;
+    long long *dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    u64 *wkeys = reinterpret_cast<u64 *>(smem_raw) + (size_t)wid * capw;
+    u64 *cta_thr = reinterpret_cast<u64 *>(smem_raw) + (size_t)NW * capw;
+    u64 *thr_w = cta_thr + 1;  // [NW]
+    const int wq = IVF ? a.w_eff : 1;
+    long long *s_off = reinterpret_cast<long long *>(smem_raw + (size_t)NW * capw * 8 + 8 + NW * 8);
+    long long *s_prow = s_off + wq;
+    int *s_gcum = reinterpret_cast<int *>(s_prow + wq);
+    int *s_take = s_gcum + wq, *s_cum = s_take + wq, *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;
+    const uint32_t hi0 = lut_off + SK_LUT_BYTES;                      // scratch above the table
+    // the warps' key buffers are idle during the coarse pass: they hold the nlist distances (host checks the size)
+    uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw);
+    if ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
+        __trap();  // host sized the launch wrongly
+    const uint32_t ring = smem_base + hi0 + wid * ST_RING_BYTES + lane * 16;  // this lane's chunk column of the warp's ring
+    const int b = blockIdx.y;
+    const bool fused = IVF && a.centers != nullptr;
+    int J = 0;  // segments of the current pass (after dropping empty ones)
+
+    // lane 0 of warp 0: turn (s_cum = inclusive local take counts, s_off, s_prow by rank) into the compact segment list
+    auto compact_segments = [&](int Jp) -> int {
+        int jj = 0, g = 0, prev = 0;
+        for (int j = 0; j < Jp; ++j) {
+            const int take = s_cum[j] - prev;
+            prev = s_cum[j];
+            if (take > 0) {
+                g += (take + 63) >> 6;
+                s_gcum[jj] = g;
+                s_take[jj] = take;
+                s_off[jj] = s_off[j];
+                s_prow[jj] = s_prow[j];
+                ++jj;
+            }
+        }
+        return jj;
+    };
+    if constexpr (IVF) {
+        if (!fused) {
+            const int Jp = (a.flags[b] != 0) ? 0 : a.J[b];
+            for (int j = threadIdx.x; j < Jp; j += blockDim.x) {
+                const int no = a.ranked[(size_t)b * a.w_eff + j];
+                s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
+                s_off[j] = a.offsets[no];
+                s_prow[j] = a.skew_off[no];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_plan[0] = compact_segments(Jp);
+        } else if (threadIdx.x == 0) {  // coarse pass: one segment, the skew64 copy of the centers
+            s_gcum[0] = (a.nlist + 63) >> 6;
+            s_take[0] = a.nlist;
+            s_off[0] = 0;
+            s_prow[0] = 0;
+            s_plan[0] = 1;
+        }
+    } else if (threadIdx.x == 0) {
+        s_gcum[0] = (int)((a.N + 63) >> 6);
+        s_take[0] = (int)a.N;
+        s_off[0] = 0;
+        s_prow[0] = 0;
+        s_plan[0] = a.N > 0 ? 1 : 0;
+    }
+    if (threadIdx.x == 0) *cta_thr = RII_KEY_MAX;
+    if (threadIdx.x < NW) thr_w[threadIdx.x] = RII_KEY_MAX;
+    __syncthreads();
+    J = s_plan[0];
+
+    const uint32_t colreg = 0x00010000u | (uint32_t)((32 - lane) * 4);  // table address 0x10000 | column byte offset
+    float keep[32], sel[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        keep[t] = lane == t ? 0.f : 1.f;
+        sel[t] = lane == t ? 1.f : 0.f;
+    }
+
+    // per-pass state (warp-uniform)
+    const uint8_t *pc = fused ? a.centers : a.codes;  // skew64 table of the pass
+    int f0 = 0, f_end = 0, cur_f = 0, nblk = 0;
+    int seg = 0, seg_g0 = 0, seg_gend = 0, seg_take = 0;
+    long long seg_prow = 0;
+    bool drain_next = false;
+    WarpTopk wt;
+    wt.keys = wkeys;
+    wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
+    wt.k = a.k;
+    wt.count = 0;
+    wt.thr_w = thr_w;
+    wt.nw = NW;
+    wt.wid = wid;
+
+    auto seg_of = [&](int f) -> int {  // segment holding flattened group f
+        int lo = 0, hi = J - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_gcum[mid] > f) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    auto load_seg = [&](int j) {
+        seg = j;
+        seg_g0 = j ? s_gcum[j - 1] : 0;
+        seg_gend = s_gcum[j];
+        seg_take = s_take[j];
+        seg_prow = s_prow[j];
+    };
+    auto set_range = [&](int nsplit, int split) {  // this warp's slice [f0, f_end) of the pass's groups
+        const int G = J ? s_gcum[J - 1] : 0;
+        const int nvs = nsplit * NW;
+        const int per = (G + nvs - 1) / nvs;
+        f0 = (split * NW + wid) * per;
+        if (f0 > G) f0 = G;
+        f_end = f0 + per < G ? f0 + per : G;
+        cur_f = f0;
+        drain_next = false;
+        nblk = 0;
+        if (f_end > f0) {
+            const int sa_ = seg_of(f0), sb_ = seg_of(f_end - 1);
+            nblk = (f_end - f0) + (sb_ - sa_ + 1);
+            load_seg(sa_);
+        }
+    };
+    uint32_t dsc[ST_R];
+#pragma unroll
+    for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
+    bool direct = fused;  // coarse pass: every distance goes to pool_d[center]
+    if (fused) set_range(1, 0);
+    else set_range(gridDim.x, blockIdx.x);
+    // the first ST_D blocks go out before the table is built
+    ST_ISSUE(0, dsc[0], 0 < nblk)
+    ST_ISSUE(1, dsc[1], 1 < nblk)
+    ST_ISSUE(2, dsc[2], 2 < nblk)
+
+    int bad = 0;
+    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (padding bytes index row 0 only)
+        if (a.T) {
+            const float *T = a.T + (size_t)b * 32 * a.Ks;
+#pragma unroll 8
+            for (int e = threadIdx.x; e < 256 * 64; e += NW * 32) {
+                int ks = e >> 6, c = e & 63;
+                const float v = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+                bad |= !(v <= ST_TABLE_LIMIT);
+                lut2[e] = v;
+            }
+        } else {
+            // K1 fused (src/rii.h:361-373): entry (m = lane, ks) -> both columns m and m + 32 of row ks; the
+            // lane's query sub-vector stays in registers, codewords come from the sub-space-fastest copy (one
+            // contiguous 32*Ds-float row per ks), stores are bank-conflict free.
+            const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
+            if (a.Ds <= 4) {
+                float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+#pragma unroll 8
+                for (int ks = wid; ks < 256; ks += NW) {
+                    float v = 0.f;
+                    if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds);
+                    bad |= !(v <= ST_TABLE_LIMIT);
+                    lut2[ks * 64 + lane] = v;
+                    lut2[ks * 64 + lane + 32] = v;
+                }
+            } else {
+#pragma unroll 1
+                for (int ks = wid; ks < 256; ks += NW) {
+                    float v = 0.f;
+                    if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds, a.variant);
+                    bad |= !(v <= ST_TABLE_LIMIT);
+                    lut2[ks * 64 + lane] = v;
+                    lut2[ks * 64 + lane + 32] = v;
+                }
+            }
+        }
+    }
+    const bool plain = __syncthreads_or(bad) != 0;  // (also: the table is visible)
+    if (dbg && threadIdx.x == 0 && !fused) dbg[1] = clock64();
+    if (dbg && threadIdx.x == 0) dbg[4] = clock64();  // table ready
+
+    uint32_t thr_hi = 0xffffffffu;
+    // id of the row `half` (0: x, 1: y) of flattened group f in this lane
+    auto row_id = [&](int f, int half) -> uint32_t {
+        if constexpr (IVF) {
+            const int j = seg_of(f);
+            const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + half * 32 + lane;
+            return (uint32_t)__ldg(a.ids + s_off[j] + r);
+        } else {
+            return (uint32_t)(f * 64 + half * 32 + lane);
+        }
+    };
+    auto emit2 = [&](float dx, float dy, uint32_t d) {
+        const int f = (int)(d >> 2);
+        if (IVF && direct) {  // coarse pass of the fused kernel: keep every distance
+            if (d & 1u) pool_d[f * 64 + lane] = __float_as_uint(dx);
+            if (d & 2u) pool_d[f * 64 + 32 + lane] = __float_as_uint(dy);
+            return;
+        }
+        // distance part of the CTA threshold: long linear scans keep a cached copy that is refreshed after every push
+        // and every few blocks (a stale value is merely less strict); the short per-query IVF passes re-read it at
+        // every emission
+        if constexpr (IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
+        const bool px = (d & 1u) && __float_as_uint(dx) <= thr_hi;
+        const bool py = (d & 2u) && __float_as_uint(dy) <= thr_hi;
+        if (__any_sync(0xffffffffu, px || py)) {
+            warp_push(wt, cta_thr, lane, dx, px ? row_id(f, 0) : 0u, px);
+            warp_push(wt, cta_thr, lane, dy, py ? row_id(f, 1) : 0u, py);
+            thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
+        }
+    };
+    // exact for ANY table (inf / NaN / huge entries): one candidate per lane and half group, natural order of
+    // additions; the lane un-skews its own stream (byte m of row b of stream s = stream byte 32 b + m)
+    auto plain_slice = [&]() {
+        for (int f = f0; f < f_end; ++f) {
+            const int j = seg_of(f);
+            const int g = f - (j ? s_gcum[j - 1] : 0);
+            float dd[2] = {0.f, 0.f};
+            uint32_t dsc_ = (uint32_t)f << 2;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int s = half * 32 + lane;
+                if (g * 64 + s < s_take[j]) {
+                    dsc_ |= 1u << half;
+                    const uint8_t *p = pc + ((size_t)s_prow[j] + (size_t)g * 64) * 32 + half * 1024 + lane * 16;
+                    float d = 0.f;
+                    for (int m = 0; m < 32; ++m) {
+                        const int x = lane + m;  // byte of the 64-byte span [window b | window b + 1] of stream s
+                        const uint32_t ks = __ldg(p + (x >> 5) * ST_BLOCK_BYTES + ((x >> 4) & 1) * 512 + (x & 15));
+                        d = m ? __fadd_rn(d, lut2[ks * 64 + m]) : lut2[ks * 64];
+                    }
+                    dd[half] = d;
+                }
+            }
+            emit2(dd[0], dd[1], dsc_);
+        }
+    };
+
+    const int npass = fused ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        if (pass == 1) {
+            // ---- between the passes: select + rank the w_eff nearest centers, plan (all in shared memory) ----------
+            if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // coarse pass done (the pass loop ended with a barrier)
+            u64 *selk = reinterpret_cast<u64 *>(smem_raw + hi0);          // (rings idle) 8 KB: <= 256 selected keys, or the full sort (nlist <= 1024)
+            int *hist = reinterpret_cast<int *>(smem_raw + hi0 + 8192);   // 260 ints
+            int np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist);
+            if (wid == 0) {
+                if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
+                    const int P = next_pow2(a.nlist);
+                    for (int i = lane; i < P; i += 32) selk[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
+                    warp_sort_smem(selk, P, lane);
+                    np = a.nlist;
+                }
+                if (dbg && lane == 0) { dbg[6] = clock64(); dbg[7] = np; }
+                int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
+                for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist, np >= w_eff
+                    const int no = (int)key_id(selk[j]);
+                    ranked_g[j] = no;
+                    s_f[j] = a.plan.glob_len[no];
+                    s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
+                    s_loc[j] = a.plan.loc_len[no];
+                    s_off[j] = a.offsets[no];
+                    s_prow[j] = a.skew_off[no];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    make_plan(a.plan, b, s_f, s_pre, s_loc, s_cum);
+                    s_plan[0] = compact_segments(a.plan.flags[b] != 0 ? 0 : a.plan.J[b]);
+                    *cta_thr = RII_KEY_MAX;  // (thr_w is still all-MAX: the coarse pass does not use the warp lists)
+                }
+            }
+            __syncthreads();
+            if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+            J = s_plan[0];
+            pc = a.codes;
+            direct = false;
+            wt.count = 0;
+            thr_hi = 0xffffffffu;
+            set_range(1, 0);
+#pragma unroll
+            for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
+            ST_ISSUE(0, dsc[0], 0 < nblk)
+            ST_ISSUE(1, dsc[1], 1 < nblk)
+            ST_ISSUE(2, dsc[2], 2 < nblk)
+        }
+
+        if (plain) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            plain_slice();
+        } else {
+            unsigned long long acc2 = 0ull, out2 = 0ull;
+#pragma unroll 1
+            for (int m = 0; m < nblk; m += ST_R) {
+                if constexpr (!IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
+                ST_STAGE(0)
+                ST_STAGE(1)
+                ST_STAGE(2)
+                ST_STAGE(3)
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // (only empty groups can be pending; the ring area is reused below)
+        if (!(IVF && direct)) warp_compact(wt, cta_thr, lane);
+        __syncthreads();
+    }
+    if (dbg && threadIdx.x == 0) dbg[2] = clock64();
+    {   // CTA merge of the (sorted) warp lists, reusing the lut2 area for the keys
+        __shared__ int s_cnt[NW];
+        if (lane == 0) s_cnt[wid] = wt.count;
+        __syncthreads();
+        int tot = 0;
+        for (int w2 = 0; w2 < NW; ++w2) tot += s_cnt[w2];
+        const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw);
+        if (tot <= 256) {
+            // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
+            if (wid == 0) {
+                u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
+                int o = 0;
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    for (int i = lane; i < s_cnt[w2]; i += 32) mk[o + i] = allkeys[(size_t)w2 * capw + i];
+                    o += s_cnt[w2];
+                }
+                warp_sort_any(mk, tot, lane);
+                const int n = tot < a.k ? tot : a.k;
+                if (a.out.final) {
+                    for (int i = lane; i < n; i += 32) {
+                        a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(mk[i]);
+                        a.out.out_dists[(size_t)b * a.k + i] = key_dist(mk[i]);
+                    }
+                    if (lane == 0) a.out.out_counts[b] = n;
+                } else {
+                    u64 *dst = a.out.partial + ((size_t)b * gridDim.x + blockIdx.x) * a.k;
+                    for (int i = lane; i < a.k; i += 32) dst[i] = i < n ? mk[i] : RII_KEY_MAX;
+                }
+            }
+        } else {
+            BlockTopk tk;
+            const int mcap = next_pow2(NW * a.k + 1);
+            tk.keys = reinterpret_cast<u64 *>(smem_raw + lut_off);
+            tk.count = reinterpret_cast<int *>(smem_raw + lut_off + (size_t)mcap * 8 + 8);
+            tk.thr = reinterpret_cast<u64 *>(smem_raw + lut_off + (size_t)mcap * 8);
+            tk.cap = mcap;
+            tk.k = a.k;
+            tk.init();
+            for (int w2 = 0; w2 < NW; ++w2)
+                for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
+            emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
+        }
+    }
+    if (dbg && threadIdx.x == 0) dbg[3] = clock64();
+}
+
+// does the launch fit?  (keys + thresholds + segment tables below the table pinned at absolute shared address 0x10000)
+static inline bool stream_fits(bool ivf, int nw, int capw, int w_eff)
+{
+    const size_t meta = (size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16;
+    return meta <= (size_t)(0x10000 - 1280) && (size_t)(0x10000 - 1024) + SK_LUT_BYTES + (size_t)nw * ST_RING_BYTES <= (size_t)SK_DYN_SMEM;
+}

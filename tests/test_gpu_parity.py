@@ -315,14 +315,25 @@ def _assign_of(offsets, ids, N):
 
 
 # ---------------------------------------------------------------- scan kernel v2 (skewed) --------------
-@pytest.mark.parametrize("N", [1, 255, 2049, 20000, 70001])
-def test_skew_kernel_matches_oracle(N):
-    """The bank-conflict-free schedule (k_scan_linear_skew32) must return exactly what the natural-layout
-    kernel and the oracle return: every tail / tile-boundary case."""
+# v2: k_scan_skew32 (one stream per lane, predicated adds); v3: k_scan_dual32 (two streams, FFMA2, 3-stage cp.async ring);
+# v4: k_scan_stream32 (two streams, FFMA2, pre-skewed skew64 layout through private cp.async rings; 12 or 8 warps)
+SKEW_KERNELS = [2, 3, 4, 408]
+
+
+def set_kernel(e, sk):
+    e.set_option("scan_kernel", 4 if sk > 100 else sk)
+    e.set_option("stream_warps", 8 if sk == 408 else 12)
+
+
+@pytest.mark.parametrize("sk", SKEW_KERNELS)
+@pytest.mark.parametrize("N", [1, 255, 2049, 20000, 70001, 300001])
+def test_skew_kernel_matches_oracle(N, sk):
+    """The bank-conflict-free schedules (k_scan_skew32, k_scan_dual32) must return exactly what the natural-layout
+    kernel and the oracle return: every tail / tile-boundary / ring-wrap case."""
     D, M, Ks = 128, 32, 256
     cw, codes, Q = synth(D, M, Ks, N, 3, seed=N)
     e = engine(cw, codes)
-    e.set_option("scan_kernel", 2)
+    set_kernel(e, sk)
     for q in Q:
         T = O.dtable(q, cw, 16)
         for topk in (1, 10, 224):
@@ -339,13 +350,14 @@ def test_skew_kernel_matches_oracle(N):
         e.query_linear(Q[0], 1, np.arange(1, dtype=np.int64))  # v2 has no target_ids path when forced
 
 
-def test_skew_kernel_small_ks_and_ties():
+@pytest.mark.parametrize("sk", SKEW_KERNELS)
+def test_skew_kernel_small_ks_and_ties(sk):
     """Ks < 256 (table rows beyond Ks are never indexed by real codes) and massive exact ties."""
     cw, codes, Q = synth(128, 32, 16, 50000, 2, seed=3)
     codes[:, 8:] = 0  # only 16^8 distinct codes -> many exact distance ties; (dist, id) order decides
     e1, e2 = engine(cw, codes), engine(cw, codes)
     e1.set_option("scan_kernel", 1)
-    e2.set_option("scan_kernel", 2)
+    set_kernel(e2, sk)
     for q in Q:
         T = O.dtable(q, cw, 16)
         for topk in (1, 50, 200):
@@ -361,17 +373,22 @@ def test_skew_kernel_large_n_vs_v1():
     for q in Q:
         e.set_option("scan_kernel", 1)
         r1 = e.query_linear(q, 100, EMPTY)
-        e.set_option("scan_kernel", 0)  # auto -> v2 at this size
+        e.set_option("scan_kernel", 0)  # auto -> v4 at this size
         r0 = e.query_linear(q, 100, EMPTY)
+        e.set_option("scan_kernel", 3)
+        r3 = e.query_linear(q, 100, EMPTY)
+        e.set_option("scan_kernel", 4)
+        r4 = e.query_linear(q, 100, EMPTY)
         e.set_option("scan_kernel", 2)
         r2 = e.query_linear(q, 100, EMPTY)
-        assert r1 == r2 == r0
+        assert r1 == r2 == r0 == r3 == r4
     T = O.dtable(Q[0], cw, 16)
     assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(O.dtable(Q[2], cw, 16), codes, 100), "5M")
 
 
-def test_ivf_skew_kernel_vs_v1_and_oracle():
-    """k_scan_ivf_skew32 (auto-selected for M = 32, no target_ids, topk <= 96) against the natural-layout
+@pytest.mark.parametrize("sk", SKEW_KERNELS)
+def test_ivf_skew_kernel_vs_v1_and_oracle(sk):
+    """The skewed posting-list scans (auto-selected for M = 32, no target_ids, topk <= 224) against the natural-layout
     kernel and the oracle: single-candidate plans, mid-list cuts, several CTAs per query, batches."""
     D, M, Ks, N, nlist = 128, 32, 256, 60000, 50
     cw, codes, Q = synth(D, M, Ks, N, 5, seed=31)
@@ -384,13 +401,13 @@ def test_ivf_skew_kernel_vs_v1_and_oracle():
         T = O.dtable(q, cw, 16)
         for topk, L in cases:
             exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
-            e.set_option("scan_kernel", 2)
+            set_kernel(e, sk)
             r2 = e.query_ivf(q, topk, EMPTY, L)
             e.set_option("scan_kernel", 1)
             r1 = e.query_ivf(q, topk, EMPTY, L)
             assert r1 == r2, (topk, L)
             assert_same_result(r2[0], np.array(r2[1], np.float32), exp[0], exp[1], "ivf skew k=%d L=%d" % (topk, L))
-    e.set_option("scan_kernel", 0)
+    set_kernel(e, sk)
     Qb = np.ascontiguousarray(np.tile(Q, (60, 1)))  # 300 queries -> one CTA per query
     bi, bd, bc = e.query_batch(Qb, 4, L=3000, method="ivf")
     for b in range(0, 300, 37):
@@ -424,13 +441,15 @@ def test_gpu_pq_encoder():
     assert np.array_equal(e2.codes, got)
 
 
-def test_fused_coarse_plan_scan_equals_unfused():
+@pytest.mark.parametrize("sk", SKEW_KERNELS)
+def test_fused_coarse_plan_scan_equals_unfused(sk):
     """One-CTA-per-query batches run coarse ranking + plan + posting-list scan in ONE kernel (two passes of the
-    skewed engine); results must equal the unfused pipeline (k_coarse_rank + k_scan_skew32) and the oracle,
+    skewed engine); results must equal the unfused pipeline (k_coarse_rank + scan) and the oracle,
     including plans that end mid-list, at the w-th list, and the empty result."""
     D, M, Ks, N, nlist = 128, 32, 256, 80000, 200
     cw, codes, Q = synth(D, M, Ks, N, 160, seed=77)
     e = engine(cw, codes)
+    set_kernel(e, sk)
     e.reconfigure(nlist, 1)
     centers = e.coarse_centers_array()
     offsets, ids = e.posting_lists_csr()
@@ -446,3 +465,69 @@ def test_fused_coarse_plan_scan_equals_unfused():
             n = int(f[2][b])
             assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "fused k=%d L=%d b=%d" % (topk, L, b))
     e.set_option("fuse_coarse", 1)
+
+
+@pytest.mark.parametrize("sk", [3, 4])
+def test_dual_kernel_huge_tables_take_the_plain_path(sk):
+    """k_scan_dual32 / k_scan_stream32 accumulate with acc * {0,1} + v, which needs finite partial sums; a distance table with huge /
+    inf entries (queries ~1e19 away from the codewords) must be detected in-kernel and scanned by the plain
+    per-candidate loop -- same results as the natural-layout kernel and the oracle, bit for bit."""
+    D, M, Ks, N, nlist = 128, 32, 256, 40000, 40
+    cw, codes, Q = synth(D, M, Ks, N, 4, seed=9)
+    Q = Q.copy()
+    Q[0, 5] = 4e18      # entries ~1.6e37 > 1e37: plain path, finite sums
+    Q[1, 17] = 3e19     # (3e19)^2 overflows: inf entries in one sub-space -> every distance inf, ids decide
+    Q[2, :] = 2.5e18    # every sub-space huge: sums reach 1e38, some overflow to inf
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 20):
+            e.set_option("scan_kernel", sk)
+            r3 = e.query_linear(q, topk, EMPTY)
+            e.set_option("scan_kernel", 1)
+            r1 = e.query_linear(q, topk, EMPTY)
+            assert r1[0] == r3[0] and bits(np.array(r1[1], np.float32)).tolist() == bits(np.array(r3[1], np.float32)).tolist()
+            assert_same_result(r3[0], np.array(r3[1], np.float32), *O.query_linear(T, codes, topk), "huge linear")
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, 3000)
+            e.set_option("scan_kernel", sk)
+            g = e.query_ivf(q, topk, EMPTY, 3000)
+            assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "huge ivf")
+    e.set_option("scan_kernel", sk)
+    bi, bd, bc = e.query_batch(np.ascontiguousarray(np.tile(Q, (40, 1))), 3, L=2000, method="ivf")  # fused, one CTA per query
+    for b in range(4):
+        exp = O.query_ivf(O.dtable(Q[b], cw, 16), codes, centers, offsets, ids, 3, 2000)
+        assert_same_result(bi[b], bd[b], exp[0], exp[1], "huge fused %d" % b)
+
+
+def test_stream_kernel_tracks_index_updates():
+    """The skew64 copies are derived state: add() after a query, add with posting-list update, reconfigure and clear
+    must all be reflected by the next query (rebuilt lazily)."""
+    D, M, Ks = 128, 32, 256
+    cw, codes, Q = synth(D, M, Ks, 9000, 3, seed=12)
+    e = engine(cw, codes[:3000])
+    e.set_option("scan_kernel", 4)
+    q = Q[0]
+    T = O.dtable(q, cw, 16)
+    r = e.query_linear(q, 5, EMPTY)
+    assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(T, codes[:3000], 5), "before add")
+    e.add_codes(codes[3000:5001], False)
+    r = e.query_linear(q, 5, EMPTY)
+    assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(T, codes[:5001], 5), "after add")
+    e.reconfigure(30, 2)
+    e.add_codes(codes[5001:], True)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    for topk, L in [(1, 100), (5, 999), (9, 9000)]:
+        exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
+        g = e.query_ivf(q, topk, EMPTY, L)
+        assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "ivf after add+update k=%d L=%d" % (topk, L))
+    e.reconfigure(7, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    bi, bd, bc = e.query_batch(np.ascontiguousarray(np.tile(Q, (50, 1))), 2, L=500, method="ivf")  # fused
+    for b in range(3):
+        exp = O.query_ivf(O.dtable(Q[b], cw, 16), codes, centers, offsets, ids, 2, 500)
+        assert_same_result(bi[b], bd[b], exp[0], exp[1], "after second reconfigure %d" % b)
