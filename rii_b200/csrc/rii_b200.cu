@@ -132,7 +132,7 @@ struct rii_index {
 
     DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
     int opt_debug_clocks = 0;
-    int opt_stream_warps = 12; // warps per CTA of the v4 engine (8 or 12)
+    int opt_stream_ctas = 0;  // v4 engine: 1 = always one CTA per SM; otherwise per-query IVF batches run two CTAs per SM
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
                               // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
@@ -441,25 +441,41 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
     return 0;
 }
 
-// ---- v4 (register-streaming over skew64) scan launcher --------------------------------------------------
-int stream_pick_nw(const rii_index *h, bool ivf, int capw, int w_eff)
+// ---- v4 (skew64 streaming) scan launcher ------------------------------------------------------------------
+// shapes: 1 = one CTA per SM (12 warps, 4-stage rings, table at 0x10000); 2 = two CTAs per SM (6 warps, 3-stage rings,
+// table at 0x2000); returns the shape that fits (0: none) and its warps / dynamic shared memory
+int stream_pick(const rii_index *h, bool ivf, bool per_query_batch, int capw, int w_eff, size_t pool_bytes, int *nw, size_t *smem)
 {
-    const int nw = h->opt_stream_warps == 8 ? 8 : 12;
-    return stream_fits(ivf, nw, capw, w_eff) ? nw : (stream_fits(ivf, 8, capw, w_eff) ? 8 : 0);
-}
-
-template <int NW, bool IVF> int launch_stream_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
-{
-    CKR(set_smem(k_scan_stream32<NW, IVF>, smem));
-    k_scan_stream32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
+    const bool want2 = ivf && per_query_batch && h->opt_stream_ctas != 1;
+    if (want2) {
+        const size_t b = stream_smem_bytes(true, 6, 3, ST_TB2, capw, w_eff, pool_bytes);
+        if (b && b <= 113 * 1024) { *nw = 6; *smem = b; return 2; }
+    }
+    const size_t b = stream_smem_bytes(ivf, 12, 4, ST_TB1, capw, w_eff, pool_bytes);
+    if (b && b <= SK_DYN_SMEM) { *nw = 12; *smem = b; return 1; }
     return 0;
 }
 
-int launch_stream(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
+template <int NW, bool IVF, int R, int MINB, uint32_t TB>
+int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
 {
-    const size_t smem = SK_DYN_SMEM;
-    if (ivf) return nw == 12 ? launch_stream_t<12, true>(a, parts, B, smem, st) : launch_stream_t<8, true>(a, parts, B, smem, st);
-    return nw == 12 ? launch_stream_t<12, false>(a, parts, B, smem, st) : launch_stream_t<8, false>(a, parts, B, smem, st);
+    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB>;
+    static bool configured = false;  // per process and instantiation
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_DYN_SMEM));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    a.smem_bytes = (uint32_t)smem;
+    kern<<<dim3(parts, B), NW * 32, smem, st>>>(a);
+    return 0;
+}
+
+int launch_stream(int shape, bool ivf, const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
+{
+    if (shape == 2) return launch_stream_t<6, true, 3, 2, ST_TB2>(a, parts, B, smem, st);
+    if (ivf) return launch_stream_t<12, true, 4, 1, ST_TB1>(a, parts, B, smem, st);
+    return launch_stream_t<12, false, 4, 1, ST_TB1>(a, parts, B, smem, st);
 }
 
 // ---- v2 (skewed) scan launcher: the most warps per SM whose shared-memory footprint fits ---------------
@@ -573,7 +589,10 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
         const int capw = std::max(64, next_pow2(c.topk + 32));
         const int eng = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;  // v4 unless v2 / v3 is asked for
-        const int nw = eng == 4 ? stream_pick_nw(h, false, capw, 0) : eng == 3 ? dual_pick_nw(false, capw, 0) : skew_pick_nw(false, capw, 0);
+        int nw = 0, shape = 0;
+        size_t smem4 = 0;
+        if (eng == 4) shape = stream_pick(h, false, false, capw, 0, 0, &nw, &smem4);
+        else nw = eng == 3 ? dual_pick_nw(false, capw, 0) : skew_pick_nw(false, capw, 0);
         const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
         const bool use_v2 = v2_ok && (h->opt_scan_kernel >= 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
         if (h->opt_scan_kernel >= 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 needs M == 32, no target_ids and topk <= 224");
@@ -595,7 +614,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 sa.codes = h->skew_lin.as<uint8_t>();
             }
             Prof pr(h, st, PK_SCAN_LINEAR);
-            CKR(eng == 4 ? launch_stream(nw, false, sa, parts, B, st)
+            CKR(eng == 4 ? launch_stream(shape, false, sa, parts, B, smem4, st)
                          : eng == 3 ? launch_dual(nw, false, sa, parts, B, st) : launch_skew(nw, false, sa, parts, B, st));
         } else {
             CKR(ensure_T());
@@ -655,7 +674,12 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // same kernel (two passes of one engine): no k_coarse_rank launch at all.
     const int capw2 = std::max(64, next_pow2(c.topk + 32));
     const int eng2 = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;
-    const int nw2 = eng2 == 4 ? stream_pick_nw(h, true, capw2, w_eff) : eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
+    int nw2 = 0, shape2 = 0;
+    size_t smem42 = 0;
+    // (the fused coarse pass keeps nlist distances in shared memory: sized for it whenever fusing is possible)
+    const size_t pool4 = h->opt_fuse_coarse && h->nlist <= 1024 ? (size_t)h->nlist * 4 : 0;
+    if (eng2 == 4) shape2 = stream_pick(h, true, B >= 148, capw2, w_eff, pool4, &nw2, &smem42);
+    else nw2 = eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
     const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
     if (h->opt_scan_kernel >= 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 (ivf) needs M == 32, topk <= 224 and a short list plan");
@@ -664,7 +688,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
     const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && h->nlist <= 1024 &&
-                      (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8;
+                      (eng2 == 4 || (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8);
     if (use_v2) {
         if (eng2 == 4) {
             CKR(ensure_skew_lists(h, st));
@@ -749,7 +773,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         Prof pr(h, st, PK_SCAN_IVF);
         if (use_v2) {
             sa.smem_bytes = SK_DYN_SMEM;
-            CKR(eng2 == 4 ? launch_stream(nw2, true, sa, parts, B, st)
+            CKR(eng2 == 4 ? launch_stream(shape2, true, sa, parts, B, smem42, st)
                           : eng2 == 3 ? launch_dual(nw2, true, sa, parts, B, st) : launch_skew(nw2, true, sa, parts, B, st));
         } else if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
@@ -1039,9 +1063,9 @@ int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk,
 int rii_set_option(rii_index_t *h, const char *name, int64_t value)
 {
     if (!h || !name) return fail(RII_ERR_ARG, "bad arguments");
-    if (!strcmp(name, "stream_warps")) {
-        if (value != 8 && value != 12) return fail(RII_ERR_ARG, "stream_warps must be 8 or 12");
-        h->opt_stream_warps = (int)value;
+    if (!strcmp(name, "stream_ctas")) {
+        if (value < 0 || value > 2) return fail(RII_ERR_ARG, "stream_ctas must be 0 (auto), 1 or 2");
+        h->opt_stream_ctas = (int)value;
         return 0;
     }
     if (!strcmp(name, "scan_kernel")) {

@@ -27,10 +27,14 @@
 // ===================================================================================================
 #pragma once
 
-#define ST_D 3                      // blocks in flight ahead of the one being scanned
-#define ST_R (ST_D + 1)             // ring stages per warp
 #define ST_BLOCK_BYTES 2048         // 64 windows of 32 bytes
-#define ST_RING_BYTES (ST_R * ST_BLOCK_BYTES)
+// Launch shapes (template parameters NW warps, R ring stages = R - 1 blocks in flight, MINB CTAs per SM, TB = absolute
+// shared address of the table):
+//   one CTA per SM:  NW = 12, R = 4, TB = 0x10000 -- long scans (linear), large topk / many lists
+//   two CTAs per SM: NW = 6,  R = 3, TB = 0x3000  -- per-query IVF batches: the serial phases of one query (table build,
+//                    coarse selection, plan, final merge) overlap the scan of the other CTA's query
+#define ST_TB1 0x10000u
+#define ST_TB2 0x3000u
 #define ST_TABLE_LIMIT 1e37f        // 32 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
 
 // physical rows of a skew64 segment holding `len` code rows
@@ -100,11 +104,25 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
         }                                                                                                     \
         asm volatile("cp.async.commit_group;");                                                               \
     }
+// one lookup step of both streams: PRMT builds ks << 8 | column byte offset, the load's immediate adds the table's
+// (compile-time) absolute shared address and the step; acc / out updates as in DU_STEP (scan_dual.cuh)
+#define ST_STEP(WX, WY, BYTE, T)                                                                              \
+    {                                                                                                         \
+        const uint32_t ax_ = __byte_perm(WX, colreg, 0x7604 | ((BYTE) << 4));                                 \
+        const uint32_t ay_ = __byte_perm(WY, colreg, 0x7604 | ((BYTE) << 4));                                 \
+        float vx_, vy_;                                                                                       \
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vx_) : "r"(ax_), "n"(TB + 4 * (T)));                \
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vy_) : "r"(ay_), "n"(TB + 4 * (T)));                \
+        asm("{.reg .b64 v, kk, ss; mov.b64 v, {%4, %5}; mov.b64 kk, {%2, %2}; mov.b64 ss, {%3, %3};"         \
+            " fma.rn.f32x2 %1, %0, ss, %1; fma.rn.f32x2 %0, %0, kk, v;}"                                     \
+            : "+l"(acc2), "+l"(out2)                                                                          \
+            : "f"(keep[T]), "f"(sel[T]), "f"(vx_), "f"(vy_));                                                 \
+    }
 #define ST_WORD(BX, BY, Q)                                                                                    \
-    DU_STEP(BX[Q], BY[Q], 0, 4 * (Q) + 0)                                                                     \
-    DU_STEP(BX[Q], BY[Q], 1, 4 * (Q) + 1)                                                                     \
-    DU_STEP(BX[Q], BY[Q], 2, 4 * (Q) + 2)                                                                     \
-    DU_STEP(BX[Q], BY[Q], 3, 4 * (Q) + 3)
+    ST_STEP(BX[Q], BY[Q], 0, 4 * (Q) + 0)                                                                     \
+    ST_STEP(BX[Q], BY[Q], 1, 4 * (Q) + 1)                                                                     \
+    ST_STEP(BX[Q], BY[Q], 2, 4 * (Q) + 2)                                                                     \
+    ST_STEP(BX[Q], BY[Q], 3, 4 * (Q) + 3)
 #define ST_BLOCK(BX, BY)                                                                                      \
     {                                                                                                         \
         ST_WORD(BX, BY, 0) ST_WORD(BX, BY, 1) ST_WORD(BX, BY, 2) ST_WORD(BX, BY, 3)                           \
@@ -115,7 +133,8 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
     if (m + (S) < nblk) {                                                                                     \
         const uint32_t dprev_ = dsc[((S) + ST_D) % ST_R];                                                     \
         ST_ISSUE(((S) + ST_D) % ST_R, dsc[((S) + ST_D) % ST_R], m + (S) + ST_D < nblk)                        \
-        asm volatile("cp.async.wait_group 3;" ::: "memory");                                                  \
+        if constexpr (ST_D == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");                         \
+        else asm volatile("cp.async.wait_group 2;" ::: "memory");                                             \
         uint32_t wx_[8], wy_[8];                                                                              \
         ST_LDS128(wx_, ring + (S) * ST_BLOCK_BYTES);                                                          \
         ST_LDS128(wx_ + 4, ring + (S) * ST_BLOCK_BYTES + 512);                                                \
@@ -130,15 +149,18 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
 
 // Args: SkewArgs (kernels.cuh) with `codes` = skew64 table of the pass-1 rows (linear: the codes by id, one segment;
 // IVF: every local posting list, segment i at physical row skew_off[i]) and `centers` = skew64 of the coarse centers.
-template <int NW, bool IVF>
-__global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
+template <int NW, bool IVF, int ST_R, int MINB, uint32_t TB>
+__global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 {
+    constexpr int ST_D = ST_R - 1;                           // blocks in flight ahead of the one being scanned
+    constexpr uint32_t ST_RING_BYTES = ST_R * ST_BLOCK_BYTES;  // per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout (dynamic shared memory; the window starts at absolute shared address ~1 KB):
     //   [NW key buffers][cta_thr][thr_w][segments: s_off, s_prow i64[wq] | s_gcum, s_take, s_cum, s_f, s_pre, s_loc i32[wq] | s_plan]
-    //   ... lut2 (64 KB) at ABSOLUTE shared address 0x10000 ... [NW rings of 8 KB; between the passes: selection scratch]
+    //   [fused IVF: nlist coarse distances]
+    //   ... lut2 (64 KB) at ABSOLUTE shared address TB ... [NW rings of ST_R x 2 KB; between the passes: selection scratch]
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t lut_off = 0x10000u - smem_base;
+    const uint32_t lut_off = TB - smem_base;
     float *lut2 = reinterpret_cast<float *>(smem_raw + lut_off);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int capw = a.cap;
@@ -153,9 +175,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
     int *s_gcum = reinterpret_cast<int *>(s_prow + wq);
     int *s_take = s_gcum + wq, *s_cum = s_take + wq, *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;
     const uint32_t hi0 = lut_off + SK_LUT_BYTES;                      // scratch above the table
-    // the warps' key buffers are idle during the coarse pass: they hold the nlist distances (host checks the size)
-    uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw);
-    if ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
+    // coarse distances of the fused coarse pass: nlist words after the segment tables
+    const size_t meta_end = ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 + 15) & ~(size_t)15;
+    uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + meta_end);
+    if (meta_end + (IVF && a.centers ? (size_t)a.nlist * 4 : 0) > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
         __trap();  // host sized the launch wrongly
     const uint32_t ring = smem_base + hi0 + wid * ST_RING_BYTES + lane * 16;  // this lane's chunk column of the warp's ring
     const int b = blockIdx.y;
@@ -209,13 +232,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
     __syncthreads();
     J = s_plan[0];
 
-    const uint32_t colreg = 0x00010000u | (uint32_t)((32 - lane) * 4);  // table address 0x10000 | column byte offset
-    float keep[32], sel[32];
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-        keep[t] = lane == t ? 0.f : 1.f;
-        sel[t] = lane == t ? 1.f : 0.f;
-    }
+    const uint32_t colreg = (uint32_t)((32 - lane) * 4);  // column byte offset of the lane (the table base is in the load's immediate)
 
     // per-pass state (warp-uniform)
     const uint8_t *pc = fused ? a.centers : a.codes;  // skew64 table of the pass
@@ -272,7 +289,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
     // the first ST_D blocks go out before the table is built
     ST_ISSUE(0, dsc[0], 0 < nblk)
     ST_ISSUE(1, dsc[1], 1 < nblk)
-    ST_ISSUE(2, dsc[2], 2 < nblk)
+    if constexpr (ST_D == 3) ST_ISSUE(2 % ST_R, dsc[2 % ST_R], 2 < nblk)
 
     int bad = 0;
     {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (padding bytes index row 0 only)
@@ -290,11 +307,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
             // lane's query sub-vector stays in registers, codewords come from the sub-space-fastest copy (one
             // contiguous 32*Ds-float row per ks), stores are bank-conflict free.
             const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
-            if (a.Ds <= 4) {
+            // every CTA of the grid reads the same 32*Ks*Ds floats at about the same time: each starts at a different
+            // codeword row, which spreads the requests over the L2 slices
+            const int rot = (int)((blockIdx.y * gridDim.x + blockIdx.x) * 53u) & 255;
+            if (a.Ds == 4 && a.Ks == 256) {  // the common shape: 16 independent 16-byte loads in flight per lane
+                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
+                const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + lane;
+#pragma unroll 16
+                for (int i = wid; i < 256; i += NW) {
+                    const int ks = (i + rot) & 255;
+                    const float4 c4 = __ldg(cw4 + ks * 32);
+                    const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                    bad |= !(v <= ST_TABLE_LIMIT);
+                    lut2[ks * 64 + lane] = v;
+                    lut2[ks * 64 + lane + 32] = v;
+                }
+            } else if (a.Ds <= 4) {
                 float qv[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
 #pragma unroll 8
-                for (int ks = wid; ks < 256; ks += NW) {
+                for (int i = wid; i < 256; i += NW) {
+                    const int ks = (i + rot) & 255;
                     float v = 0.f;
                     if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds);
                     bad |= !(v <= ST_TABLE_LIMIT);
@@ -317,6 +350,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
     if (dbg && threadIdx.x == 0 && !fused) dbg[1] = clock64();
     if (dbg && threadIdx.x == 0) dbg[4] = clock64();  // table ready
 
+    float keep[32], sel[32];  // the per-lane row-boundary constants of the accumulation (scan_dual.cuh)
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        keep[t] = lane == t ? 0.f : 1.f;
+        sel[t] = lane == t ? 1.f : 0.f;
+    }
     uint32_t thr_hi = 0xffffffffu;
     // id of the row `half` (0: x, 1: y) of flattened group f in this lane
     auto row_id = [&](int f, int half) -> uint32_t {
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
             for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
             ST_ISSUE(0, dsc[0], 0 < nblk)
             ST_ISSUE(1, dsc[1], 1 < nblk)
-            ST_ISSUE(2, dsc[2], 2 < nblk)
+            if constexpr (ST_D == 3) ST_ISSUE(2 % ST_R, dsc[2 % ST_R], 2 < nblk)
         }
 
         if (plain) {
@@ -434,7 +473,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
                 ST_STAGE(0)
                 ST_STAGE(1)
                 ST_STAGE(2)
-                ST_STAGE(3)
+                if constexpr (ST_R == 4) { ST_STAGE(3 % ST_R) }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // (only empty groups can be pending; the ring area is reused below)
@@ -488,9 +527,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_scan_stream32(SkewArgs a)
     if (dbg && threadIdx.x == 0) dbg[3] = clock64();
 }
 
-// does the launch fit?  (keys + thresholds + segment tables below the table pinned at absolute shared address 0x10000)
-static inline bool stream_fits(bool ivf, int nw, int capw, int w_eff)
+// dynamic shared memory of a launch shape, or 0 if keys + thresholds + segment tables do not fit below the table
+static inline size_t stream_smem_bytes(bool ivf, int nw, int ring_stages, uint32_t tb, int capw, int w_eff, size_t pool_bytes)
 {
-    const size_t meta = (size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16;
-    return meta <= (size_t)(0x10000 - 1280) && (size_t)(0x10000 - 1024) + SK_LUT_BYTES + (size_t)nw * ST_RING_BYTES <= (size_t)SK_DYN_SMEM;
+    const size_t meta = (((size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16 + 15) & ~(size_t)15) + pool_bytes;
+    if (meta > (size_t)tb - 1280) return 0;  // the window starts at 1 KB + static shared memory (<= 256 B allowed for)
+    return (size_t)tb - 1024 + SK_LUT_BYTES + (size_t)nw * ring_stages * ST_BLOCK_BYTES;
 }

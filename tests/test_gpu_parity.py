@@ -316,13 +316,14 @@ def _assign_of(offsets, ids, N):
 
 # ---------------------------------------------------------------- scan kernel v2 (skewed) --------------
 # v2: k_scan_skew32 (one stream per lane, predicated adds); v3: k_scan_dual32 (two streams, FFMA2, 3-stage cp.async ring);
-# v4: k_scan_stream32 (two streams, FFMA2, pre-skewed skew64 layout through private cp.async rings; 12 or 8 warps)
-SKEW_KERNELS = [2, 3, 4, 408]
+# v4: k_scan_stream32 (two streams, FFMA2, pre-skewed skew64 layout through private cp.async rings); 401 = always one
+# CTA per SM (12 warps) instead of two CTAs of 6 warps for per-query IVF batches
+SKEW_KERNELS = [2, 3, 4, 401]
 
 
 def set_kernel(e, sk):
     e.set_option("scan_kernel", 4 if sk > 100 else sk)
-    e.set_option("stream_warps", 8 if sk == 408 else 12)
+    e.set_option("stream_ctas", 1 if sk == 401 else 0)
 
 
 @pytest.mark.parametrize("sk", SKEW_KERNELS)

@@ -28,7 +28,7 @@ def main_():
     ap.add_argument("--what", default="linear,assign")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--scan-kernel", type=int, default=0)
-    ap.add_argument("--stream-warps", type=int, default=12)
+    ap.add_argument("--stream-ctas", type=int, default=0)
     a = ap.parse_args()
     lib = _capi.lib()
     dev = torch.device("cuda", 0)
@@ -49,7 +49,7 @@ def main_():
     sp = C.c_void_p(st.cuda_stream)
     lib.rii_profile_enable(e._h, 1)
     e.set_option("scan_kernel", a.scan_kernel)
-    e.set_option("stream_warps", a.stream_warps)
+    e.set_option("stream_ctas", a.stream_ctas)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if "linear" in a.what:
         for B, k in [(1, 1), (1, 10), (1, 100), (4, 10), (16, 10)]:
@@ -77,7 +77,7 @@ def main_():
             ms, n = prof(lib, e, "scan_linear")
             per = ms / n
             gbs = B * N * M / (per * 1e-3) / 1e9
-            print(json.dumps({"what": "linear", "scan_kernel": a.scan_kernel, "stream_warps": a.stream_warps, "N": N, "M": M, "B": B, "topk": k, "scan_ms": round(per, 4),
+            print(json.dumps({"what": "linear", "scan_kernel": a.scan_kernel, "stream_ctas": a.stream_ctas, "N": N, "M": M, "B": B, "topk": k, "scan_ms": round(per, 4),
                               "query_ms": round(t_tot / a.reps, 4), "code_GBps": round(gbs, 1),
                               "frac_hbm_per_query_bytes": round(N * M / (per / B * 1e-3) / 1e9 / peak, 4),
                               "lookups_per_s_T": round(B * N * M / (per * 1e-3) / 1e12, 3)}))
@@ -90,7 +90,7 @@ def main_():
         lib.rii_profile_enable(e3._h, 1)
         e3.set_option("debug_clocks", 1)
         e3.set_option("scan_kernel", a.scan_kernel)
-        e3.set_option("stream_warps", a.stream_warps)
+        e3.set_option("stream_ctas", a.stream_ctas)
         Q = torch.rand((B, D), device=dev)
         oi = torch.empty((B, 1), dtype=torch.int64, device=dev)
         od = torch.empty((B, 1), dtype=torch.float32, device=dev)
@@ -107,7 +107,7 @@ def main_():
             torch.cuda.synchronize()
             clk = np.zeros((B, 8), np.int64)
             _capi.check(lib.rii_debug_clocks(e3._h, B, clk.ctypes.data_as(C.POINTER(C.c_int64))))
-            out = {"what": "ivf_batch", "scan_kernel": a.scan_kernel, "stream_warps": a.stream_warps, "fuse_coarse": fuse, "B": B, "L": L}
+            out = {"what": "ivf_batch", "scan_kernel": a.scan_kernel, "stream_ctas": a.stream_ctas, "fuse_coarse": fuse, "B": B, "L": L}
             for name in ("coarse_rank", "scan_ivf", "dtable"):
                 ms, n = prof(lib, e3, name)
                 out[name + "_ms"] = round(ms / max(n, 1), 4)
