@@ -298,7 +298,7 @@ def run_ours(args):
             m_, n_ = C.c_double(0), C.c_int64(0)
             lib.rii_profile_get(el._h, b"scan_linear", C.byref(m_), C.byref(n_))
             lms = m_.value / max(n_.value, 1)
-            lin = {"kernel": "k_scan_skew32<NW=16, linear>", "workload": "linear scan, N=%d M=32 (random codes), topk=1, 1 query/launch" % nl,
+            lin = {"kernel": "k_scan_stream32<NW=12, linear, 4-stage rings, 1 CTA/SM>", "workload": "linear scan, N=%d M=32 (random codes), topk=1, 1 query/launch" % nl,
                    "bound": "hbm", "launch_ms": round(lms, 4), "algorithmic_bytes_per_launch": nl * M + 4 * M * CFG["Ks"],
                    "achieved": round((nl * M + 4 * M * CFG["Ks"]) / (lms * 1e-3) / 1e9, 1), "unit": "GB/s"}
             del el
@@ -311,7 +311,8 @@ def run_ours(args):
     peak, peak_src = peaks()
     # algorithmic bytes of the dominant kernel (posting-list scan), per launch: per query C*M code bytes
     # (C = L candidates) + 4*M*Ks (its distance table).  SURVEY's V*4 bytes of visited ids are NOT counted: the
-    # kernel streams a list-ordered code copy and reads ids only for survivors.
+    # kernel streams a list-ordered (skew64) code copy and reads ids only for survivors; the nlist*M center bytes of
+    # the fused coarse pass are not counted either (3 % of C*M at C2).
     frac_scanned = 1.0 / world if shard else 1.0
     q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 2048 queries
     alg = q_per_launch * (L * frac_scanned * M + 4 * M * CFG["Ks"])
@@ -330,13 +331,14 @@ def run_ours(args):
                    "index_build_s": round(t_build, 2)},
         "recall_at_1": round(recall, 4),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-        "roofline": {"kernel": "k_scan_skew32<NW=16, IVF>", "bound": "hbm", "achieved": None if achieved is None else round(achieved, 1),
+        "roofline": {"kernel": "k_scan_stream32<NW=6, IVF fused (table + coarse + plan + scan), 3-stage rings, 2 CTAs/SM>", "bound": "hbm", "achieved": None if achieved is None else round(achieved, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": None if achieved is None else round(achieved / peak, 4), "traffic": None,
                      "algorithmic_bytes_per_launch": int(alg), "queries_per_launch": int(q_per_launch),
                      "launch_ms": round(launch_ms, 4),
                      "note": "the 32 MB code table is L2-resident at N=1M: DRAM traffic << algorithmic bytes; the "
-                             "binding resource is the shared-memory lookup rate (DESIGN.md)"},
+                             "binding resource is the shared-memory lookup rate (1 wavefront per 32 lookups) plus the per-query "
+                             "serial phases; the HBM-bound case of the same engine is roofline_linear_scan (DESIGN.md)"},
         "kernel_ms": prof,
     }
     if lin is not None:
@@ -347,10 +349,10 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_sample(cw, codes, Q)
     try:  # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (tools/ncu_summary.py)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        line["roofline"]["traffic"] = tr.get("k_scan_skew32_ivf_fused_bytes_per_launch")
+        line["roofline"]["traffic"] = tr.get("k_scan_stream32_ivf_2cta_bytes_per_launch")
         line["roofline"]["traffic_source"] = tr.get("source")
         if lin is not None and "achieved" in lin:
-            lin["traffic"] = tr.get("k_scan_skew32_linear_N64M_bytes_per_launch") if int(args.linear_n) == 64000000 else None
+            lin["traffic"] = tr.get("k_scan_stream32_linear_N64M_bytes_per_launch") if int(args.linear_n) == 64000000 else None
     except Exception:
         pass
     print(json.dumps(line))

@@ -1154,11 +1154,15 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
 // 8-bit radix passes 13 K.)
 // Returns (in every thread) the number of keys in `out` (>= w), or -1 if more than 256 qualify (heavily tied
 // distances: the caller falls back to a full sort).
+// mm_ready: the caller already zeroed hist[0..255], accumulated min / max of d[] into hist[256] / hist[257] and
+// passed a CTA barrier (the v4 engine does that while it emits the distances).
 template <int NT>
-__device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist /* 256 + 4 ints */)
+__device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist /* 256 + 4 ints */,
+                                                   bool mm_ready = false)
 {
     const int lane = threadIdx.x & 31;
     uint32_t *mm = reinterpret_cast<uint32_t *>(hist + 256);  // [0] min, [1] max, [2] result count
+    if (!mm_ready) {
     for (int i = threadIdx.x; i < 256; i += NT) hist[i] = 0;
     if (threadIdx.x == 0) { mm[0] = 0xffffffffu; mm[1] = 0u; }
     __syncthreads();
@@ -1178,6 +1182,7 @@ __device__ __forceinline__ int cta_select_smallest(const uint32_t *d, int np, in
         if (lane == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
     }
     __syncthreads();
+    }
     const uint32_t mn = mm[0], range = mm[1] - mn;
     const int sh = range >= 256u ? (32 - __clz(range)) - 8 : 0;  // (v - mn) >> sh is in [0, 255]
     for (int i = threadIdx.x; i < np; i += NT) atomicAdd(&hist[(d[i] - mn) >> sh], 1);

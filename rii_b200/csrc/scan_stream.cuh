@@ -76,6 +76,92 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
     reinterpret_cast<uint4 *>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// The candidate plan of make_plan (kernels.cuh; SURVEY Appendix A.3, src/rii.h:286-322) computed by ONE WARP with prefix
+// scans instead of a serial walk, fused with the compaction into the stream engine's segment list.  Inputs by rank j <
+// w_eff in shared memory: s_f (global list length), s_pre (part held by lower ranks), s_loc (part held locally), s_off
+// (CSR offset), s_prow (first skew64 row).  Outputs: the non-empty segments, compacted in place -- s_gcum (inclusive
+// prefix of 64-row groups), s_take (local take), s_off, s_prow -- and J / take_last / flags of the query in global
+// memory exactly as make_plan writes them.  Returns the number of segments (0 when the plan is flagged).
+__device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, const int *s_f, const int *s_pre, const int *s_loc,
+                                         long long *s_off, long long *s_prow, int *s_gcum, int *s_take)
+{
+    const int W = p.w_eff;
+    // pass 1: F_j = inclusive prefix of the list lengths; jL = first rank with F_j >= L; F at rank w - 1
+    long long carry = 0, F_before = 0, F_w = -1;
+    int jL = W;
+    for (int base = 0; base < W; base += 32) {
+        const int j = base + lane;
+        const long long f = j < W ? (long long)s_f[j] : 0;
+        long long x = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        x += carry;
+        const unsigned hit = __ballot_sync(0xffffffffu, j < W && x >= p.L);
+        if (hit && jL == W) {
+            const int src = __ffs(hit) - 1;
+            jL = base + src;
+            F_before = __shfl_sync(0xffffffffu, x - f, src);
+        }
+        if (p.w - 1 >= base && p.w - 1 < base + 32 && p.w - 1 < W) F_w = __shfl_sync(0xffffffffu, x, p.w - 1 - base);
+        carry = __shfl_sync(0xffffffffu, x, 31);
+    }
+    // where the walk stops: at L (src/rii.h:302-304) or after the w-th list with >= topk candidates (src/rii.h:309)
+    int jstop = -1;
+    bool by_L = false;
+    if (jL < W && jL <= p.w - 1) { jstop = jL; by_L = true; }
+    else if (p.w - 1 < W && F_w >= p.topk) jstop = p.w - 1;
+    else if (jL < W) { jstop = jL; by_L = true; }
+    const int J = jstop >= 0 ? jstop + 1 : W;
+    const int flag = jstop >= 0 ? 0 : (W >= p.nlist ? 2 : 1);  // 2: empty result (src/rii.h:325); 1: walk beyond w (host re-runs)
+    // pass 2: local takes, compaction of the non-empty segments, group prefix
+    int cnt = 0, gcarry = 0, take_last = 0;
+    for (int base = 0; base < J; base += 32) {
+        const int j = base + lane;
+        long long take = 0;
+        int lt = 0;
+        long long off = 0, prow = 0;
+        if (j < J) {
+            take = (by_L && j == jstop) ? p.L - F_before : (long long)s_f[j];
+            long long l2 = take - s_pre[j];
+            l2 = l2 < 0 ? 0 : l2;
+            l2 = l2 > s_loc[j] ? s_loc[j] : l2;
+            lt = (int)l2;
+            off = s_off[j];
+            prow = s_prow[j];
+        }
+        if (J - 1 >= base && J - 1 < base + 32) take_last = (int)__shfl_sync(0xffffffffu, take, J - 1 - base);
+        const bool nz = flag == 0 && lt > 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        int g = nz ? (lt + 63) >> 6 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, g, o);
+            if (lane >= o) g += y;
+        }
+        g += gcarry;
+        __syncwarp();  // every lane has read its rank's inputs: compacted slots (<= j) may be overwritten
+        if (nz) {
+            const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+            s_gcum[pos] = g;
+            s_take[pos] = lt;
+            s_off[pos] = off;
+            s_prow[pos] = prow;
+        }
+        cnt += __popc(bal);
+        gcarry = __shfl_sync(0xffffffffu, g, 31);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        p.J[b] = J;
+        p.take_last[b] = take_last;
+        p.flags[b] = flag;
+    }
+    return cnt;
+}
+
 #define ST_LDS128(W, A)                                                                                       \
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"((W)[0]), "=r"((W)[1]), "=r"((W)[2]), "=r"((W)[3]) : "r"(A))
 // issue the copy of the next block of this warp's walk (data block or drain block) into ring stage S and describe
@@ -178,7 +264,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     // coarse distances of the fused coarse pass: nlist words after the segment tables
     const size_t meta_end = ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 + 15) & ~(size_t)15;
     uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + meta_end);
-    if (meta_end + (IVF && a.centers ? (size_t)a.nlist * 4 : 0) > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
+    // ... followed by the selection histogram: 256 bins + [min, max, count, -] (cta_select_smallest)
+    int *hist = reinterpret_cast<int *>(pool_d + ((IVF && a.centers ? a.nlist : 0) + 3) / 4 * 4);
+    if (meta_end + (IVF && a.centers ? (size_t)(a.nlist + 3) / 4 * 16 + 1040 : 0) > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
         __trap();  // host sized the launch wrongly
     const uint32_t ring = smem_base + hi0 + wid * ST_RING_BYTES + lane * 16;  // this lane's chunk column of the warp's ring
     const int b = blockIdx.y;
@@ -213,7 +301,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             }
             __syncthreads();
             if (threadIdx.x == 0) s_plan[0] = compact_segments(Jp);
-        } else if (threadIdx.x == 0) {  // coarse pass: one segment, the skew64 copy of the centers
+        } else {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        }
+        if (fused && threadIdx.x == 0) {  // coarse pass: one segment, the skew64 copy of the centers
+            hist[256] = -1;  // min (as unsigned)
+            hist[257] = 0;   // max
             s_gcum[0] = (a.nlist + 63) >> 6;
             s_take[0] = a.nlist;
             s_off[0] = 0;
@@ -357,6 +450,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         sel[t] = lane == t ? 1.f : 0.f;
     }
     uint32_t thr_hi = 0xffffffffu;
+    uint32_t d_lo = 0xffffffffu, d_hi = 0u;  // coarse pass: range of the distances this lane emitted
     // id of the row `half` (0: x, 1: y) of flattened group f in this lane
     auto row_id = [&](int f, int half) -> uint32_t {
         if constexpr (IVF) {
@@ -369,9 +463,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     };
     auto emit2 = [&](float dx, float dy, uint32_t d) {
         const int f = (int)(d >> 2);
-        if (IVF && direct) {  // coarse pass of the fused kernel: keep every distance
-            if (d & 1u) pool_d[f * 64 + lane] = __float_as_uint(dx);
-            if (d & 2u) pool_d[f * 64 + 32 + lane] = __float_as_uint(dy);
+        if (IVF && direct) {  // coarse pass of the fused kernel: keep every distance (and their range, for the selection)
+            const uint32_t ux = __float_as_uint(dx), uy = __float_as_uint(dy);
+            if (d & 1u) { pool_d[f * 64 + lane] = ux; d_lo = ux < d_lo ? ux : d_lo; d_hi = ux > d_hi ? ux : d_hi; }
+            if (d & 2u) { pool_d[f * 64 + 32 + lane] = uy; d_lo = uy < d_lo ? uy : d_lo; d_hi = uy > d_hi ? uy : d_hi; }
             return;
         }
         // distance part of the CTA threshold: long linear scans keep a cached copy that is refreshed after every push
@@ -420,8 +515,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             // ---- between the passes: select + rank the w_eff nearest centers, plan (all in shared memory) ----------
             if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // coarse pass done (the pass loop ended with a barrier)
             u64 *selk = reinterpret_cast<u64 *>(smem_raw + hi0);          // (rings idle) 8 KB: <= 256 selected keys, or the full sort (nlist <= 1024)
-            int *hist = reinterpret_cast<int *>(smem_raw + hi0 + 8192);   // 260 ints
-            int np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist);
+            int np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist, true);
             if (wid == 0) {
                 if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
                     const int P = next_pow2(a.nlist);
@@ -441,9 +535,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                     s_prow[j] = a.skew_off[no];
                 }
                 __syncwarp();
+                const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take);
                 if (lane == 0) {
-                    make_plan(a.plan, b, s_f, s_pre, s_loc, s_cum);
-                    s_plan[0] = compact_segments(a.plan.flags[b] != 0 ? 0 : a.plan.J[b]);
+                    s_plan[0] = jc;
                     *cta_thr = RII_KEY_MAX;  // (thr_w is still all-MAX: the coarse pass does not use the warp lists)
                 }
             }
@@ -477,7 +571,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // (only empty groups can be pending; the ring area is reused below)
-        if (!(IVF && direct)) warp_compact(wt, cta_thr, lane);
+        if (IVF && direct) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint32_t x = __shfl_xor_sync(0xffffffffu, d_lo, o), y = __shfl_xor_sync(0xffffffffu, d_hi, o);
+                d_lo = x < d_lo ? x : d_lo;
+                d_hi = y > d_hi ? y : d_hi;
+            }
+            if (lane == 0) {
+                atomicMin(reinterpret_cast<uint32_t *>(hist) + 256, d_lo);
+                atomicMax(reinterpret_cast<uint32_t *>(hist) + 257, d_hi);
+            }
+        } else {
+            warp_compact(wt, cta_thr, lane);
+        }
         __syncthreads();
     }
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();
@@ -530,7 +637,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 // dynamic shared memory of a launch shape, or 0 if keys + thresholds + segment tables do not fit below the table
 static inline size_t stream_smem_bytes(bool ivf, int nw, int ring_stages, uint32_t tb, int capw, int w_eff, size_t pool_bytes)
 {
-    const size_t meta = (((size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16 + 15) & ~(size_t)15) + pool_bytes;
+    const size_t meta = (((size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16 + 15) & ~(size_t)15) +
+                        (pool_bytes ? (pool_bytes + 15) / 16 * 16 + 1040 : 0);  // coarse distances + selection histogram
     if (meta > (size_t)tb - 1280) return 0;  // the window starts at 1 KB + static shared memory (<= 256 B allowed for)
     return (size_t)tb - 1024 + SK_LUT_BYTES + (size_t)nw * ring_stages * ST_BLOCK_BYTES;
 }
