@@ -947,6 +947,7 @@ struct SkewArgs {
     uint32_t smem_bytes;       // dynamic shared memory of the launch (the kernel lays its regions out around the table)
     const uint8_t *centers;    // IVF fused: (nlist, 32) coarse centers, or null (plan comes from a separate k_coarse_rank)
     int nlist;
+    int coarse_lists;          // v4 fused: rank the centers with the warps' top-k lists (nlist > 1024) instead of keeping every distance
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)

@@ -672,12 +672,15 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // v2 (skewed, bank-conflict-free) posting-list scan when it applies: M == 32, no target_ids, small topk, plan
     // fits shared memory.  With one CTA per query (parts == 1) the coarse ranking and the plan are fused into the
     // same kernel (two passes of one engine): no k_coarse_rank launch at all.
-    const int capw2 = std::max(64, next_pow2(c.topk + 32));
+    // (v4 with nlist > 1024 ranks the centers in the warps' top-k lists: they must hold max(topk, w_eff) keys)
+    const bool big_nlist = h->nlist > 1024;
+    const bool eng4_req = !(h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3);
+    const int capw2 = std::max(64, next_pow2((eng4_req && big_nlist ? std::max(c.topk, w_eff) : c.topk) + 32));
     const int eng2 = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;
     int nw2 = 0, shape2 = 0;
     size_t smem42 = 0;
     // (the fused coarse pass keeps nlist distances in shared memory: sized for it whenever fusing is possible)
-    const size_t pool4 = h->opt_fuse_coarse && h->nlist <= 1024 ? (size_t)h->nlist * 4 : 0;
+    const size_t pool4 = h->opt_fuse_coarse && !big_nlist ? (size_t)h->nlist * 4 : 0;
     if (eng2 == 4) shape2 = stream_pick(h, true, B >= 148, capw2, w_eff, pool4, &nw2, &smem42);
     else nw2 = eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
     const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
@@ -687,8 +690,8 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse && h->nlist <= 1024 &&
-                      (eng2 == 4 || (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8);
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse &&
+                      (eng2 == 4 || (!big_nlist && (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8));
     if (use_v2) {
         if (eng2 == 4) {
             CKR(ensure_skew_lists(h, st));
@@ -761,7 +764,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             if (eng2 == 4) {
                 sa.codes = h->skew_lists.as<uint8_t>();
                 sa.skew_off = h->skew_off.as<long long>();
-                if (fuse) sa.centers = h->centers_skew.as<uint8_t>();
+                if (fuse) { sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; }
             }
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         }

@@ -265,8 +265,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     const size_t meta_end = ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 + 15) & ~(size_t)15;
     uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + meta_end);
     // ... followed by the selection histogram: 256 bins + [min, max, count, -] (cta_select_smallest)
-    int *hist = reinterpret_cast<int *>(pool_d + ((IVF && a.centers ? a.nlist : 0) + 3) / 4 * 4);
-    if (meta_end + (IVF && a.centers ? (size_t)(a.nlist + 3) / 4 * 16 + 1040 : 0) > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
+    const bool use_pool = IVF && a.centers && !a.coarse_lists;
+    int *hist = reinterpret_cast<int *>(pool_d + ((use_pool ? a.nlist : 0) + 3) / 4 * 4);
+    if (meta_end + (use_pool ? (size_t)(a.nlist + 3) / 4 * 16 + 1040 : 0) > lut_off || hi0 + (size_t)NW * ST_RING_BYTES > a.smem_bytes)
         __trap();  // host sized the launch wrongly
     const uint32_t ring = smem_base + hi0 + wid * ST_RING_BYTES + lane * 16;  // this lane's chunk column of the warp's ring
     const int b = blockIdx.y;
@@ -301,12 +302,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             }
             __syncthreads();
             if (threadIdx.x == 0) s_plan[0] = compact_segments(Jp);
-        } else {
+        } else if (use_pool) {
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         }
         if (fused && threadIdx.x == 0) {  // coarse pass: one segment, the skew64 copy of the centers
-            hist[256] = -1;  // min (as unsigned)
-            hist[257] = 0;   // max
+            if (use_pool) {
+                hist[256] = -1;  // min (as unsigned)
+                hist[257] = 0;   // max
+            }
             s_gcum[0] = (a.nlist + 63) >> 6;
             s_take[0] = a.nlist;
             s_off[0] = 0;
@@ -376,7 +379,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     uint32_t dsc[ST_R];
 #pragma unroll
     for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
-    bool direct = fused;  // coarse pass: every distance goes to pool_d[center]
+    // coarse pass of the fused kernel.  nlist <= 1024 ("direct"): every distance goes to pool_d[center] and a histogram
+    // select ranks the w nearest.  Larger nlist (a.coarse_lists): the pass keeps the w_eff best (distance, center) keys in
+    // the warps' top-k lists like any scan, and the CTA merges them.
+    bool pass0 = fused;
+    bool direct = fused && !a.coarse_lists;
+    if (fused && !direct) {
+        wt.k = a.w_eff;
+        wt.cap = next_pow2(a.w_eff + 32) < 64 ? 64 : next_pow2(a.w_eff + 32);
+    }
+    __shared__ int s_cnt[NW];
     if (fused) set_range(1, 0);
     else set_range(gridDim.x, blockIdx.x);
     // the first ST_D blocks go out before the table is built
@@ -454,6 +466,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     // id of the row `half` (0: x, 1: y) of flattened group f in this lane
     auto row_id = [&](int f, int half) -> uint32_t {
         if constexpr (IVF) {
+            if (pass0) return (uint32_t)(f * 64 + half * 32 + lane);  // coarse pass: the center's index
             const int j = seg_of(f);
             const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + half * 32 + lane;
             return (uint32_t)__ldg(a.ids + s_off[j] + r);
@@ -514,8 +527,42 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         if (pass == 1) {
             // ---- between the passes: select + rank the w_eff nearest centers, plan (all in shared memory) ----------
             if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // coarse pass done (the pass loop ended with a barrier)
-            u64 *selk = reinterpret_cast<u64 *>(smem_raw + hi0);          // (rings idle) 8 KB: <= 256 selected keys, or the full sort (nlist <= 1024)
-            int np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist, true);
+            u64 *selk = reinterpret_cast<u64 *>(smem_raw + hi0);          // (rings idle) <= 256 selected keys, the full sort (nlist <= 1024), or the merged warp lists
+            int np = 0;
+            if (direct) {
+                np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist, true);
+            } else {  // merge the warps' sorted lists (each <= w_eff keys) into the ranked list
+                if (lane == 0) s_cnt[wid] = wt.count;
+                __syncthreads();
+                int tot = 0;
+                for (int w2 = 0; w2 < NW; ++w2) tot += s_cnt[w2];
+                const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw);
+                if (tot <= 256) {
+                    if (wid == 0) {
+                        int o = 0;
+                        for (int w2 = 0; w2 < NW; ++w2) {
+                            for (int i = lane; i < s_cnt[w2]; i += 32) selk[o + i] = allkeys[(size_t)w2 * capw + i];
+                            o += s_cnt[w2];
+                        }
+                        warp_sort_any(selk, tot, lane);
+                    }
+                } else {
+                    BlockTopk tk;
+                    const int mcap = next_pow2(NW * a.w_eff + 1);
+                    tk.keys = selk;
+                    tk.thr = selk + mcap;
+                    tk.count = reinterpret_cast<int *>(selk + mcap + 1);
+                    tk.cap = mcap;
+                    tk.k = a.w_eff;
+                    tk.init();
+                    for (int w2 = 0; w2 < NW; ++w2)
+                        for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
+                    tk.compact();
+                }
+                __syncthreads();
+                np = tot;
+                if (threadIdx.x < NW) thr_w[threadIdx.x] = RII_KEY_MAX;  // (cta_thr is reset with the plan below)
+            }
             if (wid == 0) {
                 if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
                     const int P = next_pow2(a.nlist);
@@ -538,7 +585,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take);
                 if (lane == 0) {
                     s_plan[0] = jc;
-                    *cta_thr = RII_KEY_MAX;  // (thr_w is still all-MAX: the coarse pass does not use the warp lists)
+                    *cta_thr = RII_KEY_MAX;
                 }
             }
             __syncthreads();
@@ -546,6 +593,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             J = s_plan[0];
             pc = a.codes;
             direct = false;
+            pass0 = false;
+            wt.k = a.k;
+            wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
             wt.count = 0;
             thr_hi = 0xffffffffu;
             set_range(1, 0);
@@ -589,7 +639,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     }
     if (dbg && threadIdx.x == 0) dbg[2] = clock64();
     {   // CTA merge of the (sorted) warp lists, reusing the lut2 area for the keys
-        __shared__ int s_cnt[NW];
         if (lane == 0) s_cnt[wid] = wt.count;
         __syncthreads();
         int tot = 0;

@@ -532,3 +532,26 @@ def test_stream_kernel_tracks_index_updates():
     for b in range(3):
         exp = O.query_ivf(O.dtable(Q[b], cw, 16), codes, centers, offsets, ids, 2, 500)
         assert_same_result(bi[b], bd[b], exp[0], exp[1], "after second reconfigure %d" % b)
+
+
+@pytest.mark.parametrize("sk", [4, 401])
+def test_stream_fused_large_nlist(sk):
+    """nlist > 1024: the fused v4 kernel ranks the coarse centers in the warps' top-k lists (pass 0 is an ordinary
+    scan with k = w) instead of the histogram select; same results as the unfused v1 pipeline and the oracle."""
+    D, M, Ks, N, nlist = 128, 32, 256, 150000, 1500
+    cw, codes, Q = synth(D, M, Ks, N, 150, seed=5)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    Qb = np.ascontiguousarray(Q)
+    for topk, L in [(1, 300), (5, 4000), (40, 100), (3, 20000)]:   # w = 6, 43, 4, 203 (<= 224: the lists hold them)
+        set_kernel(e, sk)
+        f = e.query_batch(Qb, topk, L=L, method="ivf")
+        e.set_option("scan_kernel", 1)
+        u = e.query_batch(Qb, topk, L=L, method="ivf")
+        assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1])), (topk, L)
+        for b in range(0, 150, 31):
+            exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
+            n = int(f[2][b])
+            assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "large nlist k=%d L=%d b=%d" % (topk, L, b))
