@@ -389,11 +389,11 @@ int ensure_codes_list(rii_index *h, cudaStream_t st)  // list-ordered copy for t
 }
 
 int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
-               long long prows, uint8_t *out, cudaStream_t st)
+               long long prows, uint8_t *out, int M, cudaStream_t st)
 {
     if (prows <= 0) return 0;
     const long long thr = prows * 2;
-    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(codes, ids, offsets, d_skew_off, nseg, n_single, 0, prows, out);
+    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(codes, ids, offsets, d_skew_off, nseg, n_single, 0, prows, out, M);
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;
@@ -402,12 +402,12 @@ int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, c
 int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id (linear scan, scan_stream.cuh)
 {
     if (h->skew_lin_rows == h->N) return 0;
-    const long long prows = skew64_rows(h->N);
+    const long long prows = skew64_rows(h->N, h->M / 32);
     CKR(h->skew_lin.ensure((size_t)prows * 32));
     CKR(h->skew_misc_off.ensure(32));
     const long long off[2] = {0, prows};
     CK(cudaMemcpyAsync(h->skew_misc_off.p, off, 16, cudaMemcpyHostToDevice, st));
-    CKR(skew_build(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N, prows, h->skew_lin.as<uint8_t>(), st));
+    CKR(skew_build(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N, prows, h->skew_lin.as<uint8_t>(), h->M, st));
     h->skew_lin_rows = h->N;
     return 0;
 }
@@ -415,13 +415,13 @@ int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id
 int ensure_centers_skew(rii_index *h, cudaStream_t st)  // skew64 of the coarse centers (fused coarse pass)
 {
     if (h->centers_skew_valid) return 0;
-    const long long prows = skew64_rows(h->nlist);
+    const long long prows = skew64_rows(h->nlist, h->M / 32);
     CKR(h->centers_skew.ensure((size_t)prows * 32));
     CKR(h->skew_misc_off.ensure(32));
     const long long off[2] = {0, prows};
     CK(cudaMemcpyAsync(h->skew_misc_off.as<long long>() + 2, off, 16, cudaMemcpyHostToDevice, st));
     CKR(skew_build(h->centers.as<uint8_t>(), nullptr, nullptr, h->skew_misc_off.as<long long>() + 2, 1, h->nlist, prows,
-                   h->centers_skew.as<uint8_t>(), st));
+                   h->centers_skew.as<uint8_t>(), h->M, st));
     h->centers_skew_valid = true;
     return 0;
 }
@@ -431,21 +431,27 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
     if (h->skew_lists_valid) return 0;
     const int nlist = h->nlist;
     std::vector<long long> off((size_t)nlist + 1, 0);
-    for (int i = 0; i < nlist; ++i) off[i + 1] = off[i] + skew64_rows(h->h_offsets[i + 1] - h->h_offsets[i]);
+    for (int i = 0; i < nlist; ++i) off[i + 1] = off[i] + skew64_rows(h->h_offsets[i + 1] - h->h_offsets[i], h->M / 32);
     CKR(h->skew_off.ensure((size_t)(nlist + 1) * 8));
     CKR(h->skew_lists.ensure((size_t)std::max<long long>(1, off[nlist]) * 32));
     CK(cudaMemcpyAsync(h->skew_off.p, off.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, st));
     CKR(skew_build(h->d_codes, h->ids.as<int>(), h->offsets.as<long long>(), h->skew_off.as<long long>(), nlist, 0, off[nlist],
-                   h->skew_lists.as<uint8_t>(), st));
+                   h->skew_lists.as<uint8_t>(), h->M, st));
     h->skew_lists_valid = true;
     return 0;
 }
 
 // ---- v4 (skew64 streaming) scan launcher ------------------------------------------------------------------
 // shapes: 1 = one CTA per SM (12 warps, 4-stage rings, table at 0x10000); 2 = two CTAs per SM (6 warps, 3-stage rings,
-// table at 0x2000); returns the shape that fits (0: none) and its warps / dynamic shared memory
+// table at 0x3000); 3 = M = 64 (8 warps, 4-stage rings, two tables at 0x6000, one CTA per SM);
+// returns the shape that fits (0: none) and its warps / dynamic shared memory
 int stream_pick(const rii_index *h, bool ivf, bool per_query_batch, int capw, int w_eff, size_t pool_bytes, int *nw, size_t *smem)
 {
+    if (h->M == 64) {
+        const size_t b = stream_smem_bytes(ivf, 8, 4, ST_TB3, capw, w_eff, pool_bytes, 2);
+        if (b && b <= SK_DYN_SMEM) { *nw = 8; *smem = b; return 3; }
+        return 0;
+    }
     const bool want2 = ivf && per_query_batch && h->opt_stream_ctas != 1;
     if (want2) {
         const size_t b = stream_smem_bytes(true, 6, 3, ST_TB2, capw, w_eff, pool_bytes);
@@ -456,10 +462,10 @@ int stream_pick(const rii_index *h, bool ivf, bool per_query_batch, int capw, in
     return 0;
 }
 
-template <int NW, bool IVF, int R, int MINB, uint32_t TB>
+template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H>
 int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
 {
-    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB>;
+    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB, H>;
     static bool configured = false;  // per process and instantiation
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_DYN_SMEM));
@@ -473,9 +479,11 @@ int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
 
 int launch_stream(int shape, bool ivf, const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
 {
-    if (shape == 2) return launch_stream_t<6, true, 3, 2, ST_TB2>(a, parts, B, smem, st);
-    if (ivf) return launch_stream_t<12, true, 4, 1, ST_TB1>(a, parts, B, smem, st);
-    return launch_stream_t<12, false, 4, 1, ST_TB1>(a, parts, B, smem, st);
+    if (shape == 3) return ivf ? launch_stream_t<8, true, 4, 1, ST_TB3, 2>(a, parts, B, smem, st)
+                               : launch_stream_t<8, false, 4, 1, ST_TB3, 2>(a, parts, B, smem, st);
+    if (shape == 2) return launch_stream_t<6, true, 3, 2, ST_TB2, 1>(a, parts, B, smem, st);
+    if (ivf) return launch_stream_t<12, true, 4, 1, ST_TB1, 1>(a, parts, B, smem, st);
+    return launch_stream_t<12, false, 4, 1, ST_TB1, 1>(a, parts, B, smem, st);
 }
 
 // ---- v2 (skewed) scan launcher: the most warps per SM whose shared-memory footprint fits ---------------
@@ -593,7 +601,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         size_t smem4 = 0;
         if (eng == 4) shape = stream_pick(h, false, false, capw, 0, 0, &nw, &smem4);
         else nw = eng == 3 ? dual_pick_nw(false, capw, 0) : skew_pick_nw(false, capw, 0);
-        const bool v2_ok = M == 32 && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
+        const bool v2_ok = (M == 32 || (M == 64 && eng == 4)) && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
         const bool use_v2 = v2_ok && (h->opt_scan_kernel >= 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
         if (h->opt_scan_kernel >= 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 needs M == 32, no target_ids and topk <= 224");
         if (use_v2) {
@@ -683,7 +691,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     const size_t pool4 = h->opt_fuse_coarse && !big_nlist ? (size_t)h->nlist * 4 : 0;
     if (eng2 == 4) shape2 = stream_pick(h, true, B >= 148, capw2, w_eff, pool4, &nw2, &smem42);
     else nw2 = eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
-    const bool v2_ok = M == 32 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
+    const bool v2_ok = (M == 32 || (M == 64 && eng2 == 4)) && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
     if (h->opt_scan_kernel >= 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 (ivf) needs M == 32, topk <= 224 and a short list plan");
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),

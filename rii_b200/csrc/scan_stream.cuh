@@ -33,19 +33,24 @@
 //   one CTA per SM:  NW = 12, R = 4, TB = 0x10000 -- long scans (linear), large topk / many lists
 //   two CTAs per SM: NW = 6,  R = 3, TB = 0x3000  -- per-query IVF batches: the serial phases of one query (table build,
 //                    coarse selection, plan, final merge) overlap the scan of the other CTA's query
+//   M = 64:          NW = 8,  R = 4, TB = 0x6000, two tables (128 KB), one CTA per SM
 #define ST_TB1 0x10000u
 #define ST_TB2 0x3000u
+#define ST_TB3 0x6000u
 #define ST_TABLE_LIMIT 1e37f        // 32 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
 
-// physical rows of a skew64 segment holding `len` code rows
-static __host__ __device__ inline long long skew64_rows(long long len) { return 64 * ((len + 63) / 64 + 1); }
+// 32-byte windows of a skew64 segment holding `len` code rows of M = 32 H bytes: H blocks of 64 windows per group of 64
+// rows, plus H blocks after the last group (the first one holds the lagging tail of the last rows; with H = 2 the
+// second keeps every segment an even number of blocks, so that a block's half-row index stays a compile-time constant
+// of the pipeline stage)
+static __host__ __device__ inline long long skew64_rows(long long len, int H = 1) { return 64 * ((len + 63) / 64 + 1) * H; }
 
 // Build (a range of) skew64 segments.  codes: (rows, 32) by id; ids / offsets: CSR of the segments (null: ONE segment
 // = rows [0, n_single) in id order); skew_off: (nseg + 1) first physical row (32-byte unit) of every segment, a
 // multiple of 64.  One thread per 16-byte chunk.
 __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__restrict__ ids, const long long *__restrict__ offsets,
                                const long long *__restrict__ skew_off, int nseg, long long n_single, long long prow0,
-                               long long prow1, uint8_t *__restrict__ out)
+                               long long prow1, uint8_t *__restrict__ out, int M)
 {
     const long long i = prow0 * 2 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the table
     const long long prow = i >> 1;
@@ -66,10 +71,10 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
     for (int j = 0; j < 16; ++j) {
         const long long x = 32 * b - lag + 16 * half + j;  // byte of stream s
         if (x >= 0) {
-            const long long r = 64 * (x >> 5) + s;         // row of the segment
+            const long long r = 64 * (x / M) + s;          // row of the segment
             if (r < len) {
                 const long long id = ids ? (long long)ids[ioff + r] : r;
-                w[j >> 2] |= (uint32_t)__ldg(codes + id * 32 + (x & 31)) << (8 * (j & 3));
+                w[j >> 2] |= (uint32_t)__ldg(codes + id * M + (x % M)) << (8 * (j & 3));
             }
         }
     }
@@ -171,17 +176,24 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
     {                                                                                                         \
         if (ACTIVE) {                                                                                         \
             const int g_ = cur_f - seg_g0;                                                                    \
-            const uint8_t *p_ = pc + ((size_t)(seg_prow + (long long)g_ * 64)) * 32 + lane * 16;              \
-            if (!drain_next) {                                                                                \
+            const long long prow_ = seg_prow; /* (load_seg below may move on to the next segment) */          \
+            int blk_;                                                                                         \
+            if (drain_left == 0) { /* block hb of group cur_f; the group's descriptor travels with its first block */ \
+                const int hb_ = H == 1 ? 0 : hb;                                                              \
+                blk_ = g_ * H + hb_;                                                                          \
                 const int r_ = g_ * 64 + lane;                                                                \
-                D = ((uint32_t)cur_f << 2) | (r_ < seg_take ? 1u : 0u) | (r_ + 32 < seg_take ? 2u : 0u);      \
-                ++cur_f;                                                                                      \
-                drain_next = cur_f == f_end || cur_f == seg_gend;                                             \
-            } else { /* the block after the segment's (or the range's) last group: only the lagging bytes matter */ \
+                D = hb_ ? 0u : (((uint32_t)cur_f << 2) | (r_ < seg_take ? 1u : 0u) | (r_ + 32 < seg_take ? 2u : 0u)); \
+                if (H == 1 || ++hb == H) {                                                                    \
+                    hb = 0;                                                                                   \
+                    ++cur_f;                                                                                  \
+                    if (cur_f == f_end || cur_f == seg_gend) drain_left = H;                                  \
+                }                                                                                             \
+            } else { /* the H blocks after the segment's (or the range's) last group: only the lagging bytes of the first matter */ \
+                blk_ = g_ * H + (H - drain_left);                                                             \
                 D = 0u;                                                                                       \
-                drain_next = false;                                                                           \
-                if (cur_f < f_end) load_seg(seg + 1);                                                         \
+                if (--drain_left == 0 && cur_f < f_end) load_seg(seg + 1);                                    \
             }                                                                                                 \
+            const uint8_t *p_ = pc + (size_t)prow_ * 32 + (size_t)blk_ * ST_BLOCK_BYTES + lane * 16;          \
             const uint32_t dst_ = ring + (S) * ST_BLOCK_BYTES;                                                \
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_), "l"(p_));                   \
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 512), "l"(p_ + 512));       \
@@ -190,19 +202,24 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
         }                                                                                                     \
         asm volatile("cp.async.commit_group;");                                                               \
     }
-// one lookup step of both streams: PRMT builds ks << 8 | column byte offset, the load's immediate adds the table's
-// (compile-time) absolute shared address and the step; acc / out updates as in DU_STEP (scan_dual.cuh)
+// one lookup step of both streams: PRMT builds ks << 8 | column byte offset, the load's immediate adds the (compile-time)
+// absolute shared address of the block's table and the step.  In a block that holds the first 32 bytes of the rows
+// (h_ == 0) the sums restart / are captured at the lane's row boundary (acc / out updates of DU_STEP, scan_dual.cuh); in
+// the other blocks of a row (M = 64) the lookups are simply added.
 #define ST_STEP(WX, WY, BYTE, T)                                                                              \
     {                                                                                                         \
         const uint32_t ax_ = __byte_perm(WX, colreg, 0x7604 | ((BYTE) << 4));                                 \
         const uint32_t ay_ = __byte_perm(WY, colreg, 0x7604 | ((BYTE) << 4));                                 \
         float vx_, vy_;                                                                                       \
-        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vx_) : "r"(ax_), "n"(TB + 4 * (T)));                \
-        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vy_) : "r"(ay_), "n"(TB + 4 * (T)));                \
-        asm("{.reg .b64 v, kk, ss; mov.b64 v, {%4, %5}; mov.b64 kk, {%2, %2}; mov.b64 ss, {%3, %3};"         \
-            " fma.rn.f32x2 %1, %0, ss, %1; fma.rn.f32x2 %0, %0, kk, v;}"                                     \
-            : "+l"(acc2), "+l"(out2)                                                                          \
-            : "f"(keep[T]), "f"(sel[T]), "f"(vx_), "f"(vy_));                                                 \
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vx_) : "r"(ax_), "n"(TB + h_ * SK_LUT_BYTES + 4 * (T))); \
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(vy_) : "r"(ay_), "n"(TB + h_ * SK_LUT_BYTES + 4 * (T))); \
+        if constexpr (h_ == 0)                                                                                \
+            asm("{.reg .b64 v, kk, ss; mov.b64 v, {%4, %5}; mov.b64 kk, {%2, %2}; mov.b64 ss, {%3, %3};"     \
+                " fma.rn.f32x2 %1, %0, ss, %1; fma.rn.f32x2 %0, %0, kk, v;}"                                 \
+                : "+l"(acc2), "+l"(out2)                                                                      \
+                : "f"(keep[T]), "f"(sel[T]), "f"(vx_), "f"(vy_));                                             \
+        else                                                                                                  \
+            asm("{.reg .b64 v; mov.b64 v, {%1, %2}; add.rn.f32x2 %0, %0, v;}" : "+l"(acc2) : "f"(vx_), "f"(vy_)); \
     }
 #define ST_WORD(BX, BY, Q)                                                                                    \
     ST_STEP(BX[Q], BY[Q], 0, 4 * (Q) + 0)                                                                     \
@@ -214,10 +231,15 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
         ST_WORD(BX, BY, 0) ST_WORD(BX, BY, 1) ST_WORD(BX, BY, 2) ST_WORD(BX, BY, 3)                           \
         ST_WORD(BX, BY, 4) ST_WORD(BX, BY, 5) ST_WORD(BX, BY, 6) ST_WORD(BX, BY, 7)                           \
     }
-// one pipeline stage: block m + S lives in ring stage S; the stage of block m + S - 1 takes block m + S + ST_D
+// one pipeline stage: block m + S lives in ring stage S (its half-row index is S % H: every walk is a whole number of
+// H-block units); the stage of block m + S - 1 takes block m + S + ST_D.  After a block with h_ == 0, out2 holds the
+// finished distances of the PREVIOUS group (descriptor d_last0).
 #define ST_STAGE(S)                                                                                           \
     if (m + (S) < nblk) {                                                                                     \
-        const uint32_t dprev_ = dsc[((S) + ST_D) % ST_R];                                                     \
+        constexpr int h_ = (S) % H;                                                                           \
+        /* descriptor of the group that completes in this block: H = 1: the previous block's (its slot is refilled */ \
+        /* below); H = 2: kept in d_last0 */                                                                  \
+        const uint32_t dsel_ = H == 1 ? dsc[((S) + ST_D) % ST_R] : dsc[S];                                    \
         ST_ISSUE(((S) + ST_D) % ST_R, dsc[((S) + ST_D) % ST_R], m + (S) + ST_D < nblk)                        \
         if constexpr (ST_D == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");                         \
         else asm volatile("cp.async.wait_group 2;" ::: "memory");                                             \
@@ -227,17 +249,27 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
         ST_LDS128(wy_, ring + (S) * ST_BLOCK_BYTES + 1024);                                                   \
         ST_LDS128(wy_ + 4, ring + (S) * ST_BLOCK_BYTES + 1536);                                               \
         ST_BLOCK(wx_, wy_)                                                                                    \
-        float dx_, dy_;                                                                                       \
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(dx_), "=f"(dy_) : "l"(out2));                                      \
-        out2 = 0ull;                                                                                          \
-        emit2(dx_, dy_, dprev_);                                                                              \
+        if constexpr (h_ == 0) {                                                                              \
+            float dx_, dy_;                                                                                   \
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(dx_), "=f"(dy_) : "l"(out2));                                  \
+            out2 = 0ull;                                                                                      \
+            if constexpr (H == 1) {                                                                           \
+                emit2(dx_, dy_, dsel_);                                                                       \
+            } else {                                                                                          \
+                emit2(dx_, dy_, d_last0);                                                                     \
+                d_last0 = dsel_;                                                                              \
+            }                                                                                                 \
+        }                                                                                                     \
     }
 
 // Args: SkewArgs (kernels.cuh) with `codes` = skew64 table of the pass-1 rows (linear: the codes by id, one segment;
 // IVF: every local posting list, segment i at physical row skew_off[i]) and `centers` = skew64 of the coarse centers.
-template <int NW, bool IVF, int ST_R, int MINB, uint32_t TB>
+template <int NW, bool IVF, int ST_R, int MINB, uint32_t TB, int H>
 __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 {
+    static_assert(H == 1 || H == 2, "M = 32 or 64");
+    static_assert(ST_R % H == 0, "a block's half-row index must be a constant of its pipeline stage");
+    constexpr int M = 32 * H;                                // bytes per code row; H tables of 64 KB
     constexpr int ST_D = ST_R - 1;                           // blocks in flight ahead of the one being scanned
     constexpr uint32_t ST_RING_BYTES = ST_R * ST_BLOCK_BYTES;  // per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -260,7 +292,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     long long *s_prow = s_off + wq;
     int *s_gcum = reinterpret_cast<int *>(s_prow + wq);
     int *s_take = s_gcum + wq, *s_cum = s_take + wq, *s_f = s_cum + wq, *s_pre = s_f + wq, *s_loc = s_pre + wq, *s_plan = s_loc + wq;
-    const uint32_t hi0 = lut_off + SK_LUT_BYTES;                      // scratch above the table
+    const uint32_t hi0 = lut_off + H * SK_LUT_BYTES;                  // rings / scratch above the table(s)
     // coarse distances of the fused coarse pass: nlist words after the segment tables
     const size_t meta_end = ((size_t)NW * capw * 8 + 8 + NW * 8 + (size_t)wq * 40 + 16 + 15) & ~(size_t)15;
     uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + meta_end);
@@ -332,10 +364,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 
     // per-pass state (warp-uniform)
     const uint8_t *pc = fused ? a.centers : a.codes;  // skew64 table of the pass
-    int f0 = 0, f_end = 0, cur_f = 0, nblk = 0;
+    int f0 = 0, f_end = 0, cur_f = 0, nblk = 0, hb = 0, drain_left = 0;
+    uint32_t d_last0 = 0u;  // descriptor of the group whose rows complete in the next first-half block
     int seg = 0, seg_g0 = 0, seg_gend = 0, seg_take = 0;
     long long seg_prow = 0;
-    bool drain_next = false;
     WarpTopk wt;
     wt.keys = wkeys;
     wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
@@ -368,11 +400,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         if (f0 > G) f0 = G;
         f_end = f0 + per < G ? f0 + per : G;
         cur_f = f0;
-        drain_next = false;
+        hb = 0;
+        drain_left = 0;
+        d_last0 = 0u;
         nblk = 0;
         if (f_end > f0) {
             const int sa_ = seg_of(f0), sb_ = seg_of(f_end - 1);
-            nblk = (f_end - f0) + (sb_ - sa_ + 1);
+            nblk = ((f_end - f0) + (sb_ - sa_ + 1)) * H;
             load_seg(sa_);
         }
     };
@@ -397,56 +431,63 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     if constexpr (ST_D == 3) ST_ISSUE(2 % ST_R, dsc[2 % ST_R], 2 < nblk)
 
     int bad = 0;
-    {   // lut2[ks][c] = T[c % 32][ks]; rows >= Ks are zero (padding bytes index row 0 only)
+    {   // table h (h < H), column c < 64 holds sub-space (32 h + c - 32) mod M: for M = 32 that is c mod 32 (every
+        // sub-space twice, so that the lane's column t + 32 - l never wraps); for M = 64 each table holds all 64
+        // sub-spaces once, table 0 arranged for the first halves of the rows and table 1 for the second halves.  Entry
+        // (m, ks) therefore goes to column (m + 32) & 63 of table 0 and to column m of table H - 1.  Rows >= Ks are zero.
+        const int rot = (int)((blockIdx.y * gridDim.x + blockIdx.x) * 53u) & 255;
+        float *lutB = lut2 + (H - 1) * (SK_LUT_BYTES / 4);
         if (a.T) {
-            const float *T = a.T + (size_t)b * 32 * a.Ks;
-#pragma unroll 8
-            for (int e = threadIdx.x; e < 256 * 64; e += NW * 32) {
-                int ks = e >> 6, c = e & 63;
-                const float v = ks < a.Ks ? __ldg(T + (c & 31) * a.Ks + ks) : 0.f;
+            const float *T = a.T + (size_t)b * M * a.Ks;
+            for (int e = threadIdx.x; e < 256 * M; e += NW * 32) {
+                const int ks = e / M, m = e % M;
+                const float v = ks < a.Ks ? __ldg(T + m * a.Ks + ks) : 0.f;
                 bad |= !(v <= ST_TABLE_LIMIT);
-                lut2[e] = v;
+                lut2[ks * 64 + ((m + 32) & 63)] = v;
+                lutB[ks * 64 + (m & 63)] = v;
             }
         } else {
-            // K1 fused (src/rii.h:361-373): entry (m = lane, ks) -> both columns m and m + 32 of row ks; the
-            // lane's query sub-vector stays in registers, codewords come from the sub-space-fastest copy (one
-            // contiguous 32*Ds-float row per ks), stores are bank-conflict free.
-            const float *qm = a.Q + (size_t)b * 32 * a.Ds + (size_t)lane * a.Ds;
-            // every CTA of the grid reads the same 32*Ks*Ds floats at about the same time: each starts at a different
-            // codeword row, which spreads the requests over the L2 slices
-            const int rot = (int)((blockIdx.y * gridDim.x + blockIdx.x) * 53u) & 255;
-            if (a.Ds == 4 && a.Ks == 256) {  // the common shape: 16 independent 16-byte loads in flight per lane
-                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
-                const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + lane;
+            // K1 fused (src/rii.h:361-373): the lane's query sub-vector(s) stay in registers, codewords come from the
+            // sub-space-fastest copy (one contiguous M*Ds-float row per ks), stores are bank-conflict free.  Every CTA
+            // of the grid reads the same M*Ks*Ds floats at about the same time: each starts at a different codeword
+            // row, which spreads the requests over the L2 slices.
+#pragma unroll
+            for (int mh = 0; mh < H; ++mh) {
+                const int m = mh * 32 + lane;
+                const float *qm = a.Q + (size_t)b * M * a.Ds + (size_t)m * a.Ds;
+                if (a.Ds == 4 && a.Ks == 256) {  // 16 independent 16-byte loads in flight per lane
+                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
+                    const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
-                for (int i = wid; i < 256; i += NW) {
-                    const int ks = (i + rot) & 255;
-                    const float4 c4 = __ldg(cw4 + ks * 32);
-                    const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
-                    bad |= !(v <= ST_TABLE_LIMIT);
-                    lut2[ks * 64 + lane] = v;
-                    lut2[ks * 64 + lane + 32] = v;
-                }
-            } else if (a.Ds <= 4) {
-                float qv[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+                    for (int i = wid; i < 256; i += NW) {
+                        const int ks = (i + rot) & 255;
+                        const float4 c4 = __ldg(cw4 + ks * M);
+                        const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + ((m + 32) & 63)] = v;
+                        lutB[ks * 64 + m] = v;
+                    }
+                } else if (a.Ds <= 4) {
+                    float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
 #pragma unroll 8
-                for (int i = wid; i < 256; i += NW) {
-                    const int ks = (i + rot) & 255;
-                    float v = 0.f;
-                    if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds);
-                    bad |= !(v <= ST_TABLE_LIMIT);
-                    lut2[ks * 64 + lane] = v;
-                    lut2[ks * 64 + lane + 32] = v;
-                }
-            } else {
+                    for (int i = wid; i < 256; i += NW) {
+                        const int ks = (i + rot) & 255;
+                        float v = 0.f;
+                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * M + m) * a.Ds, a.Ds);
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + ((m + 32) & 63)] = v;
+                        lutB[ks * 64 + m] = v;
+                    }
+                } else {
 #pragma unroll 1
-                for (int ks = wid; ks < 256; ks += NW) {
-                    float v = 0.f;
-                    if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * 32 + lane) * a.Ds, a.Ds, a.variant);
-                    bad |= !(v <= ST_TABLE_LIMIT);
-                    lut2[ks * 64 + lane] = v;
-                    lut2[ks * 64 + lane + 32] = v;
+                    for (int ks = wid; ks < 256; ks += NW) {
+                        float v = 0.f;
+                        if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * M + m) * a.Ds, a.Ds, a.variant);
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + ((m + 32) & 63)] = v;
+                        lutB[ks * 64 + m] = v;
+                    }
                 }
             }
         }
@@ -507,12 +548,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 const int s = half * 32 + lane;
                 if (g * 64 + s < s_take[j]) {
                     dsc_ |= 1u << half;
-                    const uint8_t *p = pc + ((size_t)s_prow[j] + (size_t)g * 64) * 32 + half * 1024 + lane * 16;
+                    const uint8_t *p = pc + (size_t)s_prow[j] * 32 + (size_t)g * H * ST_BLOCK_BYTES + half * 1024 + lane * 16;
                     float d = 0.f;
-                    for (int m = 0; m < 32; ++m) {
-                        const int x = lane + m;  // byte of the 64-byte span [window b | window b + 1] of stream s
+                    for (int m = 0; m < M; ++m) {
+                        const int x = lane + m;  // byte of the span [window b | window b + 1 | ...] of stream s
                         const uint32_t ks = __ldg(p + (x >> 5) * ST_BLOCK_BYTES + ((x >> 4) & 1) * 512 + (x & 15));
-                        d = m ? __fadd_rn(d, lut2[ks * 64 + m]) : lut2[ks * 64];
+                        const float v = lut2[ks * 64 + ((m + 32) & 63)];  // table 0 holds every sub-space
+                        d = m ? __fadd_rn(d, v) : v;
                     }
                     dd[half] = d;
                 }
@@ -598,7 +640,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
             wt.count = 0;
             thr_hi = 0xffffffffu;
-            set_range(1, 0);
+            set_range(1, 0);  // (also resets the walk state: hb, drain_left, d_last0)
 #pragma unroll
             for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
             ST_ISSUE(0, dsc[0], 0 < nblk)
@@ -684,10 +726,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 }
 
 // dynamic shared memory of a launch shape, or 0 if keys + thresholds + segment tables do not fit below the table
-static inline size_t stream_smem_bytes(bool ivf, int nw, int ring_stages, uint32_t tb, int capw, int w_eff, size_t pool_bytes)
+static inline size_t stream_smem_bytes(bool ivf, int nw, int ring_stages, uint32_t tb, int capw, int w_eff, size_t pool_bytes, int H = 1)
 {
     const size_t meta = (((size_t)nw * capw * 8 + 8 + (size_t)nw * 8 + (size_t)(ivf ? w_eff : 1) * 40 + 16 + 15) & ~(size_t)15) +
                         (pool_bytes ? (pool_bytes + 15) / 16 * 16 + 1040 : 0);  // coarse distances + selection histogram
     if (meta > (size_t)tb - 1280) return 0;  // the window starts at 1 KB + static shared memory (<= 256 B allowed for)
-    return (size_t)tb - 1024 + SK_LUT_BYTES + (size_t)nw * ring_stages * ST_BLOCK_BYTES;
+    return (size_t)tb - 1024 + (size_t)H * SK_LUT_BYTES + (size_t)nw * ring_stages * ST_BLOCK_BYTES;
 }

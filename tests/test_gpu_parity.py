@@ -555,3 +555,63 @@ def test_stream_fused_large_nlist(sk):
             exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
             n = int(f[2][b])
             assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "large nlist k=%d L=%d b=%d" % (topk, L, b))
+
+
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 1000, 40001, 300001])
+def test_stream_kernel_m64_linear(N):
+    """M = 64 on the v4 engine (two 64 KB tables, a row = two 32-byte half-row blocks): every tail / group-boundary
+    case against the natural-layout kernel and the oracle."""
+    D, M, Ks = 128, 64, 256
+    cw, codes, Q = synth(D, M, Ks, N, 3, seed=100 + N)
+    e = engine(cw, codes)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 10, 224):
+            if topk > N:
+                continue
+            e.set_option("scan_kernel", 4)
+            r4 = e.query_linear(q, topk, EMPTY)
+            e.set_option("scan_kernel", 1)
+            r1 = e.query_linear(q, topk, EMPTY)
+            assert r1 == r4, (N, topk)
+            assert_same_result(r4[0], np.array(r4[1], np.float32), *O.query_linear(T, codes, topk), "m64 N=%d k=%d" % (N, topk))
+    if N >= 10:
+        e.set_option("scan_kernel", 4)
+        bi, bd, bc = e.query_batch(np.ascontiguousarray(Q), 10, method="linear")
+        for b, q in enumerate(Q):
+            exp = O.query_linear(O.dtable(q, cw, 16), codes, 10)
+            assert_same_result(bi[b], bd[b], exp[0], exp[1], "m64 batch")
+
+
+def test_stream_kernel_m64_ivf():
+    """M = 64 posting-list scans on the v4 engine: unfused plans (few queries, several CTAs per query), fused
+    one-CTA-per-query batches with nlist <= 1024 (histogram select) and > 1024 (warp lists), Ds = 2 and Ds = 3."""
+    for D, nlist, N in [(128, 60, 70000), (192, 1100, 120000)]:
+        M, Ks = 64, 256
+        cw, codes, Q = synth(D, M, Ks, N, 150, seed=D)
+        e = engine(cw, codes)
+        e.reconfigure(nlist, 1)
+        centers = e.coarse_centers_array()
+        offsets, ids = e.posting_lists_csr()
+        for q in Q[:3]:
+            T = O.dtable(q, cw, 16)
+            for topk, L in [(1, 1), (3, 255), (10, 2049), (50, 33333), (96, N)]:
+                exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
+                e.set_option("scan_kernel", 4)
+                try:
+                    r4 = e.query_ivf(q, topk, EMPTY, L)
+                except Exception:  # w > 224 lists: not a v4 shape when forced
+                    e.set_option("scan_kernel", 0)
+                    r4 = e.query_ivf(q, topk, EMPTY, L)
+                assert_same_result(r4[0], np.array(r4[1], np.float32), exp[0], exp[1], "m64 ivf D=%d k=%d L=%d" % (D, topk, L))
+        Qb = np.ascontiguousarray(Q)
+        for topk, L in [(1, 400), (7, 3000), (20, 12345)]:
+            e.set_option("scan_kernel", 4)
+            f = e.query_batch(Qb, topk, L=L, method="ivf")
+            e.set_option("scan_kernel", 1)
+            u = e.query_batch(Qb, topk, L=L, method="ivf")
+            assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1])), (D, topk, L)
+            for b in range(0, 150, 37):
+                exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
+                n = int(f[2][b])
+                assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "m64 fused D=%d k=%d L=%d b=%d" % (D, topk, L, b))
