@@ -129,8 +129,26 @@ int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
 int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_dists, const int32_t *d_counts, int G,
                          int B, int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream);
 
-/* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout scan, 2 = skewed bank-conflict-free scan
- * (M == 32, no target_ids, topk <= 224).  Results are identical for every setting. */
+/* IVF + target_ids on an id-range shard (the binary_search filter of src/rii.h:294 with the ids spread over shards):
+ * the cut after L filtered candidates needs every shard's per-list member counts -- one small exchange.
+ *   w_eff = rii_ivf_subset_width(...)                       lists ranked per query (full != 0: all nlist lists)
+ *   rii_ivf_subset_counts_dev(... d_counts (B, w_eff))      phase A: this shard's member counts per ranked list
+ *   [caller: all-gather of d_counts; d_counts_all = sum over shards, d_counts_lower = sum over lower ranks]
+ *   rii_ivf_subset_scan_dev(... d_counts_all, d_counts_lower ...)   phase B: plan with the global counts, scan this
+ *                                                           shard's members, per-shard top-k (then all-gather + merge)
+ * d_flags (B, may be NULL): bit 0 = fewer than topk members in the first w lists: re-run that query with full = 1
+ * (src/rii.h:309-322); bit 1 = empty result (src/rii.h:325).  Same handle, same queries, B <= 2048, device buffers. */
+int rii_ivf_subset_width(rii_index_t *h, int topk, int64_t S, int64_t L, int full);
+int rii_ivf_subset_counts_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids, int64_t S,
+                              int64_t L, int full, int32_t *d_counts, void *stream);
+int rii_ivf_subset_scan_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t S, int64_t L, int full,
+                            const int32_t *d_counts_all, const int32_t *d_counts_lower, int64_t *d_out_ids, float *d_out_dists,
+                            int32_t *d_out_counts, int32_t *d_flags, void *stream);
+
+/* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout scan (v1), 2 = skewed bank-conflict-free scan (v2), 3 = its
+ * dual-stream FFMA2 variant (v3), 4 = the skew64 streaming engine (v4; what auto picks for M == 32 / 64, no target_ids,
+ * topk <= 224).  "stream_ctas": 1 = v4 always one CTA per SM.  "fuse_coarse": 0 = separate coarse-ranking kernel.
+ * Results are identical for every setting. */
 int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 
 /* ---- measurement ------------------------------------------------------------------------------ */

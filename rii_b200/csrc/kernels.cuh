@@ -376,7 +376,9 @@ struct PlanArgs {
     const int *glob_len;   // (nlist) global (all-shard) list lengths       [no subset]
     const int *pre_len;    // (nlist) sum of lengths on lower ranks, or null (single shard)
     const int *loc_len;    // (nlist) local list lengths
-    const int *filt_cnt;   // (B, w_eff) filtered counts per ranked list, or null  [subset]
+    const int *filt_cnt;   // (B, w_eff) filtered counts per ranked list, or null  [subset]: all shards together
+    const int *filt_pre;   // (B, w_eff) [subset, sharded] members held by lower ranks, or null
+    const int *filt_loc;   // (B, w_eff) [subset, sharded] members held locally, or null
     long long L;
     int topk;
     int w;                 // the reference's w (src/rii.h:267-277)
@@ -495,7 +497,14 @@ __global__ void __launch_bounds__(RII_THREADS) k_coarse_rank(CoarseArgs a)
 __global__ void k_plan(PlanArgs p, int B)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) make_plan(p, b, p.filt_cnt + (size_t)b * p.w_eff, nullptr, nullptr);
+    if (b >= B) return;
+    const size_t o = (size_t)b * p.w_eff;
+    make_plan(p, b, p.filt_cnt + o, p.filt_pre ? p.filt_pre + o : nullptr, p.filt_loc ? p.filt_loc + o : nullptr);
+    // sharded subset: the cut of the last segment counts members in global id order; lower ranks hold the first ones
+    if (p.filt_pre && p.J[b] > 0) {
+        const int t = p.take_last[b] - p.filt_pre[o + p.J[b] - 1];
+        p.take_last[b] = t < 0 ? 0 : t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

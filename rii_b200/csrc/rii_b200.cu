@@ -549,8 +549,12 @@ struct QueryCfg {
     int method;
 };
 
+// phase (IVF + target_ids on a shard, SURVEY 8e "one exchange step"): 0 = the whole pipeline; 1 = stop after the
+// per-list member counts (left in h->filt, (B, w_eff)); 2 = resume from the plan with the all-shard counts `ext_glob` and
+// the lower ranks' counts `ext_pre` (both (B, w_eff) device int32)
 int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const long long *d_tids, long long *d_out_ids,
-              float *d_out_dists, int *d_out_counts, cudaStream_t st, int w, int w_eff, bool *checked_flags)
+              float *d_out_dists, int *d_out_counts, cudaStream_t st, int w, int w_eff, bool *checked_flags, int phase = 0,
+              const int *ext_glob = nullptr, const int *ext_pre = nullptr)
 {
     const int M = h->M, Ks = h->Ks, lutf = M * Ks;
     // K1: the v2 scan kernels and the coarse kernel build their tables in-kernel from (Q, codewords); only the
@@ -669,7 +673,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     p.take_last = h->take_last.as<int>();
     p.J = h->J.as<int>();
     p.flags = h->flags.as<int>();
-    if (subset) {
+    if (subset && phase != 2) {
         const size_t words = (size_t)(h->N + 31) / 32 + 1;
         CKR(h->bitmap.ensure(words * 4));
         CK(cudaMemsetAsync(h->bitmap.p, 0, words * 4, st));
@@ -708,7 +712,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             CKR(ensure_codes_list(h, st));
         }
     }
-    if (!fuse) {
+    if (!fuse && phase != 2) {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
         a.centers = h->centers.as<uint8_t>();
@@ -726,13 +730,19 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         CK(cudaGetLastError());
     }
     if (subset) {
-        {
+        if (phase != 2) {
             Prof pr(h, st, PK_COUNT);
             k_count_members<<<dim3(w_eff, B), RII_THREADS, 0, st>>>(h->offsets.as<long long>(), h->ids.as<int>(), p.ranked, w_eff,
                                                                       h->bitmap.as<uint32_t>(), h->filt.as<int>());
+            LAUNCHED();
         }
-        LAUNCHED();
-        p.filt_cnt = h->filt.as<int>();
+        if (phase == 1) {
+            CK(cudaGetLastError());
+            return 0;
+        }
+        p.filt_cnt = phase == 2 ? ext_glob : h->filt.as<int>();
+        p.filt_pre = phase == 2 ? ext_pre : nullptr;
+        p.filt_loc = phase == 2 ? h->filt.as<int>() : nullptr;
         {
             Prof pr(h, st, PK_PLAN);
             k_plan<<<(B + 127) / 128, 128, 0, st>>>(p, B);
@@ -839,7 +849,9 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
         // can sum of the first w ranked lists fall short of topk?  (only then the walk continues beyond w)
         may_flag = S != 0 || (w < h->nlist && h->len_sorted_prefix.size() > (size_t)w && h->len_sorted_prefix[w] < topk &&
                               h->len_sorted_prefix[w] < L);
-        if (S != 0 && h->has_global) return fail(RII_ERR_LIMIT, "IVF + target_ids on a sharded index is not implemented yet");
+        if (S != 0 && h->has_global)
+            return fail(RII_ERR_STATE, "IVF + target_ids on a shard needs the per-list counts of the other shards: use "
+                                       "rii_ivf_subset_counts_dev / rii_ivf_subset_scan_dev (rii_b200.sharded.sharded_query_subset)");
     } else if (method != RII_METHOD_LINEAR) {
         return fail(RII_ERR_ARG, "unknown method");
     }
@@ -1145,6 +1157,68 @@ int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
     std::iota(pick.begin(), pick.end(), 0);
     std::shuffle(pick.begin(), pick.end(), std::default_random_engine(123));
     for (long long i = 0; i < ns; ++i) out_ids[i] = (int64_t)pick[i];
+    return 0;
+}
+
+// ---- IVF + target_ids on an id-range shard (the one exchange step) -------------------------------
+// Phase A: coarse ranking + per-list member counts of THIS shard -> d_counts (B, w_eff) int32.  The caller all-gathers
+// the counts of all shards, sums them (global counts) and sums those of the lower ranks (pre counts), then calls
+// phase B on the same handle with the same queries.  full != 0 ranks all nlist lists (the re-run of queries whose plan
+// came back flagged 1: fewer than topk members in the first w lists).  B <= 2048.
+static int subset_w(rii_index *h, int topk, int64_t S, int64_t L, int full, int *w, int *w_eff)
+{
+    const long long Ntot = h->n_total();
+    if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
+    if (S <= 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 < len(target_ids) <= N");
+    if (topk < 1 || topk > S) return fail(RII_ERR_ARG, "need 1 <= topk <= len(target_ids)");
+    if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");
+    size_t ww = (size_t)std::round((double)L * h->nlist / (double)S) + 3;  // src/rii.h:267-277
+    if ((size_t)h->nlist < ww) ww = h->nlist;
+    *w = (int)ww;
+    *w_eff = full ? h->nlist : (int)ww;
+    return 0;
+}
+
+int rii_ivf_subset_width(rii_index_t *h, int topk, int64_t S, int64_t L, int full)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    int w = 0, w_eff = 0;
+    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
+    return w_eff;
+}
+
+int rii_ivf_subset_counts_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids, int64_t S,
+                              int64_t L, int full, int32_t *d_counts, void *stream)
+{
+    if (!h || !d_queries || !d_target_ids || !d_counts) return fail(RII_ERR_ARG, "null argument");
+    if (B < 1 || B > 2048) return fail(RII_ERR_ARG, "need 1 <= B <= 2048");
+    int w = 0, w_eff = 0;
+    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QueryCfg c{topk, S, L, RII_METHOD_IVF};
+    bool dummy;
+    CKR(run_chunk(h, d_queries, B, c, (const long long *)d_target_ids, nullptr, nullptr, nullptr, st, w, w_eff, &dummy, 1));
+    CK(cudaMemcpyAsync(d_counts, h->filt.p, (size_t)B * w_eff * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int rii_ivf_subset_scan_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t S, int64_t L, int full,
+                            const int32_t *d_counts_all, const int32_t *d_counts_lower, int64_t *d_out_ids, float *d_out_dists,
+                            int32_t *d_out_counts, int32_t *d_flags, void *stream)
+{
+    if (!h || !d_queries || !d_counts_all || !d_counts_lower || !d_out_ids || !d_out_dists || !d_out_counts)
+        return fail(RII_ERR_ARG, "null argument");
+    if (B < 1 || B > 2048) return fail(RII_ERR_ARG, "need 1 <= B <= 2048");
+    int w = 0, w_eff = 0;
+    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QueryCfg c{topk, S, L, RII_METHOD_IVF};
+    bool dummy;
+    CKR(run_chunk(h, d_queries, B, c, nullptr, (long long *)d_out_ids, d_out_dists, d_out_counts, st, w, w_eff, &dummy, 2,
+                  d_counts_all, d_counts_lower));
+    if (d_flags) CK(cudaMemcpyAsync(d_flags, h->flags.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -133,6 +133,48 @@ def sharded_query(engine, Q, topk, L, method, dist, world):
     return engine.merge(g_ids, g_d, g_c)
 
 
+def sharded_query_subset(engine, Q, topk, L, tids, dist, world, rank):
+    """IVF + target_ids on id-range shards (the one exchange step; src/rii.h:286-322 with the
+    binary_search filter of :294).  Phase A: every shard counts, per ranked list, its own members of `tids`;
+    all-gather of the (B, w) counts; phase B: every shard plans with the global counts (the cut after L filtered
+    candidates and the topk test at the w-th list are global), scans its own members and returns its top-k;
+    all-gather + merge as for any sharded query.  Queries whose plan is flagged (fewer than topk members in the first w
+    lists: the reference walks on through ALL lists) are re-run with the full ranking.
+    `tids`: sorted global int64 ids (a tensor on the engine's device).  <= 2048 queries per call."""
+    import torch
+
+    def one_round(Qr, full):
+        cnt = engine.subset_counts(Qr, topk, tids, L, full)               # (B, w_eff) int32, this shard
+        if world > 1:
+            g = torch.empty((world,) + tuple(cnt.shape), dtype=cnt.dtype, device=cnt.device)
+            dist.all_gather_into_tensor(g.view(-1), cnt.contiguous().view(-1))
+        else:
+            g = cnt[None]
+        glob = g.sum(0, dtype=torch.int32)
+        pre = g[:rank].sum(0, dtype=torch.int32) if rank > 0 else torch.zeros_like(cnt)
+        ids, d, c, flags = engine.subset_scan(Qr, topk, tids, L, full, glob.contiguous(), pre.contiguous())
+        if world > 1:
+            B, k = ids.shape
+            g_ids = torch.empty((world, B, k), dtype=ids.dtype, device=ids.device)
+            g_d = torch.empty((world, B, k), dtype=d.dtype, device=d.device)
+            g_c = torch.empty((world, B), dtype=c.dtype, device=c.device)
+            dist.all_gather_into_tensor(g_ids.view(-1), ids.contiguous().view(-1))
+            dist.all_gather_into_tensor(g_d.view(-1), d.contiguous().view(-1))
+            dist.all_gather_into_tensor(g_c.view(-1), c.contiguous().view(-1))
+            ids, d, c = engine.merge(g_ids, g_d, g_c)
+        return ids, d, c, flags
+
+    ids, d, c, flags = one_round(Q, 0)
+    redo = torch.nonzero(flags & 1).flatten()      # the plan is global: the same queries on every rank
+    if redo.numel():
+        i2, d2, c2, _ = one_round(Q[redo].contiguous(), 1)
+        ids[redo], d[redo], c[redo] = i2, d2, c2
+    empty = torch.nonzero((flags & 2) != 0).flatten()
+    if empty.numel():
+        c[empty] = 0
+    return ids, d, c
+
+
 def _cuda_query_local(self, Q, topk, L, method):
     import torch
     B = Q.shape[0]
@@ -160,5 +202,34 @@ def _cuda_merge(self, g_ids, g_d, g_c):
     return ids, d, c
 
 
+def _cuda_subset_counts(self, Q, topk, tids, L, full):
+    import torch
+    B, S = Q.shape[0], tids.numel()
+    w = self.lib.rii_ivf_subset_width(self.e._h, topk, S, int(L), int(full))
+    self.check(w)
+    cnt = torch.empty((B, w), dtype=torch.int32, device=Q.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    self.check(self.lib.rii_ivf_subset_counts_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, C.c_void_p(tids.data_ptr()), S,
+                                                  int(L), int(full), C.c_void_p(cnt.data_ptr()), st))
+    return cnt
+
+
+def _cuda_subset_scan(self, Q, topk, tids, L, full, glob, pre):
+    import torch
+    B, dev = Q.shape[0], Q.device
+    ids = torch.empty((B, topk), dtype=torch.int64, device=dev)
+    d = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    c = torch.empty((B,), dtype=torch.int32, device=dev)
+    flags = torch.empty((B,), dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    self.check(self.lib.rii_ivf_subset_scan_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, tids.numel(), int(L), int(full),
+                                                C.c_void_p(glob.data_ptr()), C.c_void_p(pre.data_ptr()),
+                                                C.c_void_p(ids.data_ptr()), C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()),
+                                                C.c_void_p(flags.data_ptr()), st))
+    return ids, d, c, flags
+
+
 CudaShardEngine.query_local = _cuda_query_local
+CudaShardEngine.subset_counts = _cuda_subset_counts
+CudaShardEngine.subset_scan = _cuda_subset_scan
 CudaShardEngine.merge = _cuda_merge

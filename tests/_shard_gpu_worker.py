@@ -40,9 +40,25 @@ def run():
             assert n == len(exp[0]), (method, topk, L, n, len(exp[0]))
             assert np.array_equal(gi[b, :n], exp[0]), (method, topk, L, gi[b, :n][:5], exp[0][:5])
             assert np.array_equal(gd[b, :n].view(np.uint32), exp[1].view(np.uint32)), (method, topk, L)
+    # IVF + target_ids across shards (two-phase C ABI): uniform subsets and one concentrated in far lists (flagged re-run)
+    rng = np.random.default_rng(5)
+    far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), oc))[-5:]
+    far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+    for tids, topk, L in [(np.sort(rng.choice(N, 20000, replace=False)).astype(np.int64), 10, 3200),
+                          (np.sort(rng.choice(N, 3000, replace=False)).astype(np.int64), 1, 3000),
+                          (far_ids, 3, 40)]:
+        gi, gd, gc = sharded.sharded_query_subset(eng, Qd, topk, L, torch.from_numpy(tids).to(dev), dist, world, rank)
+        torch.cuda.synchronize()
+        gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+        for b, q in enumerate(Q):
+            exp = O.query_ivf(O.dtable(q, cw, 16), codes, oc, offsets, ids, topk, L, tids)
+            n = int(gc[b])
+            assert n == len(exp[0]), ("subset", topk, L, n, len(exp[0]))
+            assert np.array_equal(gi[b, :n], exp[0]), ("subset", topk, L, gi[b, :n][:5], exp[0][:5])
+            assert np.array_equal(gd[b, :n].view(np.uint32), exp[1].view(np.uint32)), ("subset", topk, L)
     dist.barrier()
     if rank == 0:
-        print("sharded GPU parity ok: world=%d" % world)
+        print("sharded GPU parity ok (linear, ivf, ivf + target_ids): world=%d" % world)
     dist.destroy_process_group()
 
 

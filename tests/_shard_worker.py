@@ -81,6 +81,58 @@ class OracleShardEngine(object):
             return None
         return np.concatenate(cand).astype(np.int64) if cand else np.zeros(0, np.int64)
 
+    # ---- IVF + target_ids, two phases (restated in numpy independently of the CUDA pipeline) ----
+    def _rank_lists(self, q, topk, S, L, full):
+        nlist = self.centers.shape[0]
+        T = O.dtable(q, self.cw, 16)
+        cd = O.adist_all(T, self.centers)
+        order = np.lexsort((np.arange(nlist), cd))
+        w = min(int(np.floor(L * nlist / S + 0.5)) + 3, nlist)
+        return T, order[: (nlist if full else w)], w
+
+    def subset_counts(self, Q, topk, tids, L, full):
+        t = tids.numpy() - self.lo
+        member = np.zeros(len(self.codes), bool)
+        member[t[(t >= 0) & (t < len(self.codes))]] = True
+        self._member = member
+        out = []
+        for q in Q.numpy():
+            _, order, _ = self._rank_lists(q, topk, len(tids), L, full)
+            out.append([int(member[self.ids[self.offsets[no]:self.offsets[no + 1]]].sum()) for no in order])
+        return torch.tensor(out, dtype=torch.int32)
+
+    def subset_scan(self, Q, topk, tids, L, full, glob, pre):
+        B = Q.shape[0]
+        ids = np.full((B, topk), -1, np.int64)
+        d = np.full((B, topk), np.inf, np.float32)
+        c = np.zeros(B, np.int32)
+        flags = np.zeros(B, np.int32)
+        nlist = self.centers.shape[0]
+        for b, q in enumerate(Q.numpy()):
+            T, order, w = self._rank_lists(q, topk, len(tids), L, full)
+            P, cand, done = 0, [], False
+            for j, no in enumerate(order):
+                f = int(glob[b, j])
+                take = f
+                if P + f >= L:
+                    take, done = L - P, True
+                P += take
+                mem = self.ids[self.offsets[no]:self.offsets[no + 1]]
+                mem = mem[self._member[mem]]
+                lt = int(np.clip(take - int(pre[b, j]), 0, len(mem)))
+                cand.append(mem[:lt])
+                if done or (j == w - 1 and P >= topk):
+                    done = True
+                    break
+            if not done:
+                flags[b] = 2 if len(order) >= nlist else 1
+                continue
+            cand = np.concatenate(cand).astype(np.int64) if cand else np.zeros(0, np.int64)
+            dd = O.adist_all(T, self.codes[cand]) if len(cand) else np.zeros(0, np.float32)
+            o = np.lexsort((cand, dd))[:topk]
+            ids[b, :len(o)], d[b, :len(o)], c[b] = cand[o] + self.lo, dd[o], len(o)
+        return torch.from_numpy(ids), torch.from_numpy(d), torch.from_numpy(c), torch.from_numpy(flags)
+
     def merge(self, g_ids, g_d, g_c):
         G, B, k = g_ids.shape
         ids = torch.full((B, k), -1, dtype=torch.int64)
@@ -129,6 +181,20 @@ def main():
             n = int(gc[bq])
             assert n == len(exp[0]), (method, topk, L, n, len(exp[0]))
             assert np.array_equal(gi[bq, :n].numpy(), exp[0]) and np.array_equal(gd[bq, :n].numpy().view(np.uint32), exp[1].view(np.uint32)), (method, topk, L)
+    # IVF + target_ids across shards: uniform subset, a subset concentrated in few lists far from the queries (walk
+    # beyond w -> flagged re-run with the full ranking), and one where L is never reached (empty result)
+    rng = np.random.default_rng(5)
+    far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), centers))[-4:]
+    far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+    for tids, topk, L in [(np.sort(rng.choice(N, 900, replace=False)).astype(np.int64), 5, 300),
+                          (np.sort(rng.choice(N, 900, replace=False)).astype(np.int64), 1, 900),
+                          (far_ids, 3, 20), (far_ids[:6], 5, 6)]:
+        gi, gd, gc = sharded.sharded_query_subset(eng, Qt, topk, L, torch.from_numpy(tids), dist, world, rank)
+        for bq, q in enumerate(Q):
+            exp = O.query_ivf(O.dtable(q, cw, 16), codes, centers, offsets, ids, topk, L, tids)
+            n = int(gc[bq])
+            assert n == len(exp[0]), ("subset", topk, L, n, len(exp[0]))
+            assert np.array_equal(gi[bq, :n].numpy(), exp[0]) and np.array_equal(gd[bq, :n].numpy().view(np.uint32), exp[1].view(np.uint32)), ("subset", topk, L)
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok" % rank)

@@ -615,3 +615,32 @@ def test_stream_kernel_m64_ivf():
                 exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
                 n = int(f[2][b])
                 assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "m64 fused D=%d k=%d L=%d b=%d" % (D, topk, L, b))
+
+
+def test_two_phase_subset_api_single_shard():
+    """rii_ivf_subset_counts_dev / rii_ivf_subset_scan_dev (the sharded IVF + target_ids path) with one shard must equal
+    the ordinary query_ivf(target_ids): uniform subset, subset concentrated in far lists (flagged -> full ranking)."""
+    import torch
+    from rii_b200 import sharded
+    D, M, Ks, N, nlist = 128, 32, 256, 60000, 60
+    cw, codes, Q = synth(D, M, Ks, N, 6, seed=77)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    eng = sharded.CudaShardEngine(e)
+    dev = torch.device("cuda", 0)
+    Qd = torch.from_numpy(Q).to(dev)
+    rng = np.random.default_rng(3)
+    far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), centers))[-4:]
+    far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+    for tids, topk, L in [(np.sort(rng.choice(N, 6000, replace=False)).astype(np.int64), 10, 1000), (far_ids, 3, 30)]:
+        gi, gd, gc = sharded.sharded_query_subset(eng, Qd, topk, L, torch.from_numpy(tids).to(dev), None, 1, 0)
+        torch.cuda.synchronize()
+        gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+        for b, q in enumerate(Q):
+            exp = O.query_ivf(O.dtable(q, cw, 16), codes, centers, offsets, ids, topk, L, tids)
+            n = int(gc[b])
+            assert_same_result(gi[b, :n], gd[b, :n], exp[0], exp[1], "two-phase subset k=%d L=%d b=%d" % (topk, L, b))
+            one = e.query_ivf(q, topk, tids, L)
+            assert one[0] == gi[b, :n].tolist()
