@@ -314,7 +314,7 @@ def run_ours(args):
     # kernel streams a list-ordered (skew64) code copy and reads ids only for survivors; the nlist*M center bytes of
     # the fused coarse pass are not counted either (3 % of C*M at C2).
     frac_scanned = 1.0 / world if shard else 1.0
-    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 2048 queries
+    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 8192 queries
     alg = q_per_launch * (L * frac_scanned * M + 4 * M * CFG["Ks"])
     launch_ms = scan_ms.value / max(scan_n.value, 1)
     achieved = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
@@ -428,7 +428,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="queries per step")
+    ap.add_argument("--batch", type=int, default=32768, help="queries per step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--linear-n", type=int, default=64000000,
                     help="also time the HBM-bound linear scan over this many random codes (0 = skip); 1 GPU only")
