@@ -242,7 +242,8 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
         const uint32_t dsel_ = H == 1 ? dsc[((S) + ST_D) % ST_R] : dsc[S];                                    \
         ST_ISSUE(((S) + ST_D) % ST_R, dsc[((S) + ST_D) % ST_R], m + (S) + ST_D < nblk)                        \
         if constexpr (ST_D == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");                         \
-        else asm volatile("cp.async.wait_group 2;" ::: "memory");                                             \
+        else if constexpr (ST_D == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");                    \
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");                                             \
         uint32_t wx_[8], wy_[8];                                                                              \
         ST_LDS128(wx_, ring + (S) * ST_BLOCK_BYTES);                                                          \
         ST_LDS128(wx_ + 4, ring + (S) * ST_BLOCK_BYTES + 512);                                                \
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     else set_range(gridDim.x, blockIdx.x);
     // the first ST_D blocks go out before the table is built
     ST_ISSUE(0, dsc[0], 0 < nblk)
-    ST_ISSUE(1, dsc[1], 1 < nblk)
+    if constexpr (ST_D >= 2) ST_ISSUE(1 % ST_R, dsc[1 % ST_R], 1 < nblk)
     if constexpr (ST_D == 3) ST_ISSUE(2 % ST_R, dsc[2 % ST_R], 2 < nblk)
 
     int bad = 0;
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 #pragma unroll
             for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
             ST_ISSUE(0, dsc[0], 0 < nblk)
-            ST_ISSUE(1, dsc[1], 1 < nblk)
+            if constexpr (ST_D >= 2) ST_ISSUE(1 % ST_R, dsc[1 % ST_R], 1 < nblk)
             if constexpr (ST_D == 3) ST_ISSUE(2 % ST_R, dsc[2 % ST_R], 2 < nblk)
         }
 
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 if constexpr (!IVF) thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
                 ST_STAGE(0)
                 ST_STAGE(1)
-                ST_STAGE(2)
+                if constexpr (ST_R >= 3) { ST_STAGE(2 % ST_R) }
                 if constexpr (ST_R == 4) { ST_STAGE(3 % ST_R) }
             }
         }
