@@ -402,12 +402,26 @@ int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, c
 int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id (linear scan, scan_stream.cuh)
 {
     if (h->skew_lin_rows == h->N) return 0;
-    const long long prows = skew64_rows(h->N, h->M / 32);
-    CKR(h->skew_lin.ensure((size_t)prows * 32));
+    const int H = h->M / 32;
+    const long long prows = skew64_rows(h->N, H);
+    // rows appended since the last build only change the windows from the first incomplete group on: keep the rest
+    long long keep = h->skew_lin_rows > 0 && h->skew_lin_rows < h->N ? (h->skew_lin_rows / 64) * H * 64 : 0;
+    if ((size_t)prows * 32 > h->skew_lin.cap) {
+        DevBuf nb;
+        CKR(nb.ensure((size_t)prows * 32));  // (DevBuf over-allocates by 25 %: amortises a stream of adds)
+        if (keep) CK(cudaMemcpyAsync(nb.p, h->skew_lin.p, (size_t)keep * 32, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        h->skew_lin.release();
+        h->skew_lin = nb;
+    }
     CKR(h->skew_misc_off.ensure(32));
     const long long off[2] = {0, prows};
     CK(cudaMemcpyAsync(h->skew_misc_off.p, off, 16, cudaMemcpyHostToDevice, st));
-    CKR(skew_build(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N, prows, h->skew_lin.as<uint8_t>(), h->M, st));
+    const long long thr = (prows - keep) * 2;
+    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N,
+                                                                  keep, prows, h->skew_lin.as<uint8_t>(), h->M);
+    LAUNCHED();
+    CK(cudaGetLastError());
     h->skew_lin_rows = h->N;
     return 0;
 }
@@ -983,8 +997,7 @@ int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_fl
     CKR(grow_codes(h, N0 + n));
     if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->N = N0 + n;
-    h->skew_lin_rows = -1;
+    h->N = N0 + n;  // (skew_lin_rows keeps the row count of the last build: the next linear query extends the copy)
     if (h->verbose) printf("%lld new vectors are added.\nTotal number of codes is %lld\n", (long long)n, h->N);
     if (update_flag) {
         if (h->verbose) printf("Start to update posting lists\n");

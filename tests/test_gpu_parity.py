@@ -644,3 +644,22 @@ def test_two_phase_subset_api_single_shard():
             assert_same_result(gi[b, :n], gd[b, :n], exp[0], exp[1], "two-phase subset k=%d L=%d b=%d" % (topk, L, b))
             one = e.query_ivf(q, topk, tids, L)
             assert one[0] == gi[b, :n].tolist()
+
+
+@pytest.mark.parametrize("M", [32, 64])
+def test_stream_kernel_incremental_adds(M):
+    """A stream of add() calls interleaved with linear queries: the skew64 copy is extended from the first incomplete
+    group of 64 rows on (not rebuilt), and every query must see exactly the codes added so far."""
+    D, Ks = 128, 256
+    cw, codes, Q = synth(D, M, Ks, 5000, 2, seed=M)
+    e = engine(cw)
+    e.set_option("scan_kernel", 4)
+    n = 0
+    for step in (1, 62, 1, 1, 64, 127, 500, 3, 1000, 2241, 1000):
+        e.add_codes(codes[n:n + step], False)
+        n += step
+        for q in Q:
+            k = min(5, n)
+            r = e.query_linear(q, k, EMPTY)
+            assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(O.dtable(q, cw, 16), codes[:n], k), "after %d rows" % n)
+    assert n == 5000
