@@ -480,11 +480,13 @@ template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H>
 int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
 {
     auto kern = k_scan_stream32<NW, IVF, R, MINB, TB, H>;
-    static bool configured = false;  // per process and instantiation
-    if (!configured) {
+    static bool configured[64] = {false};  // function attributes are per device: once per (instantiation, device)
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_DYN_SMEM));
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     a.smem_bytes = (uint32_t)smem;
     kern<<<dim3(parts, B), NW * 32, smem, st>>>(a);
