@@ -1,4 +1,4 @@
-"""Multi-GPU parity worker (run under torchrun on a box with >= 2 GPUs; tools/gpu_multi.sh):
+"""Multi-GPU parity worker (run under torchrun on a box with >= 2 GPUs; tools/gpu_multi2.sh):
 id-range sharded index over NCCL == unsharded oracle, for linear and IVF batches."""
 import os
 import sys
