@@ -335,7 +335,7 @@ def run_ours(args):
     # kernel streams a list-ordered (skew64) code copy and reads ids only for survivors; the nlist*M center bytes of
     # the fused coarse pass are not counted either (3 % of C*M at C2).
     frac_scanned = 1.0 / world if shard else 1.0
-    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 8192 queries
+    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 32768 queries
     alg = q_per_launch * (L * frac_scanned * M + 4 * M * CFG["Ks"])
     launch_ms = scan_ms.value / max(scan_n.value, 1)
     achieved = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
@@ -371,7 +371,10 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_sample(cw, codes, Q)
     try:  # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (tools/ncu_summary.py)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        line["roofline"]["traffic"] = tr.get("k_scan_stream32_ivf_2cta_bytes_per_launch")
+        # (captured on a launch of 8192 queries; DRAM traffic of this L2-resident workload is per query: scale to the
+        # queries one launch of this run processes)
+        t_ivf, q_ivf = tr.get("k_scan_stream32_ivf_2cta_bytes_per_launch"), tr.get("k_scan_stream32_ivf_2cta_queries_per_launch", 8192)
+        line["roofline"]["traffic"] = None if t_ivf is None else int(t_ivf * q_per_launch / q_ivf)
         line["roofline"]["traffic_source"] = tr.get("source")
         if lin is not None and "achieved" in lin:
             lin["traffic"] = tr.get("k_scan_stream32_linear_N64M_bytes_per_launch") if int(args.linear_n) == 64000000 else None

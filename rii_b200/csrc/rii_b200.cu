@@ -872,7 +872,7 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
         return fail(RII_ERR_ARG, "unknown method");
     }
     const int D = h->M * h->Ds;
-    const int CH = 8192;  // queries per launch: long grids keep the tail (last partial wave of CTAs) small
+    const int CH = 32768;  // queries per launch: long grids keep the tail (last partial wave of CTAs) small
     for (int b0 = 0; b0 < B; b0 += CH) {
         const int bc = std::min(CH, B - b0);
         bool ran_ivf = false;
