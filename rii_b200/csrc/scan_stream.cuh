@@ -37,7 +37,7 @@
 #define ST_TB1 0x10000u
 #define ST_TB2 0x3000u
 #define ST_TB3 0x6000u
-#define ST_TABLE_LIMIT 1e37f        // 32 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
+#define ST_TABLE_LIMIT 5e36f        // 64 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
 
 // 32-byte windows of a skew64 segment holding `len` code rows of M = 32 H bytes: H blocks of 64 windows per group of 64
 // rows, plus H blocks after the last group (the first one holds the lagging tail of the last rows; with H = 2 the
