@@ -98,3 +98,104 @@ def test_skew64_is_a_permutation_of_the_codes_plus_padding():
     stream = w[:, s, :].reshape(-1)[lag:lag + rows.size]
     assert np.array_equal(stream, rows.reshape(-1))
     assert int(w.astype(np.int64).sum()) == int(codes.astype(np.int64).sum())   # everything else is zero padding
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The walk over SEVERAL segments by several warps (the ST_ISSUE / ST_STAGE logic of k_scan_stream32): flattened groups
+# split into contiguous warp ranges, H blocks per group, H drain blocks at the end of a segment or of a range, the
+# group's descriptor (flattened group, row-valid bits) travelling with its first block and used when the rows complete.
+def issue_blocks(segs_groups, takes, f0, f_end, H):
+    """Block sequence of one warp: list of (segment, block in segment, descriptor or None)."""
+    gcum = np.cumsum(segs_groups)
+    seg = int(np.searchsorted(gcum, f0, side="right"))
+    out, cur_f, hb, drain_left = [], f0, 0, 0
+    g0 = lambda j: int(gcum[j - 1]) if j else 0
+    while True:
+        g = cur_f - g0(seg)
+        if drain_left == 0:
+            if cur_f >= f_end:
+                break
+            dsc = (cur_f, seg, g) if hb == 0 else None
+            out.append((seg, g * H + hb, dsc))
+            hb += 1
+            if hb == H:
+                hb = 0
+                cur_f += 1
+                if cur_f == f_end or cur_f == gcum[seg]:
+                    drain_left = H
+        else:
+            out.append((seg, g * H + (H - drain_left), None))
+            drain_left -= 1
+            if drain_left == 0:
+                if cur_f < f_end:
+                    seg += 1
+                else:
+                    break
+    return out
+
+
+def walk_segments(seg_windows, takes, T, M, nwarps):
+    H, Ks, f32 = M // 32, T.shape[1], np.float32
+    tab = np.zeros((H, Ks, 64), f32)
+    for h in range(H):
+        for c in range(64):
+            tab[h, :, c] = T[(32 * h + c - 32) % M]
+    lanes = np.arange(32)
+    groups = [(t + 63) // 64 for t in takes]
+    Gtot = sum(groups)
+    per = (Gtot + nwarps - 1) // nwarps
+    got = {}
+    for w in range(nwarps):
+        f0, f_end = min(w * per, Gtot), min((w + 1) * per, Gtot)
+        if f_end <= f0:
+            continue
+        blocks = issue_blocks(groups, takes, f0, f_end, H)
+        assert len(blocks) % H == 0
+        acc, out = np.zeros((2, 32), f32), np.zeros((2, 32), f32)
+        d_last = None
+        for pos, (seg, blk, dsc) in enumerate(blocks):
+            h = pos % H
+            assert h == blk % H, "a block's half-row index must equal its pipeline-stage parity"
+            win = seg_windows[seg][blk]
+            for t in range(32):
+                col = t + 32 - lanes
+                for y in range(2):
+                    v = tab[h, win[32 * y + lanes, t], col]
+                    if h == 0:
+                        out[y] = (acc[y] * (lanes == t) + out[y]).astype(f32)
+                        acc[y] = (acc[y] * (lanes != t) + v).astype(f32)
+                    else:
+                        acc[y] = (acc[y] + v).astype(f32)
+            if h == 0:
+                if d_last is not None:
+                    _, s2, g2 = d_last
+                    for y in range(2):
+                        for l in range(32):
+                            r = 64 * g2 + 32 * y + l
+                            if r < takes[s2]:
+                                assert (s2, r) not in got, "a candidate was emitted twice"
+                                got[(s2, r)] = out[y][l]
+                out[:] = 0
+                d_last = dsc
+    return got
+
+
+@pytest.mark.parametrize("M,nwarps", [(32, 1), (32, 6), (32, 12), (64, 3), (64, 8)])
+def test_segment_walk_emits_every_candidate_once_with_the_exact_distance(M, nwarps):
+    D, Ks = 4 * M, 256
+    rng = np.random.default_rng(M + nwarps)
+    lens = [1, 64, 65, 130, 7, 200, 64, 333]
+    takes = [1, 64, 65, 100, 7, 129, 10, 333]          # whole lists and lists cut mid-way (the plan's last segment)
+    cw, codes, Q = synth(D, M, Ks, sum(lens), 1, seed=3 * M + nwarps)
+    T = O.dtable(Q[0], cw, 16).reshape(M, Ks)
+    seg_codes, o = [], 0
+    for n in lens:
+        seg_codes.append(codes[o:o + n])
+        o += n
+    seg_windows = [skew64_build(c) for c in seg_codes]
+    got = walk_segments(seg_windows, takes, T, M, nwarps)
+    assert len(got) == sum(takes)
+    for s, (c, take) in enumerate(zip(seg_codes, takes)):
+        exp = O.adist_all(T, c[:take])
+        g = np.array([got[(s, r)] for r in range(take)], np.float32)
+        assert np.array_equal(bits(g), bits(exp)), "segment %d" % s
