@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             for (int mh = 0; mh < H; ++mh) {
                 const int m = mh * 32 + lane;
                 const float *qm = a.Q + (size_t)b * M * a.Ds + (size_t)m * a.Ds;
-                if (a.Ds == 4 && a.Ks == 256) {  // 16 independent 16-byte loads in flight per lane
+                if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {  // 16 independent 16-byte loads in flight per lane
                     const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
                     const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
