@@ -10,6 +10,9 @@
 // libstdc++ shuffles that define the reconfigure sampling, src/rii.h:120-124, src/pqkmeans.cpp:177-191).
 #include "../../include/rii_b200.h"
 #include "kernels.cuh"
+#include "launch.h"
+#include "skew64_build.cuh"
+#include "warp_topk.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -88,6 +91,9 @@ int host_l2_variant()
 
 }  // namespace
 
+int rii_fail(int code, const std::string &msg) { return fail(code, msg); }
+void rii_count_launch() { LAUNCHED(); }
+
 enum { PK_DTABLE = 0, PK_SCAN_LINEAR, PK_MERGE, PK_COARSE, PK_COUNT, PK_PLAN, PK_SCAN_IVF, PK_ASSIGN, PK_N };
 static const char *PK_NAMES[PK_N] = {"dtable", "scan_linear", "merge", "coarse_rank", "count_members", "plan",
                                       "scan_ivf", "assign"};
@@ -112,8 +118,6 @@ struct rii_index {
     float *d_Dm = nullptr;
     uint8_t *d_codes = nullptr;
     DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
-    DevBuf codes_list;  // (N, 32) list-ordered copy of the codes (row p <-> ids[p]); M == 32, v2 / v3 engines only (lazy)
-    bool codes_list_valid = false;
     // skew64 copies (scan_stream.cuh; M == 32, built lazily on the query stream): the codes by id, every local posting
     // list (segment i at physical row skew_off[i]) and the coarse centers
     DevBuf skew_lin, skew_lists, skew_off, centers_skew, skew_misc_off;
@@ -253,8 +257,7 @@ int upload_lists(rii_index *h)
     std::vector<int> len(nlist);
     for (int i = 0; i < nlist; ++i) len[i] = (int)(h->h_offsets[i + 1] - h->h_offsets[i]);
     if (nlist) CK(cudaMemcpyAsync(h->loc_len.p, len.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, h->stream));
-    h->codes_list_valid = false;  // derived copies are rebuilt lazily by the first query that needs them
-    h->skew_lists_valid = false;
+    h->skew_lists_valid = false;  // derived copies are rebuilt lazily by the first query that needs them
     CK(cudaStreamSynchronize(h->stream));
     if (!h->has_global) {
         std::sort(len.begin(), len.end());
@@ -376,18 +379,6 @@ int grow_codes(rii_index *h, long long rows)
 }
 
 // ---- derived code layouts (M == 32), built lazily on the query stream ------------------------------------
-int ensure_codes_list(rii_index *h, cudaStream_t st)  // list-ordered copy for the v2 / v3 posting-list scans
-{
-    if (h->codes_list_valid || h->h_ids.empty()) return 0;
-    const long long n = (long long)h->h_ids.size();
-    CKR(h->codes_list.ensure((size_t)n * 32));
-    k_gather_rows32_by_list<<<(unsigned)((n * 2 + 255) / 256), 256, 0, st>>>(h->d_codes, h->ids.as<int>(), n, h->codes_list.as<uint8_t>());
-    LAUNCHED();
-    CK(cudaGetLastError());
-    h->codes_list_valid = true;
-    return 0;
-}
-
 int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
                long long prows, uint8_t *out, int M, cudaStream_t st)
 {
@@ -455,109 +446,6 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
     return 0;
 }
 
-// ---- v4 (skew64 streaming) scan launcher ------------------------------------------------------------------
-// shapes: 1 = one CTA per SM (12 warps, 4-stage rings, table at 0x10000); 2 = two CTAs per SM (6 warps, 3-stage rings,
-// table at 0x3000); 3 = M = 64 (8 warps, 4-stage rings, two tables at 0x6000, one CTA per SM);
-// returns the shape that fits (0: none) and its warps / dynamic shared memory
-int stream_pick(const rii_index *h, bool ivf, bool per_query_batch, int capw, int w_eff, size_t pool_bytes, int *nw, size_t *smem)
-{
-    if (h->M == 64) {
-        const size_t b = stream_smem_bytes(ivf, 8, 4, ST_TB3, capw, w_eff, pool_bytes, 2);
-        if (b && b <= SK_DYN_SMEM) { *nw = 8; *smem = b; return 3; }
-        return 0;
-    }
-    const bool want2 = ivf && per_query_batch && h->opt_stream_ctas != 1;
-    if (want2) {
-        const size_t b = stream_smem_bytes(true, 6, 3, ST_TB2, capw, w_eff, pool_bytes);
-        if (b && b <= 113 * 1024) { *nw = 6; *smem = b; return 2; }
-    }
-    const size_t b = stream_smem_bytes(ivf, 12, 4, ST_TB1, capw, w_eff, pool_bytes);
-    if (b && b <= SK_DYN_SMEM) { *nw = 12; *smem = b; return 1; }
-    return 0;
-}
-
-template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H>
-int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
-{
-    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB, H>;
-    static bool configured[64] = {false};  // function attributes are per device: once per (instantiation, device)
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_DYN_SMEM));
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    a.smem_bytes = (uint32_t)smem;
-    kern<<<dim3(parts, B), NW * 32, smem, st>>>(a);
-    return 0;
-}
-
-int launch_stream(int shape, bool ivf, const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
-{
-    if (shape == 3) return ivf ? launch_stream_t<8, true, 4, 1, ST_TB3, 2>(a, parts, B, smem, st)
-                               : launch_stream_t<8, false, 4, 1, ST_TB3, 2>(a, parts, B, smem, st);
-    if (shape == 2) return launch_stream_t<6, true, 3, 2, ST_TB2, 1>(a, parts, B, smem, st);
-    if (ivf) return launch_stream_t<12, true, 4, 1, ST_TB1, 1>(a, parts, B, smem, st);
-    return launch_stream_t<12, false, 4, 1, ST_TB1, 1>(a, parts, B, smem, st);
-}
-
-// ---- v2 (skewed) scan launcher: the most warps per SM whose shared-memory footprint fits ---------------
-int skew_pick_nw(bool ivf, int capw, int w_eff)
-{
-    for (int nw : {16, 14, 12})
-        if (skew_regions_fit(ivf, nw, capw, w_eff) >= nw) return nw;
-    return 0;
-}
-
-template <int NW, bool IVF> int launch_skew_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
-{
-    CKR(set_smem(k_scan_skew32<NW, IVF>, smem));
-    k_scan_skew32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
-    return 0;
-}
-
-// ---- v3 (dual-stream FFMA2) scan launcher -------------------------------------------------------------
-int dual_pick_nw(bool ivf, int capw, int w_eff)
-{
-    for (int nw : {11, 10, 8})
-        if (dual_regions_fit(ivf, nw, capw, w_eff) >= nw) return nw;
-    return 0;
-}
-
-template <int NW, bool IVF> int launch_dual_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
-{
-    CKR(set_smem(k_scan_dual32<NW, IVF>, smem));
-    k_scan_dual32<NW, IVF><<<dim3(parts, B), NW * 32, smem, st>>>(a);
-    return 0;
-}
-
-int launch_dual(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
-{
-    const size_t smem = SK_DYN_SMEM;
-    if (ivf) {
-        if (nw == 11) return launch_dual_t<11, true>(a, parts, B, smem, st);
-        if (nw == 10) return launch_dual_t<10, true>(a, parts, B, smem, st);
-        return launch_dual_t<8, true>(a, parts, B, smem, st);
-    }
-    if (nw == 11) return launch_dual_t<11, false>(a, parts, B, smem, st);
-    if (nw == 10) return launch_dual_t<10, false>(a, parts, B, smem, st);
-    return launch_dual_t<8, false>(a, parts, B, smem, st);
-}
-
-int launch_skew(int nw, bool ivf, const SkewArgs &a, int parts, int B, cudaStream_t st)
-{
-    const size_t smem = SK_DYN_SMEM;
-    if (ivf) {
-        if (nw == 16) return launch_skew_t<16, true>(a, parts, B, smem, st);
-        if (nw == 14) return launch_skew_t<14, true>(a, parts, B, smem, st);
-        return launch_skew_t<12, true>(a, parts, B, smem, st);
-    }
-    if (nw == 16) return launch_skew_t<16, false>(a, parts, B, smem, st);
-    if (nw == 14) return launch_skew_t<14, false>(a, parts, B, smem, st);
-    return launch_skew_t<12, false>(a, parts, B, smem, st);
-}
-
 // ---- the query pipeline on device buffers -----------------------------------------------------------
 struct QueryCfg {
     int topk;
@@ -616,14 +504,12 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         const size_t smem = scan_smem_bytes(lutf, cap, 0);
         // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
         const int capw = std::max(64, next_pow2(c.topk + 32));
-        const int eng = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;  // v4 unless v2 / v3 is asked for
         int nw = 0, shape = 0;
         size_t smem4 = 0;
-        if (eng == 4) shape = stream_pick(h, false, false, capw, 0, 0, &nw, &smem4);
-        else nw = eng == 3 ? dual_pick_nw(false, capw, 0) : skew_pick_nw(false, capw, 0);
-        const bool v2_ok = (M == 32 || (M == 64 && eng == 4)) && c.S == 0 && c.topk <= SK_MAX_K && nw > 0;
-        const bool use_v2 = v2_ok && (h->opt_scan_kernel >= 2 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
-        if (h->opt_scan_kernel >= 2 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 needs M == 32, no target_ids and topk <= 224");
+        if (M == 32 || M == 64) shape = stream_pick(M, false, false, capw, 0, 0, &nw, &smem4);
+        const bool v2_ok = shape > 0 && c.S == 0 && c.topk <= SK_MAX_K;
+        const bool use_v2 = v2_ok && (h->opt_scan_kernel == 4 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
+        if (h->opt_scan_kernel == 4 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=4 needs M == 32 / 64, no target_ids and topk <= 224");
         if (use_v2) {
             parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                              std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
@@ -637,13 +523,10 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
             sa.smem_bytes = SK_DYN_SMEM;
-            if (eng == 4) {
-                CKR(ensure_skew_lin(h, st));
-                sa.codes = h->skew_lin.as<uint8_t>();
-            }
+            CKR(ensure_skew_lin(h, st));
+            sa.codes = h->skew_lin.as<uint8_t>();
             Prof pr(h, st, PK_SCAN_LINEAR);
-            CKR(eng == 4 ? launch_stream(shape, false, sa, parts, B, smem4, st)
-                         : eng == 3 ? launch_dual(nw, false, sa, parts, B, st) : launch_skew(nw, false, sa, parts, B, st));
+            CKR(launch_stream(shape, false, sa, parts, B, smem4, st));
         } else {
             CKR(ensure_T());
             a.T = h->T.as<float>();
@@ -652,9 +535,9 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 CKR(set_smem(k_scan_linear<MT>, smem));
                 k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
             });
+            LAUNCHED();
+            CK(cudaGetLastError());
         }
-        LAUNCHED();
-        CK(cudaGetLastError());
         if (!out.final) {
             const int mcap = next_pow2(c.topk + RII_THREADS);
             const size_t msmem = scan_smem_bytes(0, mcap, 0);
@@ -702,31 +585,23 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     // same kernel (two passes of one engine): no k_coarse_rank launch at all.
     // (v4 with nlist > 1024 ranks the centers in the warps' top-k lists: they must hold max(topk, w_eff) keys)
     const bool big_nlist = h->nlist > 1024;
-    const bool eng4_req = !(h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3);
-    const int capw2 = std::max(64, next_pow2((eng4_req && big_nlist ? std::max(c.topk, w_eff) : c.topk) + 32));
-    const int eng2 = h->opt_scan_kernel == 2 || h->opt_scan_kernel == 3 ? h->opt_scan_kernel : 4;
+    const int capw2 = std::max(64, next_pow2((big_nlist ? std::max(c.topk, w_eff) : c.topk) + 32));
     int nw2 = 0, shape2 = 0;
     size_t smem42 = 0;
     // (the fused coarse pass keeps nlist distances in shared memory: sized for it whenever fusing is possible)
     const size_t pool4 = h->opt_fuse_coarse && !big_nlist ? (size_t)h->nlist * 4 : 0;
-    if (eng2 == 4) shape2 = stream_pick(h, true, B >= 148, capw2, w_eff, pool4, &nw2, &smem42);
-    else nw2 = eng2 == 3 ? dual_pick_nw(true, capw2, w_eff) : skew_pick_nw(true, capw2, w_eff);
-    const bool v2_ok = (M == 32 || (M == 64 && eng2 == 4)) && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && nw2 > 0 && !h->h_ids.empty();
+    if (M == 32 || M == 64) shape2 = stream_pick(M, true, B >= 148 && h->opt_stream_ctas != 1, capw2, w_eff, pool4, &nw2, &smem42);
+    const bool v2_ok = shape2 > 0 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && !h->h_ids.empty();
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-    if (h->opt_scan_kernel >= 2 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=2/3/4 (ivf) needs M == 32, topk <= 224 and a short list plan");
+    if (h->opt_scan_kernel == 4 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=4 (ivf) needs M == 32 / 64, topk <= 224 and a short list plan");
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
     // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse &&
-                      (eng2 == 4 || (!big_nlist && (size_t)h->nlist * 4 <= (size_t)nw2 * capw2 * 8));
+    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse;
     if (use_v2) {
-        if (eng2 == 4) {
-            CKR(ensure_skew_lists(h, st));
-            if (fuse) CKR(ensure_centers_skew(h, st));
-        } else {
-            CKR(ensure_codes_list(h, st));
-        }
+        CKR(ensure_skew_lists(h, st));
+        if (fuse) CKR(ensure_centers_skew(h, st));
     }
     if (!fuse && phase != 2) {
         CoarseArgs a{};
@@ -792,14 +667,11 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 out.partial = h->partial.as<u64>();
             }
             sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
-            sa.codes = h->codes_list.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
+            sa.codes = h->skew_lists.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
             if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
-            if (eng2 == 4) {
-                sa.codes = h->skew_lists.as<uint8_t>();
-                sa.skew_off = h->skew_off.as<long long>();
-                if (fuse) { sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; }
-            }
+            sa.skew_off = h->skew_off.as<long long>();
+            if (fuse) { sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; }
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         }
         if (!use_v2) {
@@ -810,8 +682,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         Prof pr(h, st, PK_SCAN_IVF);
         if (use_v2) {
             sa.smem_bytes = SK_DYN_SMEM;
-            CKR(eng2 == 4 ? launch_stream(shape2, true, sa, parts, B, smem42, st)
-                          : eng2 == 3 ? launch_dual(nw2, true, sa, parts, B, st) : launch_skew(nw2, true, sa, parts, B, st));
+            CKR(launch_stream(shape2, true, sa, parts, B, smem42, st));
         } else if (subset) {
             const size_t smem = scan_smem_bytes(lutf, cap, 64);
             DISPATCH_M(M, {
@@ -826,7 +697,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
             });
         }
         }
-        LAUNCHED();
+        if (!use_v2) LAUNCHED();
         CK(cudaGetLastError());
         if (!out.final) {
             const int mcap = next_pow2(c.topk + RII_THREADS);
@@ -974,7 +845,7 @@ int rii_destroy(rii_index_t *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->codes_list, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
+    for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
         b->release();
@@ -1054,7 +925,7 @@ int rii_clear(rii_index_t *h)
     h->N = 0;
     h->nlist = 0;
     h->skew_lin_rows = -1;
-    h->skew_lists_valid = h->centers_skew_valid = h->codes_list_valid = false;
+    h->skew_lists_valid = h->centers_skew_valid = false;
     h->h_centers.clear();
     h->h_offsets.assign(1, 0);
     h->h_ids.clear();
@@ -1107,8 +978,8 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
         return 0;
     }
     if (!strcmp(name, "scan_kernel")) {
-        if (value < 0 || value > 4)
-            return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural layout), 2 (skewed), 3 (dual-stream skewed) or 4 (register streaming)");
+        if (value != 0 && value != 1 && value != 4)
+            return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural-layout kernels) or 4 (skew64 streaming engine)");
         h->opt_scan_kernel = (int)value;
         return 0;
     }

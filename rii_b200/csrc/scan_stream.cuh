@@ -26,6 +26,8 @@
 // count are masked when their distance completes.
 // ===================================================================================================
 #pragma once
+#include "common.cuh"
+#include "warp_topk.cuh"
 
 #define ST_BLOCK_BYTES 2048         // 64 windows of 32 bytes
 // Launch shapes (template parameters NW warps, R ring stages = R - 1 blocks in flight, MINB CTAs per SM, TB = absolute
@@ -39,47 +41,7 @@
 #define ST_TB3 0x6000u
 #define ST_TABLE_LIMIT 5e36f        // 64 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
 
-// 32-byte windows of a skew64 segment holding `len` code rows of M = 32 H bytes: H blocks of 64 windows per group of 64
-// rows, plus H blocks after the last group (the first one holds the lagging tail of the last rows; with H = 2 the
-// second keeps every segment an even number of blocks, so that a block's half-row index stays a compile-time constant
-// of the pipeline stage)
-static __host__ __device__ inline long long skew64_rows(long long len, int H = 1) { return 64 * ((len + 63) / 64 + 1) * H; }
-
-// Build (a range of) skew64 segments.  codes: (rows, 32) by id; ids / offsets: CSR of the segments (null: ONE segment
-// = rows [0, n_single) in id order); skew_off: (nseg + 1) first physical row (32-byte unit) of every segment, a
-// multiple of 64.  One thread per 16-byte chunk.
-__global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__restrict__ ids, const long long *__restrict__ offsets,
-                               const long long *__restrict__ skew_off, int nseg, long long n_single, long long prow0,
-                               long long prow1, uint8_t *__restrict__ out, int M)
-{
-    const long long i = prow0 * 2 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the table
-    const long long prow = i >> 1;
-    if (prow >= prow1) return;
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (skew_off[mid] <= prow) lo = mid; else hi = mid - 1;
-    }
-    const long long c16 = i - skew_off[lo] * 2;  // chunk within the segment: block b, quarter q, lane l
-    const long long b = c16 >> 7;
-    const int q = (int)(c16 >> 5) & 3, l = (int)(c16 & 31);
-    const int s = (q >> 1) * 32 + l, half = q & 1, lag = l;
-    const long long len = offsets ? offsets[lo + 1] - offsets[lo] : n_single;
-    const long long ioff = offsets ? offsets[lo] : 0;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const long long x = 32 * b - lag + 16 * half + j;  // byte of stream s
-        if (x >= 0) {
-            const long long r = 64 * (x / M) + s;          // row of the segment
-            if (r < len) {
-                const long long id = ids ? (long long)ids[ioff + r] : r;
-                w[j >> 2] |= (uint32_t)__ldg(codes + id * M + (x % M)) << (8 * (j & 3));
-            }
-        }
-    }
-    reinterpret_cast<uint4 *>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
-}
+#include "skew64.cuh"
 
 // The candidate plan of make_plan (kernels.cuh; SURVEY Appendix A.3, src/rii.h:286-322) computed by ONE WARP with prefix
 // scans instead of a serial walk, fused with the compaction into the stream engine's segment list.  Inputs by rank j <

@@ -315,10 +315,10 @@ def _assign_of(offsets, ids, N):
 
 
 # ---------------------------------------------------------------- scan kernel v2 (skewed) --------------
-# v2: k_scan_skew32 (one stream per lane, predicated adds); v3: k_scan_dual32 (two streams, FFMA2, 3-stage cp.async ring);
-# v4: k_scan_stream32 (two streams, FFMA2, pre-skewed skew64 layout through private cp.async rings); 401 = always one
-# CTA per SM (12 warps) instead of two CTAs of 6 warps for per-query IVF batches
-SKEW_KERNELS = [2, 3, 4, 401]
+# 4: k_scan_stream32 (two streams per lane, FFMA2, pre-skewed skew64 layout through private cp.async rings); 401 = always
+# one CTA per SM (12 warps) instead of two CTAs of 6 warps for per-query IVF batches.  (The earlier skewed engines v2 / v3
+# were removed in round 2.)
+SKEW_KERNELS = [4, 401]
 
 
 def set_kernel(e, sk):
@@ -376,13 +376,9 @@ def test_skew_kernel_large_n_vs_v1():
         r1 = e.query_linear(q, 100, EMPTY)
         e.set_option("scan_kernel", 0)  # auto -> v4 at this size
         r0 = e.query_linear(q, 100, EMPTY)
-        e.set_option("scan_kernel", 3)
-        r3 = e.query_linear(q, 100, EMPTY)
         e.set_option("scan_kernel", 4)
-        r4 = e.query_linear(q, 100, EMPTY)
-        e.set_option("scan_kernel", 2)
         r2 = e.query_linear(q, 100, EMPTY)
-        assert r1 == r2 == r0 == r3 == r4
+        assert r1 == r2 == r0
     T = O.dtable(Q[0], cw, 16)
     assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(O.dtable(Q[2], cw, 16), codes, 100), "5M")
 
@@ -468,7 +464,7 @@ def test_fused_coarse_plan_scan_equals_unfused(sk):
     e.set_option("fuse_coarse", 1)
 
 
-@pytest.mark.parametrize("sk", [3, 4])
+@pytest.mark.parametrize("sk", [4])
 def test_dual_kernel_huge_tables_take_the_plain_path(sk):
     """k_scan_dual32 / k_scan_stream32 accumulate with acc * {0,1} + v, which needs finite partial sums; a distance table with huge /
     inf entries (queries ~1e19 away from the codewords) must be detected in-kernel and scanned by the plain
