@@ -18,6 +18,7 @@ SYMBOLS = {
     "rii_create": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rii_destroy": (C.c_int, [_vp]),
     "rii_add_codes": (C.c_int, [_vp, _u8p, C.c_int64, C.c_int]),
+    "rii_add_codes_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
     "rii_reconfigure": (C.c_int, [_vp, C.c_int, C.c_int]),
     "rii_clear": (C.c_int, [_vp]),
     "rii_query_linear": (C.c_int64, [_vp, _f32p, C.c_int, _i64p, C.c_int64, _i64p, _f32p]),

@@ -180,6 +180,7 @@ struct SkewArgs {
     const float *cw;           // (32, Ks, Ds)
     const float *cw_t;         // (Ks, 32, Ds): the same codewords, sub-space fastest (coalesced in-kernel table build)
     int Ds, variant;
+    int M;                     // sub-spaces (the engine pads rows to 32 or 64 bytes)
     const uint8_t *codes;      // linear: (N, 32) by id.  IVF: (N, 32) list-ordered copy (row p <-> ids[p])
     long long N;               // linear: rows of the shard
     const long long *offsets;  // IVF: CSR

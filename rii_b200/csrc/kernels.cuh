@@ -648,11 +648,11 @@ __global__ void k_vote_hist(const uint8_t *__restrict__ codes, const int *__rest
 
 // sparse voting, src/pqkmeans.cpp:235-258: vote[k2] = sum over k1 (ascending, freq != 0) of
 // (float)freq * Dm[m][k1][k2] (mul then add), argmin with strict '<' from FLT_MAX.
-// grid (M, K), Ks <= 256 threads.  Empty clusters keep their center (src/pqkmeans.cpp:115-120).
+// grid (K, M), Ks <= 256 threads.  Empty clusters keep their center (src/pqkmeans.cpp:115-120).
 __global__ void __launch_bounds__(256) k_vote_centers(const float *__restrict__ Dm, const int *__restrict__ hist,
                                                       int M, int Ks, uint8_t *centers)
 {
-    const int m = blockIdx.x, k = blockIdx.y, k2 = threadIdx.x;
+    const int k = blockIdx.x, m = blockIdx.y, k2 = threadIdx.x;
     __shared__ int s_hist[256];
     __shared__ float s_vote[256];
     __shared__ int s_total;

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "launch.h"
 #include "skew64_build.cuh"
+#include "build_kernels.cuh"
 #include "warp_topk.cuh"
 
 #include <algorithm>
@@ -108,6 +109,7 @@ struct rii_index {
     double prof_ms[PK_N] = {0};
     long long prof_n[PK_N] = {0};
     int M = 0, Ks = 0, Ds = 0, variant = 16, verbose = 0, device = 0;
+    int rb = 0;  // bytes of a (zero-padded) code row on the streaming engine: 32 (12 <= M <= 32), 64 (32 < M <= 64), 0: natural-layout kernels only
     long long N = 0, cap_rows = 0;      // local rows
     long long id_base = 0, N_total = -1;  // sharding (N_total < 0: single shard, N_total = N)
     int nlist = 0;
@@ -127,7 +129,12 @@ struct rii_index {
 
     std::vector<uint8_t> h_centers;      // (nlist, M)
     std::vector<long long> h_offsets;    // (nlist+1)
-    std::vector<int> h_ids;              // (N) local ids grouped by list
+    DevBuf assign;                       // (N) list of every row (kept for subset searches: sub-index build)
+    long long N_assigned = 0;            // rows of `assign` that are valid
+    DevBuf ws_best, ws_arg, d_flag;      // assignment engine workspaces; d_flag: [0] Dm max bits, [2] engine flag
+    bool dm_ok = true;                   // every Dm entry is small enough for the packed accumulation
+    SortTmp sort_tmp;
+    bool shard_stale = false;            // rows were added to / removed from a shard: rii_set_shard must be called again
     std::vector<long long> len_sorted_prefix;  // prefix sums of ascending *global* list lengths
 
     // scratch (grow only)
@@ -138,6 +145,7 @@ struct rii_index {
     int opt_debug_clocks = 0;
     int opt_stream_ctas = 0;  // v4 engine: 1 = always one CTA per SM; otherwise per-query IVF batches run two CTAs per SM
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
+    int opt_assign_kernel = 0;  // 0 auto (streaming engine, two CTAs per SM), 1 natural-layout k_assign, 3 streaming engine with one CTA per SM
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
                               // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
                               // when it applies).  v2 / v3 / v4: M == 32 only
@@ -202,20 +210,77 @@ template <class F> int set_smem(F *kernel, size_t bytes)
 int ensure_Dm(rii_index *h)
 {
     if (h->d_Dm) return 0;
-    CK(cudaMalloc(&h->d_Dm, (size_t)h->M * h->Ks * h->Ks * sizeof(float)));
+    const size_t nDm = (size_t)h->M * h->Ks * h->Ks;
+    CK(cudaMalloc(&h->d_Dm, nDm * sizeof(float)));
     dim3 grid((h->Ks * h->Ks + RII_THREADS - 1) / RII_THREADS, h->M);
     k_symmat<<<grid, RII_THREADS, 0, h->stream>>>(h->d_cw, h->d_Dm, h->Ks, h->Ds);
     LAUNCHED();
     CK(cudaGetLastError());
+    // the packed accumulation of the streaming engine needs finite partial sums (scan_stream.cuh ST_TABLE_LIMIT)
+    CKR(h->d_flag.ensure(16));
+    CK(cudaMemsetAsync(h->d_flag.p, 0, 16, h->stream));
+    k_max_bits<<<296, 256, 0, h->stream>>>(h->d_Dm, (long long)nDm, h->d_flag.as<unsigned int>());
+    LAUNCHED();
+    unsigned int mx = 0;
+    CK(cudaMemcpyAsync(&mx, h->d_flag.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float lim = 5e36f;
+    unsigned int lim_bits;
+    std::memcpy(&lim_bits, &lim, 4);
+    h->dm_ok = mx <= lim_bits;
     return 0;
 }
 
-// K6 launcher: d_codes (n, M) device, d_centers (K, M) device -> d_assign (n) [, d_dist (n)]
-int launch_assign(rii_index *h, const uint8_t *d_codes, long long n, const uint8_t *d_centers, int K, int *d_assign,
-                  float *d_dist)
+// Rows to assign: natural layout (n, M) and, for the streaming engine, their skew64 copy (one segment).
+struct AssignSrc {
+    const uint8_t *natural = nullptr;
+    const uint8_t *skew = nullptr;  // null: natural-layout kernel only
+    long long n = 0;
+};
+
+int ensure_skew_lin(rii_index *h, cudaStream_t st);
+int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
+               long long prows, uint8_t *out, int M, int RB, cudaStream_t st);
+
+// skew64 copy of n natural-layout rows into `buf` (reused across the iterations of a fit)
+int make_assign_src(rii_index *h, const uint8_t *d_rows, long long n, DevBuf *buf, AssignSrc *out)
 {
+    out->natural = d_rows;
+    out->n = n;
+    out->skew = nullptr;
+    CKR(ensure_Dm(h));
+    if (!h->rb || !h->dm_ok || h->opt_assign_kernel == 1 || n <= 0) return 0;
+    if (d_rows == h->d_codes && n == h->N) {  // the whole index: the linear scan's copy
+        CKR(ensure_skew_lin(h, h->stream));
+        out->skew = h->skew_lin.as<uint8_t>();
+        return 0;
+    }
+    const long long prows = skew64_rows(n, h->rb / 32);
+    CKR(buf->ensure((size_t)prows * 32 + 32));
+    long long *off = reinterpret_cast<long long *>(buf->as<uint8_t>() + (size_t)prows * 32);
+    const long long hoff[2] = {0, prows};
+    CK(cudaMemcpyAsync(off, hoff, 16, cudaMemcpyHostToDevice, h->stream));
+    CKR(skew_build(d_rows, nullptr, nullptr, off, 1, n, prows, buf->as<uint8_t>(), h->M, h->rb, h->stream));
+    out->skew = buf->as<uint8_t>();
+    return 0;
+}
+
+// K6 launcher: rows `src`, d_centers (K, M) device -> d_assign (n) [, d_dist (n)]
+int launch_assign(rii_index *h, const AssignSrc &src, const uint8_t *d_centers, int K, int *d_assign, float *d_dist)
+{
+    const long long n = src.n;
     if (n == 0) return 0;
     CKR(ensure_Dm(h));
+    Prof pr(h, h->stream, PK_ASSIGN);
+    if (src.skew) {  // streaming engine (assign_stream.cuh)
+        const AssignPlan pl = assign_stream_plan(n, K, h->rb, h->opt_assign_kernel == 3 ? 1 : 0);
+        CKR(h->ws_best.ensure((size_t)pl.groups * pl.n_pad * 4));
+        CKR(h->ws_arg.ensure((size_t)pl.groups * pl.n_pad * 4));
+        CKR(h->d_flag.ensure(16));
+        return launch_assign_stream(pl, h->d_Dm, d_centers, K, h->M, h->Ks, src.skew, n, h->ws_best.as<float>(), h->ws_arg.as<int>(),
+                                    h->d_flag.as<int>() + 2, d_assign, d_dist, h->stream);
+    }
+    const uint8_t *d_codes = src.natural;
     const size_t lut1 = (size_t)h->M * h->Ks * sizeof(float);
     int G = 0, CPT = 4;
     for (int g : {4, 2, 1}) {
@@ -228,7 +293,6 @@ int launch_assign(rii_index *h, const uint8_t *d_codes, long long n, const uint8
     const int tile = RII_THREADS * CPT;
     const size_t smem = lut1 * G + (size_t)tile * h->M;
     const unsigned grid = (unsigned)((n + tile - 1) / tile);
-    Prof pr(h, h->stream, PK_ASSIGN);
 #define LAUNCH_ASSIGN(GG, CC)                                                                                        \
     do {                                                                                                             \
         CKR(set_smem(k_assign<GG, CC>, smem));                                                                       \
@@ -245,56 +309,90 @@ int launch_assign(rii_index *h, const uint8_t *d_codes, long long n, const uint8
     return 0;
 }
 
-int upload_lists(rii_index *h)
+// Publish the host-side offsets: device copies of the offsets and lengths, derived layouts invalidated.
+int finish_lists(rii_index *h)
 {
     const int nlist = h->nlist;
     CKR(h->offsets.ensure((size_t)(nlist + 1) * 8));
-    CKR(h->ids.ensure(std::max<size_t>(4, h->h_ids.size() * 4)));
     CKR(h->loc_len.ensure((size_t)std::max(1, nlist) * 4));
     CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    if (!h->h_ids.empty())
-        CK(cudaMemcpyAsync(h->ids.p, h->h_ids.data(), h->h_ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
     std::vector<int> len(nlist);
     for (int i = 0; i < nlist; ++i) len[i] = (int)(h->h_offsets[i + 1] - h->h_offsets[i]);
     if (nlist) CK(cudaMemcpyAsync(h->loc_len.p, len.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, h->stream));
     h->skew_lists_valid = false;  // derived copies are rebuilt lazily by the first query that needs them
     CK(cudaStreamSynchronize(h->stream));
-    if (!h->has_global) {
-        std::sort(len.begin(), len.end());
-        h->len_sorted_prefix.assign(nlist + 1, 0);
-        for (int i = 0; i < nlist; ++i) h->len_sorted_prefix[i + 1] = h->len_sorted_prefix[i] + len[i];
-    }
+    h->has_global = false;  // a shard must exchange its lengths again (rii_set_global_lengths)
+    std::sort(len.begin(), len.end());
+    h->len_sorted_prefix.assign(nlist + 1, 0);
+    for (int i = 0; i < nlist; ++i) h->len_sorted_prefix[i + 1] = h->len_sorted_prefix[i] + len[i];
     return 0;
 }
 
-// src/rii.h:335-359 UpdatePostingLists(start, num): assign on the GPU, append ids in ascending order.
+int grow_assign(rii_index *h, long long rows)
+{
+    if ((size_t)rows * 4 <= h->assign.cap) return 0;
+    DevBuf nb;
+    CKR(nb.ensure((size_t)std::max(rows, h->cap_rows) * 4));
+    if (h->assign.p && h->N_assigned > 0)
+        CK(cudaMemcpyAsync(nb.p, h->assign.p, (size_t)h->N_assigned * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->assign.release();
+    h->assign = nb;
+    return 0;
+}
+
+// src/rii.h:335-359 UpdatePostingLists(start, num): assign rows [start, start + num) on the GPU and append their ids to
+// the lists, all on the device: a stable radix sort of the (list, id) pairs keeps every list ascending in id (new ids
+// are larger than every id already listed), the per-list segments are merged behind the old lists.
 int update_posting_lists(rii_index *h, long long start, long long num)
 {
-    if (num <= 0) return upload_lists(h);
-    CKR(h->tmp0.ensure((size_t)num * 4));
-    CKR(launch_assign(h, h->d_codes + start * h->M, num, h->centers.as<uint8_t>(), h->nlist, h->tmp0.as<int>(), nullptr));
-    std::vector<int> assign(num);
-    CK(cudaMemcpyAsync(assign.data(), h->tmp0.p, (size_t)num * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (num <= 0) return finish_lists(h);
     const int nlist = h->nlist;
-    std::vector<long long> add(nlist, 0);
-    for (long long n = 0; n < num; ++n) {
-        if (assign[n] < 0 || assign[n] >= nlist) return fail(RII_ERR_CUDA, "assignment kernel produced an invalid list id");
-        add[assign[n]]++;
+    CKR(grow_assign(h, start + num));
+    int *d_new = h->assign.as<int>() + start;
+    {
+        AssignSrc src;
+        DevBuf tmp_skew;
+        int rc = make_assign_src(h, h->d_codes + start * h->M, num, &tmp_skew, &src);
+        if (rc == 0) rc = launch_assign(h, src, h->centers.as<uint8_t>(), nlist, d_new, nullptr);
+        if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(RII_ERR_CUDA, "assignment failed");
+        tmp_skew.release();
+        CKR(rc);
     }
+    h->N_assigned = start + num;
+    // (list, id) pairs sorted by list
+    CKR(h->tmp0.ensure((size_t)num * 4));  // ids in
+    CKR(h->tmp1.ensure((size_t)num * 4));  // lists out
+    CKR(h->tmp2.ensure((size_t)num * 4));  // ids out
+    CKR(h->tmp3.ensure((size_t)(nlist + 2) * 8 * 2));  // bounds of the new ids per list | new offsets
+    k_iota_u32<<<(unsigned)((num + 255) / 256), 256, 0, h->stream>>>(h->tmp0.as<uint32_t>(), num, (uint32_t)start);
+    LAUNCHED();
+    int bits = 1;
+    while ((1ll << bits) <= nlist) ++bits;  // keys 0..nlist-1 and the invalid marker -1 (all ones) sort correctly on `bits` bits
+    CKR(dev_sort_pairs_u32(reinterpret_cast<const uint32_t *>(d_new), h->tmp1.as<uint32_t>(), h->tmp0.as<uint32_t>(), h->tmp2.as<uint32_t>(),
+                           num, bits, &h->sort_tmp, h->stream));
+    long long *d_bounds = h->tmp3.as<long long>(), *d_noff = d_bounds + nlist + 2;
+    k_list_bounds<<<(nlist + 1 + 255) / 256, 256, 0, h->stream>>>(h->tmp1.as<uint32_t>(), num, nlist, d_bounds);
+    LAUNCHED();
+    std::vector<long long> bounds(nlist + 1);
+    CK(cudaMemcpyAsync(bounds.data(), d_bounds, (size_t)(nlist + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (bounds[nlist] != num) return fail(RII_ERR_CUDA, "assignment kernel produced an invalid list id");
     std::vector<long long> noff(nlist + 1, 0);
-    for (int i = 0; i < nlist; ++i) noff[i + 1] = noff[i] + (h->h_offsets[i + 1] - h->h_offsets[i]) + add[i];
-    std::vector<int> nids((size_t)noff[nlist]);
-    std::vector<long long> cur(nlist);
-    for (int i = 0; i < nlist; ++i) {
-        long long len = h->h_offsets[i + 1] - h->h_offsets[i];
-        if (len) std::memcpy(&nids[noff[i]], &h->h_ids[h->h_offsets[i]], (size_t)len * 4);
-        cur[i] = noff[i] + len;
-    }
-    for (long long n = 0; n < num; ++n) nids[cur[assign[n]]++] = (int)(start + n);
+    for (int i = 0; i < nlist; ++i) noff[i + 1] = noff[i] + (h->h_offsets[i + 1] - h->h_offsets[i]) + (bounds[i + 1] - bounds[i]);
+    const long long old_total = h->h_offsets[nlist];
+    DevBuf nids;
+    CKR(nids.ensure(std::max<size_t>(4, (size_t)noff[nlist] * 4)));
+    CK(cudaMemcpyAsync(d_noff, noff.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    k_merge_lists<<<nlist, 256, 0, h->stream>>>(old_total ? h->offsets.as<long long>() : nullptr, h->ids.as<int>(), d_bounds,
+                                               h->tmp2.as<uint32_t>(), d_noff, nids.as<int>());
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->ids.release();
+    h->ids = nids;
     h->h_offsets.swap(noff);
-    h->h_ids.swap(nids);
-    return upload_lists(h);
+    return finish_lists(h);
 }
 
 int set_centers(rii_index *h, const uint8_t *centers_host, int nlist)
@@ -305,7 +403,7 @@ int set_centers(rii_index *h, const uint8_t *centers_host, int nlist)
     CKR(h->centers.ensure((size_t)nlist * h->M));
     CK(cudaMemcpyAsync(h->centers.p, h->h_centers.data(), (size_t)nlist * h->M, cudaMemcpyHostToDevice, h->stream));
     h->h_offsets.assign(nlist + 1, 0);
-    h->h_ids.clear();
+    h->N_assigned = 0;
     h->has_global = false;
     return 0;
 }
@@ -335,23 +433,29 @@ int fit_coarse(rii_index *h, const uint8_t *d_sample, long long ns, int nlist, i
         LAUNCHED();
         CK(cudaGetLastError());
     }
-    DevBuf assign, hist;
+    DevBuf assign, hist, skew_tmp;
+    AssignSrc src;
     int rc = 0;
     do {
+        if ((rc = make_assign_src(h, d_sample, ns, &skew_tmp, &src)) < 0) break;
         if ((rc = assign.ensure((size_t)ns * 4)) < 0) break;
         if (iter > 1 && (rc = hist.ensure((size_t)nlist * M * Ks * 4)) < 0) break;
         for (int itr = 0; itr < iter; ++itr) {
             if (h->verbose) printf("Iteration start: %d / %d\n", itr, iter);
-            cudaMemcpyAsync(h->tmp3.p, h->tmp2.p, (size_t)nlist * M, cudaMemcpyDeviceToDevice, h->stream);
-            if ((rc = launch_assign(h, d_sample, ns, h->tmp3.as<uint8_t>(), nlist, assign.as<int>(), nullptr)) < 0) break;
+            cudaError_t ce = cudaMemcpyAsync(h->tmp3.p, h->tmp2.p, (size_t)nlist * M, cudaMemcpyDeviceToDevice, h->stream);
+            if (ce != cudaSuccess) { rc = fail(RII_ERR_CUDA, std::string("fit_coarse: ") + cudaGetErrorString(ce)); break; }
+            if ((rc = launch_assign(h, src, h->tmp3.as<uint8_t>(), nlist, assign.as<int>(), nullptr)) < 0) break;
             if (itr != iter - 1) {  // src/pqkmeans.cpp:110
-                cudaMemsetAsync(hist.p, 0, (size_t)nlist * M * Ks * 4, h->stream);
+                ce = cudaMemsetAsync(hist.p, 0, (size_t)nlist * M * Ks * 4, h->stream);
                 long long tot = ns * M;
                 k_vote_hist<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(d_sample, assign.as<int>(), ns, M, Ks,
                                                                                 hist.as<int>());
                 LAUNCHED();
-                k_vote_centers<<<dim3(M, nlist), 256, 0, h->stream>>>(h->d_Dm, hist.as<int>(), M, Ks, h->tmp2.as<uint8_t>());
+                if (ce == cudaSuccess) ce = cudaGetLastError();
+                k_vote_centers<<<dim3(nlist, M), 256, 0, h->stream>>>(h->d_Dm, hist.as<int>(), M, Ks, h->tmp2.as<uint8_t>());
                 LAUNCHED();
+                if (ce == cudaSuccess) ce = cudaGetLastError();
+                if (ce != cudaSuccess) { rc = fail(RII_ERR_CUDA, std::string("fit_coarse: ") + cudaGetErrorString(ce)); break; }
             }
         }
         if (rc < 0) break;
@@ -359,8 +463,10 @@ int fit_coarse(rii_index *h, const uint8_t *d_sample, long long ns, int nlist, i
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(RII_ERR_CUDA, std::string("fit_coarse: ") + cudaGetErrorString(e));
     } while (0);
+    if (rc < 0) cudaStreamSynchronize(h->stream);
     assign.release();
     hist.release();
+    skew_tmp.release();
     return rc;
 }
 
@@ -380,11 +486,11 @@ int grow_codes(rii_index *h, long long rows)
 
 // ---- derived code layouts (M == 32), built lazily on the query stream ------------------------------------
 int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
-               long long prows, uint8_t *out, int M, cudaStream_t st)
+               long long prows, uint8_t *out, int M, int RB, cudaStream_t st)
 {
     if (prows <= 0) return 0;
     const long long thr = prows * 2;
-    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(codes, ids, offsets, d_skew_off, nseg, n_single, 0, prows, out, M);
+    k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(codes, ids, offsets, d_skew_off, nseg, n_single, 0, prows, out, M, RB);
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;
@@ -393,7 +499,7 @@ int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, c
 int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id (linear scan, scan_stream.cuh)
 {
     if (h->skew_lin_rows == h->N) return 0;
-    const int H = h->M / 32;
+    const int H = h->rb / 32;
     const long long prows = skew64_rows(h->N, H);
     // rows appended since the last build only change the windows from the first incomplete group on: keep the rest
     long long keep = h->skew_lin_rows > 0 && h->skew_lin_rows < h->N ? (h->skew_lin_rows / 64) * H * 64 : 0;
@@ -410,7 +516,7 @@ int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id
     CK(cudaMemcpyAsync(h->skew_misc_off.p, off, 16, cudaMemcpyHostToDevice, st));
     const long long thr = (prows - keep) * 2;
     k_skew64_build<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(h->d_codes, nullptr, nullptr, h->skew_misc_off.as<long long>(), 1, h->N,
-                                                                  keep, prows, h->skew_lin.as<uint8_t>(), h->M);
+                                                                  keep, prows, h->skew_lin.as<uint8_t>(), h->M, h->rb);
     LAUNCHED();
     CK(cudaGetLastError());
     h->skew_lin_rows = h->N;
@@ -420,13 +526,13 @@ int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id
 int ensure_centers_skew(rii_index *h, cudaStream_t st)  // skew64 of the coarse centers (fused coarse pass)
 {
     if (h->centers_skew_valid) return 0;
-    const long long prows = skew64_rows(h->nlist, h->M / 32);
+    const long long prows = skew64_rows(h->nlist, h->rb / 32);
     CKR(h->centers_skew.ensure((size_t)prows * 32));
     CKR(h->skew_misc_off.ensure(32));
     const long long off[2] = {0, prows};
     CK(cudaMemcpyAsync(h->skew_misc_off.as<long long>() + 2, off, 16, cudaMemcpyHostToDevice, st));
     CKR(skew_build(h->centers.as<uint8_t>(), nullptr, nullptr, h->skew_misc_off.as<long long>() + 2, 1, h->nlist, prows,
-                   h->centers_skew.as<uint8_t>(), h->M, st));
+                   h->centers_skew.as<uint8_t>(), h->M, h->rb, st));
     h->centers_skew_valid = true;
     return 0;
 }
@@ -436,12 +542,12 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
     if (h->skew_lists_valid) return 0;
     const int nlist = h->nlist;
     std::vector<long long> off((size_t)nlist + 1, 0);
-    for (int i = 0; i < nlist; ++i) off[i + 1] = off[i] + skew64_rows(h->h_offsets[i + 1] - h->h_offsets[i], h->M / 32);
+    for (int i = 0; i < nlist; ++i) off[i + 1] = off[i] + skew64_rows(h->h_offsets[i + 1] - h->h_offsets[i], h->rb / 32);
     CKR(h->skew_off.ensure((size_t)(nlist + 1) * 8));
     CKR(h->skew_lists.ensure((size_t)std::max<long long>(1, off[nlist]) * 32));
     CK(cudaMemcpyAsync(h->skew_off.p, off.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, st));
     CKR(skew_build(h->d_codes, h->ids.as<int>(), h->offsets.as<long long>(), h->skew_off.as<long long>(), nlist, 0, off[nlist],
-                   h->skew_lists.as<uint8_t>(), h->M, st));
+                   h->skew_lists.as<uint8_t>(), h->M, h->rb, st));
     h->skew_lists_valid = true;
     return 0;
 }
@@ -506,10 +612,10 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
         const int capw = std::max(64, next_pow2(c.topk + 32));
         int nw = 0, shape = 0;
         size_t smem4 = 0;
-        if (M == 32 || M == 64) shape = stream_pick(M, false, false, capw, 0, 0, &nw, &smem4);
+        if (h->rb) shape = stream_pick(h->rb, false, false, capw, 0, 0, &nw, &smem4);
         const bool v2_ok = shape > 0 && c.S == 0 && c.topk <= SK_MAX_K;
         const bool use_v2 = v2_ok && (h->opt_scan_kernel == 4 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
-        if (h->opt_scan_kernel == 4 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=4 needs M == 32 / 64, no target_ids and topk <= 224");
+        if (h->opt_scan_kernel == 4 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=4 needs 12 <= M <= 64, no target_ids and topk <= 224");
         if (use_v2) {
             parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                              std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
@@ -519,7 +625,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 out.partial = h->partial.as<u64>();
             }
             SkewArgs sa{};
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
             sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
             if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
             sa.smem_bytes = SK_DYN_SMEM;
@@ -590,10 +696,10 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
     size_t smem42 = 0;
     // (the fused coarse pass keeps nlist distances in shared memory: sized for it whenever fusing is possible)
     const size_t pool4 = h->opt_fuse_coarse && !big_nlist ? (size_t)h->nlist * 4 : 0;
-    if (M == 32 || M == 64) shape2 = stream_pick(M, true, B >= 148 && h->opt_stream_ctas != 1, capw2, w_eff, pool4, &nw2, &smem42);
-    const bool v2_ok = shape2 > 0 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && !h->h_ids.empty();
+    if (h->rb) shape2 = stream_pick(h->rb, true, B >= 148 && h->opt_stream_ctas != 1, capw2, w_eff, pool4, &nw2, &smem42);
+    const bool v2_ok = shape2 > 0 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && h->h_offsets.back() > 0;
     const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-    if (h->opt_scan_kernel == 4 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=4 (ivf) needs M == 32 / 64, topk <= 224 and a short list plan");
+    if (h->opt_scan_kernel == 4 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=4 (ivf) needs 12 <= M <= 64, topk <= 224 and a short list plan");
     const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                            std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
                                 : 0;
@@ -666,7 +772,7 @@ int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const lo
                 CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
                 out.partial = h->partial.as<u64>();
             }
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant;
+            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
             sa.codes = h->skew_lists.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
             sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
             if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
@@ -719,6 +825,7 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
     if (B <= 0) return 0;
     if (h->N <= 0 && h->n_total() <= 0) return fail(RII_ERR_STATE, "query on an empty index");
     if (topk < 1) return fail(RII_ERR_ARG, "topk must be >= 1");
+    if (h->shard_stale) return fail(RII_ERR_STATE, "codes were added to / cleared from this shard: call rii_set_shard (and rii_set_global_lengths) again");
     const long long Ntot = h->n_total();
     if (S < 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 <= len(target_ids) <= N");            // src/rii.h:220
     if ((long long)topk > (S ? S : Ntot)) return fail(RII_ERR_ARG, "need topk <= N (and topk <= len(target_ids))");  // :200,:219
@@ -727,6 +834,8 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
     bool may_flag = false;
     if (method == RII_METHOD_IVF) {
         if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
+        if (h->N_total >= 0 && h->N_total != h->N && !h->has_global)
+            return fail(RII_ERR_STATE, "IVF query on a shard whose list lengths were not exchanged: call rii_set_global_lengths");
         if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");           // src/rii.h:251
         // src/rii.h:267-277
         size_t ww = (size_t)std::round((double)L * h->nlist / (double)(S == 0 ? Ntot : S));
@@ -818,7 +927,7 @@ int rii_create(const float *codewords, int M, int Ks, int Ds, int verbose, int d
     if (device < 0 || device >= ndev) return fail(RII_ERR_ARG, "no such CUDA device");
     CK(cudaSetDevice(device));
     rii_index *h = new rii_index();
-    h->M = M; h->Ks = Ks; h->Ds = Ds; h->verbose = verbose; h->device = device; h->variant = l2_variant;
+    h->M = M; h->Ks = Ks; h->Ds = Ds; h->rb = M >= 12 && M <= 32 ? 32 : (M > 32 && M <= 64 ? 64 : 0); h->verbose = verbose; h->device = device; h->variant = l2_variant;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cw, (size_t)M * Ks * Ds * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cw, codewords, (size_t)M * Ks * Ds * sizeof(float), cudaMemcpyHostToDevice);
@@ -847,8 +956,9 @@ int rii_destroy(rii_index_t *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
-                      &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
+                      &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3, &h->assign, &h->ws_best, &h->ws_arg, &h->d_flag})
         b->release();
+    if (h->sort_tmp.p) cudaFree(h->sort_tmp.p);
     if (h->d_cw) cudaFree(h->d_cw);
     if (h->d_cw_t) cudaFree(h->d_cw_t);
     if (h->d_Dm) cudaFree(h->d_Dm);
@@ -858,7 +968,7 @@ int rii_destroy(rii_index_t *h)
     return 0;
 }
 
-int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag)
+static int add_codes_impl(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag, cudaMemcpyKind kind)
 {
     if (!h || n < 0 || (n > 0 && !codes)) return fail(RII_ERR_ARG, "bad arguments");
     if (update_flag && h->nlist == 0)  // src/rii.h:166-170
@@ -868,15 +978,26 @@ int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_fl
     CK(cudaSetDevice(h->device));
     const long long N0 = h->N;
     CKR(grow_codes(h, N0 + n));
-    if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream));
+    if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, kind, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->N = N0 + n;  // (skew_lin_rows keeps the row count of the last build: the next linear query extends the copy)
+    if (n && h->N_total >= 0) { h->shard_stale = true; h->has_global = false; }  // lengths / N_total of a shard are stale now
     if (h->verbose) printf("%lld new vectors are added.\nTotal number of codes is %lld\n", (long long)n, h->N);
     if (update_flag) {
         if (h->verbose) printf("Start to update posting lists\n");
         CKR(update_posting_lists(h, N0, n));
     }
     return 0;
+}
+
+int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag)
+{
+    return add_codes_impl(h, codes, n, update_flag, cudaMemcpyHostToDevice);
+}
+
+int rii_add_codes_dev(rii_index_t *h, const uint8_t *d_codes, int64_t n, int update_flag)
+{
+    return add_codes_impl(h, d_codes, n, update_flag, cudaMemcpyDeviceToDevice);
 }
 
 int rii_reconfigure(rii_index_t *h, int nlist, int iter)
@@ -901,15 +1022,18 @@ int rii_reconfigure(rii_index_t *h, int nlist, int iter)
     do {
         if ((rc = d_pick.ensure((size_t)ns * 8)) < 0) break;
         if ((rc = d_sample.ensure((size_t)ns * h->M)) < 0) break;
-        cudaMemcpyAsync(d_pick.p, pick.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaError_t ce = cudaMemcpyAsync(d_pick.p, pick.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, h->stream);
         long long tot = ns * h->M;
         k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_codes, d_pick.as<long long>(), ns, h->M,
                                                                           d_sample.as<uint8_t>());
         LAUNCHED();
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) { rc = fail(RII_ERR_CUDA, std::string("rii_reconfigure: ") + cudaGetErrorString(ce)); break; }
         // (2)+(3) PQk-means, src/rii.h:136-146
         if (h->verbose) printf("Start to run PQk-means\n");
         rc = fit_coarse(h, d_sample.as<uint8_t>(), ns, nlist, iter, centers.data());
     } while (0);
+    if (rc < 0) cudaStreamSynchronize(h->stream);
     d_pick.release();
     d_sample.release();
     if (rc < 0) return rc;
@@ -928,9 +1052,19 @@ int rii_clear(rii_index_t *h)
     h->skew_lists_valid = h->centers_skew_valid = false;
     h->h_centers.clear();
     h->h_offsets.assign(1, 0);
-    h->h_ids.clear();
+    h->N_assigned = 0;
     h->has_global = false;
     h->len_sorted_prefix.clear();
+    if (h->N_total >= 0) h->shard_stale = true;
+    // the reference's clear() releases its vectors (src/rii.h:328-333): give the code table and every derived layout back
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->d_codes) cudaFree(h->d_codes);
+    h->d_codes = nullptr;
+    h->cap_rows = 0;
+    for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->ids, &h->assign, &h->ws_best, &h->ws_arg,
+                      &h->partial, &h->T, &h->bitmap, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3})
+        b->release();
     return 0;
 }
 
@@ -981,6 +1115,11 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
         if (value != 0 && value != 1 && value != 4)
             return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural-layout kernels) or 4 (skew64 streaming engine)");
         h->opt_scan_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "assign_kernel")) {
+        if (value != 0 && value != 1 && value != 3) return fail(RII_ERR_ARG, "assign_kernel must be 0 (auto), 1 (natural layout) or 3 (streaming, one CTA per SM)");
+        h->opt_assign_kernel = (int)value;
         return 0;
     }
     if (!strcmp(name, "fuse_coarse")) {
@@ -1160,7 +1299,12 @@ int rii_copy_posting_lists(const rii_index_t *h, int64_t *offsets, int32_t *ids)
 {
     if (!h || !offsets) return fail(RII_ERR_ARG, "null argument");
     for (int i = 0; i <= h->nlist; ++i) offsets[i] = h->h_offsets[i];
-    if (ids && !h->h_ids.empty()) std::memcpy(ids, h->h_ids.data(), h->h_ids.size() * 4);
+    const long long tot = h->h_offsets[h->nlist];
+    if (ids && tot > 0) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(ids, h->ids.p, (size_t)tot * 4, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 
@@ -1183,9 +1327,21 @@ int rii_set_state(rii_index_t *h, const uint8_t *coarse_centers, int nlist, cons
             if (offsets[i + 1] < offsets[i]) return fail(RII_ERR_ARG, "posting list offsets must be non-decreasing");
         for (long long i = 0; i < tot; ++i)
             if (ids[i] < 0 || ids[i] >= N) return fail(RII_ERR_ARG, "posting list id outside [0, N)");
+        if (offsets[0] != 0) return fail(RII_ERR_ARG, "posting list offsets must start at 0");
         h->h_offsets.assign(offsets, offsets + nlist + 1);
-        h->h_ids.assign(ids, ids + tot);
-        CKR(upload_lists(h));
+        CKR(h->ids.ensure(std::max<size_t>(4, (size_t)tot * 4)));
+        if (tot) CK(cudaMemcpyAsync(h->ids.p, ids, (size_t)tot * 4, cudaMemcpyHostToDevice, h->stream));
+        CKR(finish_lists(h));
+        if (tot) {  // row -> list map (rows that are in no list keep -1)
+            CKR(grow_assign(h, N));
+            CK(cudaMemsetAsync(h->assign.p, 0xff, (size_t)N * 4, h->stream));
+            k_assign_from_csr<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->offsets.as<long long>(), h->ids.as<int>(), nlist, tot,
+                                                                                    h->assign.as<int>());
+            LAUNCHED();
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->stream));
+            h->N_assigned = N;
+        }
     }
     return 0;
 }
@@ -1238,7 +1394,7 @@ int rii_assign(rii_index_t *h, const uint8_t *codes, int64_t n, const uint8_t *c
     if (!h || !codes || !centers || !out_assign || n < 0 || K <= 0) return fail(RII_ERR_ARG, "bad arguments");
     if (n == 0) return 0;
     CK(cudaSetDevice(h->device));
-    DevBuf dc, dk, da, dd;
+    DevBuf dc, dk, da, dd, dsk;
     int rc = 0;
     do {
         if ((rc = dc.ensure((size_t)n * h->M)) < 0) break;
@@ -1247,13 +1403,15 @@ int rii_assign(rii_index_t *h, const uint8_t *codes, int64_t n, const uint8_t *c
         if (out_dist && (rc = dd.ensure((size_t)n * 4)) < 0) break;
         cudaMemcpyAsync(dc.p, codes, (size_t)n * h->M, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyAsync(dk.p, centers, (size_t)K * h->M, cudaMemcpyHostToDevice, h->stream);
-        if ((rc = launch_assign(h, dc.as<uint8_t>(), n, dk.as<uint8_t>(), K, da.as<int>(), out_dist ? dd.as<float>() : nullptr)) < 0) break;
+        AssignSrc src;
+        if ((rc = make_assign_src(h, dc.as<uint8_t>(), n, &dsk, &src)) < 0) break;
+        if ((rc = launch_assign(h, src, dk.as<uint8_t>(), K, da.as<int>(), out_dist ? dd.as<float>() : nullptr)) < 0) break;
         cudaMemcpyAsync(out_assign, da.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
         if (out_dist) cudaMemcpyAsync(out_dist, dd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(RII_ERR_CUDA, std::string("rii_assign: ") + cudaGetErrorString(e));
     } while (0);
-    dc.release(); dk.release(); da.release(); dd.release();
+    dc.release(); dk.release(); da.release(); dd.release(); dsk.release();
     return rc;
 }
 
@@ -1300,8 +1458,10 @@ int rii_encode(rii_index_t *h, const float *vecs, int64_t n, uint8_t *out_codes)
 int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total)
 {
     if (!h || id_base < 0 || N_total < 0) return fail(RII_ERR_ARG, "bad arguments");
+    if (N_total < h->N) return fail(RII_ERR_ARG, "N_total is smaller than the number of local codes");
     h->id_base = id_base;
     h->N_total = N_total;
+    h->shard_stale = false;
     return 0;
 }
 

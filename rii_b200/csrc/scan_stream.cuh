@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 {
     static_assert(H == 1 || H == 2, "M = 32 or 64");
     static_assert(ST_R % H == 0, "a block's half-row index must be a constant of its pipeline stage");
-    constexpr int M = 32 * H;                                // bytes per code row; H tables of 64 KB
+    constexpr int M = 32 * H;                                // bytes per (zero-padded) code row; H tables of 64 KB
+    const int Mr = a.M;                                      // real sub-spaces (<= M): columns beyond look up +0.0f, and x + 0 == x
     constexpr int ST_D = ST_R - 1;                           // blocks in flight ahead of the one being scanned
     constexpr uint32_t ST_RING_BYTES = ST_R * ST_BLOCK_BYTES;  // per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -401,10 +402,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         const int rot = (int)((blockIdx.y * gridDim.x + blockIdx.x) * 53u) & 255;
         float *lutB = lut2 + (H - 1) * (SK_LUT_BYTES / 4);
         if (a.T) {
-            const float *T = a.T + (size_t)b * M * a.Ks;
+            const float *T = a.T + (size_t)b * Mr * a.Ks;
             for (int e = threadIdx.x; e < 256 * M; e += NW * 32) {
                 const int ks = e / M, m = e % M;
-                const float v = ks < a.Ks ? __ldg(T + m * a.Ks + ks) : 0.f;
+                const float v = ks < a.Ks && m < Mr ? __ldg(T + m * a.Ks + ks) : 0.f;
                 bad |= !(v <= ST_TABLE_LIMIT);
                 lut2[ks * 64 + ((m + 32) & 63)] = v;
                 lutB[ks * 64 + (m & 63)] = v;
@@ -417,14 +418,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 #pragma unroll
             for (int mh = 0; mh < H; ++mh) {
                 const int m = mh * 32 + lane;
-                const float *qm = a.Q + (size_t)b * M * a.Ds + (size_t)m * a.Ds;
-                if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {  // 16 independent 16-byte loads in flight per lane
+                const float *qm = a.Q + (size_t)b * Mr * a.Ds + (size_t)m * a.Ds;
+                if (m >= Mr) {  // padded sub-space: a column of zeros
+                    for (int ks = wid; ks < 256; ks += NW) {
+                        lut2[ks * 64 + ((m + 32) & 63)] = 0.f;
+                        lutB[ks * 64 + m] = 0.f;
+                    }
+                } else if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {  // 16 independent 16-byte loads in flight per lane
                     const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
                     const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
                     for (int i = wid; i < 256; i += NW) {
                         const int ks = (i + rot) & 255;
-                        const float4 c4 = __ldg(cw4 + ks * M);
+                        const float4 c4 = __ldg(cw4 + ks * Mr);
                         const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + ((m + 32) & 63)] = v;
@@ -437,7 +443,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                     for (int i = wid; i < 256; i += NW) {
                         const int ks = (i + rot) & 255;
                         float v = 0.f;
-                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * M + m) * a.Ds, a.Ds);
+                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds);
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + ((m + 32) & 63)] = v;
                         lutB[ks * 64 + m] = v;
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 #pragma unroll 1
                     for (int ks = wid; ks < 256; ks += NW) {
                         float v = 0.f;
-                        if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * M + m) * a.Ds, a.Ds, a.variant);
+                        if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds, a.variant);
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + ((m + 32) & 63)] = v;
                         lutB[ks * 64 + m] = v;

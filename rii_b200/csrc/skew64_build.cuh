@@ -2,12 +2,12 @@
 #pragma once
 #include "skew64.cuh"
 
-// Build (a range of) skew64 segments.  codes: (rows, 32) by id; ids / offsets: CSR of the segments (null: ONE segment
+// Build (a range of) skew64 segments.  codes: (rows, M) by id, padded with zeros to RB = 32 or 64 bytes per row; ids / offsets: CSR of the segments (null: ONE segment
 // = rows [0, n_single) in id order); skew_off: (nseg + 1) first physical row (32-byte unit) of every segment, a
 // multiple of 64.  One thread per 16-byte chunk.
 __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__restrict__ ids, const long long *__restrict__ offsets,
                                const long long *__restrict__ skew_off, int nseg, long long n_single, long long prow0,
-                               long long prow1, uint8_t *__restrict__ out, int M)
+                               long long prow1, uint8_t *__restrict__ out, int M, int RB)
 {
     const long long i = prow0 * 2 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the table
     const long long prow = i >> 1;
@@ -28,10 +28,11 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
     for (int j = 0; j < 16; ++j) {
         const long long x = 32 * b - lag + 16 * half + j;  // byte of stream s
         if (x >= 0) {
-            const long long r = 64 * (x / M) + s;          // row of the segment
-            if (r < len) {
+            const long long r = 64 * (x / RB) + s;         // row of the segment
+            const int bb = (int)(x % RB);                  // byte of the padded row
+            if (r < len && bb < M) {
                 const long long id = ids ? (long long)ids[ioff + r] : r;
-                w[j >> 2] |= (uint32_t)__ldg(codes + id * M + (x % M)) << (8 * (j & 3));
+                w[j >> 2] |= (uint32_t)__ldg(codes + id * M + bb) << (8 * (j & 3));
             }
         }
     }

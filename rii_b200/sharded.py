@@ -233,3 +233,80 @@ CudaShardEngine.query_local = _cuda_query_local
 CudaShardEngine.subset_counts = _cuda_subset_counts
 CudaShardEngine.subset_scan = _cuda_subset_scan
 CudaShardEngine.merge = _cuda_merge
+
+
+class LocalShardGroup(object):
+    """G id-range shards held by ONE process as G index handles (all on one GPU, or spread over the GPUs the process
+    sees).  Exactly the C-ABI sequence of the multi-process path -- rii_set_shard, rii_fit_coarse, rii_set_coarse_centers,
+    rii_set_global_lengths, per-shard queries, rii_merge_shards_dev -- with every collective replaced by a concatenation
+    on the host / device.  It is what the single-GPU parity test of the sharded planner drives (pre_len / glob_len), and
+    a way to shard an index over several GPUs without torch.distributed."""
+
+    def __init__(self, impls):
+        self.engines = [CudaShardEngine(e) for e in impls]
+        self.G = len(impls)
+
+    def build(self, codes_all, nlist, iter):
+        n_total = codes_all.shape[0]
+        b = shard_bounds(n_total, self.G)
+        ids = reference_sample_ids(n_total, nlist)
+        for g, eng in enumerate(self.engines):
+            eng.add_codes(np.ascontiguousarray(codes_all[b[g]:b[g + 1]]))
+            eng.set_shard(b[g], n_total)
+        sample = np.ascontiguousarray(codes_all[ids])        # == the concatenation gather_sample() assembles
+        centers = self.engines[0].fit_coarse(sample, nlist, iter)
+        lens = []
+        for eng in self.engines:
+            eng.set_coarse_centers(centers)
+            lens.append(eng.list_lengths().astype(np.int64))
+        lens = np.stack(lens)
+        for g, eng in enumerate(self.engines):
+            eng.set_global_lengths(lens.sum(0).astype(np.int32), lens[:g].sum(0).astype(np.int32))
+        return centers
+
+    def _merge(self, outs):
+        import torch
+        if self.G == 1:
+            return outs[0]
+        dev = outs[0][0].device
+        g_ids = torch.stack([o[0].to(dev) for o in outs]).contiguous()
+        g_d = torch.stack([o[1].to(dev) for o in outs]).contiguous()
+        g_c = torch.stack([o[2].to(dev) for o in outs]).contiguous()
+        return self.engines[0].merge(g_ids, g_d, g_c)
+
+    def query(self, Q, topk, L, method):
+        import torch
+        outs = []
+        for eng in self.engines:
+            with torch.cuda.device(eng.e._device):
+                outs.append(eng.query_local(Q.to("cuda:%d" % eng.e._device), topk, L, method))
+                torch.cuda.synchronize()
+        return self._merge(outs)
+
+    def query_subset(self, Q, topk, L, tids):
+        """IVF + target_ids over the shards (two-phase: per-list member counts of every shard, then the scans)."""
+        import torch
+
+        def one_round(Qr, full):
+            cnts = [eng.subset_counts(Qr, topk, tids, L, full) for eng in self.engines]
+            g = torch.stack(cnts)
+            glob = g.sum(0, dtype=torch.int32).contiguous()
+            outs, flags = [], None
+            for r, eng in enumerate(self.engines):
+                pre = (g[:r].sum(0, dtype=torch.int32) if r else torch.zeros_like(cnts[0])).contiguous()
+                # phase B must follow phase A of the SAME handle with the same queries (it reuses the ranking)
+                eng.subset_counts(Qr, topk, tids, L, full)
+                ids, d, c, flags = eng.subset_scan(Qr, topk, tids, L, full, glob, pre)
+                outs.append((ids, d, c))
+            ids, d, c = self._merge(outs)
+            return ids, d, c, flags
+
+        ids, d, c, flags = one_round(Q, 0)
+        redo = torch.nonzero(flags & 1).flatten()
+        if redo.numel():
+            i2, d2, c2, _ = one_round(Q[redo].contiguous(), 1)
+            ids[redo], d[redo], c[redo] = i2, d2, c2
+        empty = torch.nonzero((flags & 2) != 0).flatten()
+        if empty.numel():
+            c[empty] = 0
+        return ids, d, c

@@ -659,3 +659,105 @@ def test_stream_kernel_incremental_adds(M):
             r = e.query_linear(q, k, EMPTY)
             assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(O.dtable(q, cw, 16), codes[:n], k), "after %d rows" % n)
     assert n == 5000
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_id_range_shards_on_one_gpu(G):
+    """SURVEY 8e on ONE device: G id-range shards as G handles on cuda:0 (rii_set_shard, rii_fit_coarse,
+    rii_set_coarse_centers, rii_set_global_lengths; concat of the per-shard outputs + rii_merge_shards_dev) must equal the
+    unsharded oracle bit for bit: linear, IVF (the global cut planned from glob_len / pre_len) and IVF + target_ids."""
+    import torch
+    from rii_b200 import sharded
+    D, M, Ks, N, nlist = 128, 32, 256, 150000, 90
+    cw, codes, Q = synth(D, M, Ks, N, 6, seed=4321)
+    grp = sharded.LocalShardGroup([main.RiiCpp(cw, False, l2_variant=16) for _ in range(G)])
+    centers = grp.build(codes, nlist, 2)
+    oc, oa = O.reconfigure(cw, codes, nlist, 2)
+    assert np.array_equal(centers, oc), "sharded coarse centers differ from the oracle"
+    offsets, ids = O.assign_to_lists(oa, nlist)
+    # the shards' posting lists are the id-range slices of the oracle's lists
+    b = sharded.shard_bounds(N, G)
+    for g, eng in enumerate(grp.engines):
+        so, si = eng.e.posting_lists_csr()
+        for no in range(0, nlist, 7):
+            full = ids[offsets[no]:offsets[no + 1]]
+            assert np.array_equal(si[so[no]:so[no + 1]] + b[g], full[(full >= b[g]) & (full < b[g + 1])])
+    dev = torch.device("cuda", 0)
+    Qd = torch.from_numpy(Q).to(dev)
+    for method, topk, L in [("linear", 1, 0), ("linear", 50, 0), ("ivf", 1, 2000), ("ivf", 10, 6400), ("ivf", 100, 150),
+                            ("ivf", 5, N), ("ivf", 3, 1666)]:
+        gi, gd, gc = grp.query(Qd, topk, L, method)
+        torch.cuda.synchronize()
+        gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+        for bq, q in enumerate(Q):
+            T = O.dtable(q, cw, 16)
+            exp = O.query_linear(T, codes, topk) if method == "linear" else O.query_ivf(T, codes, oc, offsets, ids, topk, L)
+            n = int(gc[bq])
+            assert_same_result(gi[bq, :n], gd[bq, :n], exp[0], exp[1], "shards G=%d %s k=%d L=%d" % (G, method, topk, L))
+    rng = np.random.default_rng(5)
+    far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), oc))[-5:]
+    far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+    for tids, topk, L in [(np.sort(rng.choice(N, 20000, replace=False)).astype(np.int64), 10, 3200),
+                          (np.sort(rng.choice(N, 3000, replace=False)).astype(np.int64), 1, 3000), (far_ids, 3, 40)]:
+        gi, gd, gc = grp.query_subset(Qd, topk, L, torch.from_numpy(tids).to(dev))
+        torch.cuda.synchronize()
+        gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+        for bq, q in enumerate(Q):
+            exp = O.query_ivf(O.dtable(q, cw, 16), codes, oc, offsets, ids, topk, L, tids)
+            n = int(gc[bq])
+            assert_same_result(gi[bq, :n], gd[bq, :n], exp[0], exp[1], "shards G=%d subset k=%d L=%d" % (G, topk, L))
+    # mutating a shard invalidates its global state until the lengths are exchanged again (ADVICE r1)
+    grp.engines[0].e.add_codes(codes[:10], False)
+    with pytest.raises(Exception):
+        grp.engines[0].query_local(Qd, 1, 1000, "ivf")
+
+
+@pytest.mark.parametrize("D,M,Ks", [(40, 20, 256), (96, 24, 64), (96, 48, 256), (60, 12, 256)])
+def test_padded_rows_on_the_streaming_engine(D, M, Ks):
+    """12 <= M <= 64 that are not 32 / 64 run on the streaming engine with zero-padded rows and zero table columns
+    (x + 0.0f == x: still the reference's sequential sum): linear, IVF, and the assignment engine."""
+    N, nlist = 30000, 40
+    cw, codes, Q = synth(D, M, Ks, N, 4, seed=M * 7)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 2)
+    oc, oa = O.reconfigure(cw, codes, nlist, 2)
+    assert np.array_equal(e.coarse_centers_array(), oc)
+    offsets, ids = O.assign_to_lists(oa, nlist)
+    eo, ei = e.posting_lists_csr()
+    assert np.array_equal(eo, offsets) and np.array_equal(ei, ids)
+    e.set_option("scan_kernel", 4)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 17):
+            r = e.query_linear(q, topk, EMPTY)
+            assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(T, codes, topk), "padded linear M=%d" % M)
+            for L in (topk, 900, 5000):
+                r = e.query_ivf(q, topk, EMPTY, L)
+                exp = O.query_ivf(T, codes, oc, offsets, ids, topk, L)
+                assert_same_result(r[0], np.array(r[1], np.float32), exp[0], exp[1], "padded ivf M=%d L=%d" % (M, L))
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 1, 1), (32, 63, 5), (32, 64, 64), (32, 65, 300), (32, 5000, 1000), (32, 100000, 37),
+                                   (64, 777, 129), (64, 40000, 50), (20, 3000, 77), (48, 3000, 77)])
+def test_assign_stream_engine_vs_natural_and_oracle(M, N, K):
+    """K6 on the streaming engine (k_assign_stream + k_assign_reduce) == natural-layout k_assign == oracle: assignments
+    and distances bit for bit, every row / center tail, first minimum wins (duplicated centers)."""
+    D, Ks = 4 * M, 256
+    cw, codes, _ = synth(D, M, Ks, N, 1, seed=N + K)
+    rng = np.random.default_rng(N * 31 + K)
+    centers = rng.integers(0, Ks, (K, M), dtype=np.uint8)
+    if K > 4:
+        centers[K // 2] = centers[1]  # exact tie between two centers: the lower index must win
+        centers[K - 1] = centers[0]
+    e = engine(cw)
+    res = {}
+    for ak in (1, 0, 3):
+        e.set_option("assign_kernel", ak)
+        res[ak] = e.assign(codes, centers, return_dist=True)
+    for ak in (0, 3):
+        assert np.array_equal(res[ak][0], res[1][0]), "assign_kernel=%d" % ak
+        assert np.array_equal(bits(res[ak][1]), bits(res[1][1])), "assign_kernel=%d" % ak
+    n_chk = min(N, 2000)
+    Dm = O.sym_matrices(cw)
+    oa, od = O.assign(Dm, codes[:n_chk], centers, return_dist=True)
+    assert np.array_equal(res[0][0][:n_chk], oa) and np.array_equal(bits(res[0][1][:n_chk]), bits(od))

@@ -137,18 +137,24 @@ def main_():
             print(json.dumps({"what": "ivf_batch_topk", "topk": topk, "B": B, "L": L, "scan_ivf_ms": round(ms / max(n, 1), 4)}))
     if "assign" in a.what:
         n_as = min(N, 1000000)
-        e2 = main.RiiCpp(cw, False, l2_variant=16)
         codes = torch.randint(0, 256, (n_as, M), dtype=torch.uint8).numpy()
-        e2.add_codes(codes, False)
-        lib.rii_profile_enable(e2._h, 1)
-        t0 = time.time()
-        e2.reconfigure(1000, 5)
-        torch.cuda.synchronize()
-        dt = time.time() - t0
-        ms, n = prof(lib, e2, "assign")
-        print(json.dumps({"what": "reconfigure", "N": n_as, "nlist": 1000, "iter": 5, "seconds": round(dt, 3),
-                          "assign_ms_total": round(ms, 2), "assign_launches": n,
-                          "lookups_per_s_T": round((n_as + 5 * 100000) * 1000 * M / (ms * 1e-3) / 1e12, 3)}))
+        for ak in (1, 0, 3):  # natural-layout k_assign, streaming engine (2 CTAs / SM), streaming engine (1 CTA / SM)
+            e2 = main.RiiCpp(cw, False, l2_variant=16)
+            e2.set_option("assign_kernel", ak)
+            e2.add_codes(codes, False)
+            e2.reconfigure(1000, 1)  # warm-up: Dm, skew copies, allocations
+            torch.cuda.synchronize()
+            lib.rii_profile_enable(e2._h, 1)
+            lib.rii_profile_reset(e2._h)
+            t0 = time.time()
+            e2.reconfigure(1000, 5)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            ms, n = prof(lib, e2, "assign")
+            print(json.dumps({"what": "reconfigure", "assign_kernel": ak, "N": n_as, "M": M, "nlist": 1000, "iter": 5, "seconds": round(dt, 4),
+                              "assign_ms_total": round(ms, 3), "assign_launches": n,
+                              "lookups_per_s_T": round((n_as + 5 * 100000) * 1000 * M / (ms * 1e-3) / 1e12, 3)}))
+            del e2
 
 
 if __name__ == "__main__":
