@@ -89,6 +89,7 @@ struct TopkOut {
     float *out_dists;    // (B, k)
     int *out_counts;     // (B)
     long long id_base;
+    const long long *id_map;  // when set: key id -> global id (subset scans over a compact copy of the target rows)
     int final;
 };
 __device__ __forceinline__ void emit_topk(BlockTopk &tk, const TopkOut &o, int b, int part, int parts)
@@ -99,7 +100,7 @@ __device__ __forceinline__ void emit_topk(BlockTopk &tk, const TopkOut &o, int b
     if (o.final) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             u64 key = tk.keys[i];
-            o.out_ids[(size_t)b * k + i] = o.id_base + (long long)key_id(key);
+            o.out_ids[(size_t)b * k + i] = o.id_map ? o.id_map[key_id(key)] : o.id_base + (long long)key_id(key);
             o.out_dists[(size_t)b * k + i] = key_dist(key);
         }
         if (threadIdx.x == 0) o.out_counts[b] = n;
@@ -192,6 +193,8 @@ struct SkewArgs {
     uint32_t smem_bytes;       // dynamic shared memory of the launch (the kernel lays its regions out around the table)
     const uint8_t *centers;    // IVF fused: (nlist, 32) coarse centers, or null (plan comes from a separate k_coarse_rank)
     int nlist;
+    int coarse_mode;           // IVF: 0 = one launch does everything; 1 = coarse pass only (write plan.ranked, no scan);
+                               //      2 = no coarse pass: the ranking is read from plan.ranked, the plan is made in-kernel
     int coarse_lists;          // v4 fused: rank the centers with the warps' top-k lists (nlist > 1024) instead of keeping every distance
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;

@@ -50,7 +50,7 @@
 // prefix of 64-row groups), s_take (local take), s_off, s_prow -- and J / take_last / flags of the query in global
 // memory exactly as make_plan writes them.  Returns the number of segments (0 when the plan is flagged).
 __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, const int *s_f, const int *s_pre, const int *s_loc,
-                                         long long *s_off, long long *s_prow, int *s_gcum, int *s_take)
+                                         long long *s_off, long long *s_prow, int *s_gcum, int *s_take, bool publish = true)
 {
     const int W = p.w_eff;
     // pass 1: F_j = inclusive prefix of the list lengths; jL = first rank with F_j >= L; F at rank w - 1
@@ -121,7 +121,7 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
         gcarry = __shfl_sync(0xffffffffu, g, 31);
         __syncwarp();
     }
-    if (lane == 0) {
+    if (lane == 0 && publish) {
         p.J[b] = J;
         p.take_last[b] = take_last;
         p.flags[b] = flag;
@@ -288,7 +288,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         return jj;
     };
     if constexpr (IVF) {
-        if (!fused) {
+        if (!fused && a.coarse_mode == 2) {
+            // the ranking comes from a separate coarse-only launch (possibly of another GPU: the coarse phase of a sharded
+            // batch is split over the ranks); the plan is made here, identically by every CTA of the query
+            if (wid == 0) {
+                const int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
+                for (int j = lane; j < a.w_eff; j += 32) {
+                    const int no = ranked_g[j];
+                    s_f[j] = a.plan.glob_len[no];
+                    s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
+                    s_loc[j] = a.plan.loc_len[no];
+                    s_off[j] = a.offsets[no];
+                    s_prow[j] = a.skew_off[no];
+                }
+                __syncwarp();
+                const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take, blockIdx.x == 0);
+                if (lane == 0) s_plan[0] = jc;
+            }
+        } else if (!fused) {
             const int Jp = (a.flags[b] != 0) ? 0 : a.J[b];
             for (int j = threadIdx.x; j < Jp; j += blockDim.x) {
                 const int no = a.ranked[(size_t)b * a.w_eff + j];
@@ -541,7 +558,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             u64 *selk = reinterpret_cast<u64 *>(smem_raw + hi0);          // (rings idle) <= 256 selected keys, the full sort (nlist <= 1024), or the merged warp lists
             int np = 0;
             if (direct) {
-                np = cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist, true);
+                np = a.w_eff <= 224 ? cta_select_smallest<NW * 32>(pool_d, a.nlist, a.w_eff, selk, hist, true) : -1;
+                if (np < 0) {  // many lists to rank (subset searches), or > 256 exact ties at the w-th distance: sort all (dist, index) keys
+                    const int P = next_pow2(a.nlist);
+                    for (int i = threadIdx.x; i < P; i += NW * 32) selk[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
+                    cta_sort_smem<NW * 32>(selk, P);
+                    np = a.nlist;
+                }
             } else {  // merge the warps' sorted lists (each <= w_eff keys) into the ranked list
                 if (lane == 0) s_cnt[wid] = wt.count;
                 __syncthreads();
@@ -575,12 +598,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 if (threadIdx.x < NW) thr_w[threadIdx.x] = RII_KEY_MAX;  // (cta_thr is reset with the plan below)
             }
             if (wid == 0) {
-                if (np < 0) {  // > 256 exact ties at the w-th distance: full sort of all (dist, index) keys
-                    const int P = next_pow2(a.nlist);
-                    for (int i = lane; i < P; i += 32) selk[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
-                    warp_sort_smem(selk, P, lane);
-                    np = a.nlist;
-                }
                 if (dbg && lane == 0) { dbg[6] = clock64(); dbg[7] = np; }
                 int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
                 for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist, np >= w_eff
@@ -593,12 +610,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                     s_prow[j] = a.skew_off[no];
                 }
                 __syncwarp();
-                const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take);
+                const int jc = a.coarse_mode == 1 ? 0 : plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take);
                 if (lane == 0) {
                     s_plan[0] = jc;
                     *cta_thr = RII_KEY_MAX;
                 }
             }
+            if (a.coarse_mode == 1) return;  // coarse-only launch: the ranking is all that was asked for (CTA-uniform)
             __syncthreads();
             if (dbg && threadIdx.x == 0) dbg[1] = clock64();
             J = s_plan[0];
@@ -668,7 +686,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 const int n = tot < a.k ? tot : a.k;
                 if (a.out.final) {
                     for (int i = lane; i < n; i += 32) {
-                        a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(mk[i]);
+                        a.out.out_ids[(size_t)b * a.k + i] = a.out.id_map ? a.out.id_map[key_id(mk[i])] : a.out.id_base + (long long)key_id(mk[i]);
                         a.out.out_dists[(size_t)b * a.k + i] = key_dist(mk[i]);
                     }
                     if (lane == 0) a.out.out_counts[b] = n;

@@ -132,6 +132,25 @@ __device__ __forceinline__ void warp_sort_smem(u64 *k, int P, int lane)
         }
 }
 
+// bitonic sort of P (power of two) keys in shared memory by the whole CTA of NT threads
+template <int NT>
+__device__ __forceinline__ void cta_sort_smem(u64 *k, int P)
+{
+    __syncthreads();
+    for (int kk = 2; kk <= P; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += NT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const u64 x = k[i], y = k[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) { k[i] = y; k[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 // Coarse selection (fused kernel): the w smallest of np (distance bits, index) pairs, distances in shared memory.
 // One CTA-wide histogram pass: 256 equal-width buckets over [min, max] of the (non-negative float) distance bits, a
 // redundant per-warp scan finds the bucket b* holding the w-th smallest; everything in buckets <= b* (w keys plus the

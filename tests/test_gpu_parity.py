@@ -670,7 +670,7 @@ def test_id_range_shards_on_one_gpu(G):
     from rii_b200 import sharded
     D, M, Ks, N, nlist = 128, 32, 256, 150000, 90
     cw, codes, Q = synth(D, M, Ks, N, 6, seed=4321)
-    grp = sharded.LocalShardGroup([main.RiiCpp(cw, False, l2_variant=16) for _ in range(G)])
+    grp = sharded.LocalShardGroup([engine(cw) for _ in range(G)])
     centers = grp.build(codes, nlist, 2)
     oc, oa = O.reconfigure(cw, codes, nlist, 2)
     assert np.array_equal(centers, oc), "sharded coarse centers differ from the oracle"
