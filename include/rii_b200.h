@@ -132,30 +132,41 @@ int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_di
                          int B, int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream);
 
 /* IVF + target_ids on an id-range shard (the binary_search filter of src/rii.h:294 with the ids spread over shards):
- * the cut after L filtered candidates needs every shard's per-list member counts -- one small exchange.
- *   w_eff = rii_ivf_subset_width(...)                       lists ranked per query (full != 0: all nlist lists)
- *   rii_ivf_subset_counts_dev(... d_counts (B, w_eff))      phase A: this shard's member counts per ranked list
- *   [caller: all-gather of d_counts; d_counts_all = sum over shards, d_counts_lower = sum over lower ranks]
- *   rii_ivf_subset_scan_dev(... d_counts_all, d_counts_lower ...)   phase B: plan with the global counts, scan this
- *                                                           shard's members, per-shard top-k (then all-gather + merge)
- * d_flags (B, may be NULL): bit 0 = fewer than topk members in the first w lists: re-run that query with full = 1
- * (src/rii.h:309-322); bit 1 = empty result (src/rii.h:325).  Same handle, same queries, B <= 2048, device buffers. */
-int rii_ivf_subset_width(rii_index_t *h, int topk, int64_t S, int64_t L, int full);
-int rii_ivf_subset_counts_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids, int64_t S,
-                              int64_t L, int full, int32_t *d_counts, void *stream);
-int rii_ivf_subset_scan_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t S, int64_t L, int full,
-                            const int32_t *d_counts_all, const int32_t *d_counts_lower, int64_t *d_out_ids, float *d_out_dists,
-                            int32_t *d_out_counts, int32_t *d_flags, void *stream);
+ * the cut after L member candidates and the topk test at the w-th list are global, so every shard needs the member
+ * counts of the others -- per list.  Per target set, on every shard:
+ *   rii_subset_begin_dev(d_target_ids (sorted ascending, global ids), S, d_list_counts (nlist) out)
+ *        builds the sub-index of this shard's members and returns its per-list member counts
+ *   [caller: all-gather of the counts; d_counts_all = sum over shards, d_counts_lower = sum over lower ranks]
+ *   rii_subset_set_global_dev(d_counts_all, d_counts_lower)        (skip on a single shard)
+ *   rii_subset_query_dev(queries ...)   any number of times: an ordinary sharded IVF search over the sub-indexes, S taken
+ *        from begin; per-shard top-k out (then all-gather + rii_merge_shards_dev).  Queries that walk beyond the first w
+ *        lists (src/rii.h:309-322) are re-run with the full ranking inside the call; count 0 = the reference's empty
+ *        result (src/rii.h:325).
+ * The prepared sub-index stays valid until the next begin / subset query through rii_query_batch* / index update. */
+int rii_subset_begin_dev(rii_index_t *h, const int64_t *d_target_ids, int64_t S, int32_t *d_list_counts, void *stream);
+int rii_subset_set_global_dev(rii_index_t *h, const int32_t *d_counts_all, const int32_t *d_counts_lower, void *stream);
+int rii_subset_query_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, int64_t *d_out_ids, float *d_out_dists,
+                         int32_t *d_out_counts, void *stream);
 
-/* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout scan (v1), 2 = skewed bank-conflict-free scan (v2), 3 = its
- * dual-stream FFMA2 variant (v3), 4 = the skew64 streaming engine (v4; what auto picks for M == 32 / 64, no target_ids,
- * topk <= 224).  "stream_ctas": 1 = v4 always one CTA per SM.  "fuse_coarse": 0 = separate coarse-ranking kernel.
- * Results are identical for every setting. */
+/* The coarse phase of IVF (src/rii.h:259-280) split from the posting-list scan, for sharded batches: every rank ranks the
+ * lists for ITS share of the batch (the ranking does not depend on the shard), the (B, w) rankings are all-gathered, and
+ * every rank scans its shard for all queries with the rankings given.  w = rii_coarse_width(h, L).
+ * d_flags (B, may be NULL): bit 0 = fewer than topk candidates in the first w lists (re-run through rii_query_batch_dev,
+ * which ranks all lists), bit 1 = empty result.  Streaming-engine shapes only (12 <= M <= 64, topk <= 224). */
+int rii_coarse_width(rii_index_t *h, int64_t L);
+int rii_coarse_rank_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, int32_t *d_ranked, void *stream);
+int rii_query_ranked_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, const int32_t *d_ranked, int64_t *d_out_ids,
+                         float *d_out_dists, int32_t *d_out_counts, int32_t *d_flags, void *stream);
+
+/* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout kernels only, 4 = the skew64 streaming engine or fail
+ * (what auto picks for 12 <= M <= 64, topk <= 224, ascending target_ids).  "stream_ctas": 1 = always one CTA per SM.
+ * "fuse_coarse": 0 = coarse ranking in its own launch.  "assign_kernel": 0 = auto, 1 = natural-layout k_assign, 3 =
+ * streaming assignment engine with one CTA per SM.  Results are identical for every setting. */
 int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* Per-kernel device time from CUDA events recorded around every launch on the launching stream.
- * kernel: "dtable" | "scan_linear" | "merge" | "coarse_rank" | "count_members" | "plan" | "scan_ivf" | "assign". */
+ * kernel: "dtable" | "scan_linear" | "merge" | "coarse_rank" | "subset_build" | "plan" | "scan_ivf" | "assign" | "sort". */
 int rii_profile_enable(rii_index_t *h, int on);
 int rii_profile_reset(rii_index_t *h);
 int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches);

@@ -48,9 +48,12 @@ SYMBOLS = {
     "rii_set_global_lengths": (C.c_int, [_vp, _i32p, _i32p]),
     "rii_sample_ids": (C.c_int, [C.c_int64, C.c_int, _i64p, _i64p]),
     "rii_merge_shards_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
-    "rii_ivf_subset_width": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_int]),
-    "rii_ivf_subset_counts_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int, _vp, _vp]),
-    "rii_ivf_subset_scan_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rii_subset_begin_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
+    "rii_subset_set_global_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "rii_subset_query_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp]),
+    "rii_coarse_width": (C.c_int, [_vp, C.c_int64]),
+    "rii_coarse_rank_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int64, _vp, _vp]),
+    "rii_query_ranked_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rii_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "rii_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rii_profile_reset": (C.c_int, [_vp]),

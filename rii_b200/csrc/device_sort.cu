@@ -51,15 +51,15 @@ int dev_sort_keys_u64(const unsigned long long *in, unsigned long long *out, lon
     return 0;
 }
 
-int dev_segsort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, int nseg, const long long *d_seg_off,
-                         SortTmp *tmp, cudaStream_t st)
+int dev_segsort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, int nseg, const long long *d_seg_beg,
+                         const long long *d_seg_end, SortTmp *tmp, cudaStream_t st)
 {
     if (n <= 0 || nseg <= 0) return 0;
     if (n >= (1ll << 31)) return rii_fail(RII_ERR_LIMIT, "sort of >= 2^31 items");
     size_t need = 0;
-    CK(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, need, in, out, (int)n, nseg, d_seg_off, d_seg_off + 1, 0, 64, st));
+    CK(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, need, in, out, (int)n, nseg, d_seg_beg, d_seg_end, 0, 64, st));
     if (int rc = ensure_tmp(tmp, need)) return rc;
-    CK(cub::DeviceSegmentedRadixSort::SortKeys(tmp->p, need, in, out, (int)n, nseg, d_seg_off, d_seg_off + 1, 0, 64, st));
+    CK(cub::DeviceSegmentedRadixSort::SortKeys(tmp->p, need, in, out, (int)n, nseg, d_seg_beg, d_seg_end, 0, 64, st));
     rii_count_launch();
     return 0;
 }

@@ -432,94 +432,198 @@ __global__ void __launch_bounds__(RII_THREADS) k_scan_ivf(IvfArgs a)
     emit_topk(s.tk, a.out, b, blockIdx.x, gridDim.x);
 }
 
-// Subset variant (src/rii.h:294 binary_search filter): membership comes from a bitmap over local ids.
-// One CTA walks whole segments (segment j -> CTA j % parts) in stored order; the last segment is cut
-// after its first take_last[b] *member* ids, which needs the in-order rank of every member.
+// ---------------------------------------------------------------------------------------------------
+// Subset searches (target_ids).  src/rii.h:218-228 (linear: exactly the given ids) and :294 (IVF: binary_search filter
+// while walking the lists).  Both run as ordinary scans over a temporary SUB-INDEX built from the target ids:
+//   linear: a compact copy of the target rows (one segment, in the given order), ids mapped back through the target ids;
+//   IVF   : the posting lists restricted to the members (a stable sort of the (list, id) pairs of the targets keeps every
+//           list ascending in id), so "skip non-members, stop after L members" IS the plain walk over the sub-lists.
+// ---------------------------------------------------------------------------------------------------
+// flags[0] |= 1 if not ascending; flags[1] = ids < lo; flags[2] = ids >= hi  (the in-range run of a sorted array)
+__global__ void k_tids_scan(const long long *__restrict__ tids, long long S, long long lo, long long hi, int *flags)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const long long t = tids[i];
+    if (i > 0 && tids[i - 1] > t) atomicOr(flags, 1);
+    if (t < lo) atomicAdd(flags + 1, 1);
+    if (t >= hi) atomicAdd(flags + 2, 1);
+}
+
+// rows[i] = tids[i] - id_base (the caller passes the in-range run)
+__global__ void k_tids_to_rows(const long long *__restrict__ tids, long long n, long long id_base, int *__restrict__ rows)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rows[i] = (int)(tids[i] - id_base);
+}
+
+// (list, row) pair of every target id: list = assign[row]; ids outside this shard, repeated ids (the reference tests
+// membership, so a posting-list id is a candidate once) and rows that are in no list get the key ~0 and sort to the end
+__global__ void k_sub_keys(const long long *__restrict__ tids, long long S, long long id_base, long long N, const int *__restrict__ assign,
+                           uint32_t *__restrict__ keys, uint32_t *__restrict__ rows)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const long long t = tids[i], r = t - id_base;
+    uint32_t key = 0xffffffffu;
+    if (r >= 0 && r < N && !(i > 0 && tids[i - 1] == t)) key = (uint32_t)assign[r];
+    keys[i] = key;
+    rows[i] = (uint32_t)(r >= 0 && r < N ? r : 0);
+}
+
+// per-list lengths and skew64 segment offsets from the CSR bounds of the sorted pairs.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_sub_layout(const long long *__restrict__ bounds, int nlist, int H, int *__restrict__ len,
+                                                      long long *__restrict__ skew_off)
+{
+    __shared__ long long s_part[1024];
+    const int per = (nlist + 1023) / 1024;
+    const int i0 = threadIdx.x * per, i1 = min(nlist, i0 + per);
+    long long sum = 0;
+    for (int i = i0; i < i1; ++i) {
+        const long long l = bounds[i + 1] - bounds[i];
+        len[i] = (int)l;
+        sum += 64 * ((l + 63) / 64 + 1) * H;
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long y = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    long long run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = i0; i < i1; ++i) {
+        skew_off[i] = run;
+        const long long l = bounds[i + 1] - bounds[i];
+        run += 64 * ((l + 63) / 64 + 1) * H;
+    }
+    if (threadIdx.x == 1023) skew_off[nlist] = s_part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// General (global-memory) path: every M, any topk (the reference allows topk = N, rii/rii.py:280-281) and any number
+// of ranked lists.  Distances go to HBM as (dist, id) keys, a segmented radix sort (device_sort.cu) orders them.
+// ---------------------------------------------------------------------------------------------------
+// keys[b][i] for the ncand candidates of a linear scan (all rows, or the given target ids).  grid (blocks, B)
 template <int M_T>
-__global__ void __launch_bounds__(RII_THREADS) k_scan_ivf_subset(IvfArgs a)
+__global__ void __launch_bounds__(RII_THREADS) k_keys_linear(LinearArgs a, u64 *__restrict__ keys, long long stride)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScanSmem s = carve_smem(smem_raw, a.M * a.Ks, a.cap, a.k);
+    float *lut = reinterpret_cast<float *>(smem_raw);
     const int b = blockIdx.y;
+    load_lut(lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    __syncthreads();
+    const long long ncand = a.S ? a.S : a.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = a.S ? a.tids[i] - a.id_base : i;
+        u64 key = RII_KEY_MAX;
+        if (r >= 0 && r < a.N) key = pack_key(adc_row<M_T, false>(lut, a.Ks, a.M, a.codes + r * a.M), (uint32_t)r);
+        keys[(size_t)b * stride + i] = key;
+    }
+}
+
+// coarse keys[b][no] = (ADC distance to center no, no).  grid (blocks, B)
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_coarse_keys(const float *__restrict__ T, const uint8_t *__restrict__ centers, int nlist, int M,
+                                                             int Ks, u64 *__restrict__ keys)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    const int b = blockIdx.y;
+    load_lut(lut, T + (size_t)b * M * Ks, M * Ks);
+    __syncthreads();
+    for (int no = blockIdx.x * blockDim.x + threadIdx.x; no < nlist; no += gridDim.x * blockDim.x)
+        keys[(size_t)b * nlist + no] = pack_key(adc_row<M_T, false>(lut, Ks, M, centers + (size_t)no * M), (uint32_t)no);
+}
+
+// ranked[b][j] and the list lengths by rank (what k_plan consumes) from the sorted coarse keys.  grid (blocks, B)
+__global__ void k_rank_gather(const u64 *__restrict__ sorted, int nlist, int w_eff, const int *__restrict__ glob_len, const int *__restrict__ pre_len,
+                              const int *__restrict__ loc_len, int *__restrict__ ranked, int *__restrict__ f, int *__restrict__ pre, int *__restrict__ loc)
+{
+    const int b = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < w_eff; j += gridDim.x * blockDim.x) {
+        const int no = (int)key_id(sorted[(size_t)b * nlist + j]);
+        const size_t o = (size_t)b * w_eff + j;
+        ranked[o] = no;
+        f[o] = glob_len[no];
+        pre[o] = pre_len ? pre_len[no] : 0;
+        loc[o] = loc_len[no];
+    }
+}
+
+// keys of the planned candidates of every query: position p < cum[J - 1] -> (segment, offset) -> id -> ADC.  grid (blocks, B)
+template <int M_T>
+__global__ void __launch_bounds__(RII_THREADS) k_ivf_keys(IvfArgs a, u64 *__restrict__ keys, long long stride, int *__restrict__ ncand)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    const int b = blockIdx.y;
+    load_lut(lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
+    __syncthreads();
     const int J = (a.flags[b] != 0) ? 0 : a.J[b];
-    int *s_warp = reinterpret_cast<int *>(s.tail);  // 8 warp counts + running base
-    load_lut(s.lut, a.T + (size_t)b * a.M * a.Ks, a.M * a.Ks);
-    s.tk.init();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int j = blockIdx.x; j < J; j += gridDim.x) {
-        const int no = a.ranked[(size_t)b * a.w_eff + j];
-        const long long beg = a.offsets[no];
-        const int len = (int)(a.offsets[no + 1] - beg);
-        const int limit = (j == J - 1) ? a.take_last[b] : 0x7fffffff;
-        int base = 0;  // members seen so far in this list (uniform across the CTA)
-        for (int pos = 0; pos < len && base < limit; pos += RII_THREADS) {
-            s.tk.reserve(RII_THREADS);
-            const uint32_t thr_hi = s.tk.thr_hi();
-            const u64 thr_key = s.tk.thr_key();
-            int i = pos + threadIdx.x;
-            int id = -1;
-            bool member = false;
-            if (i < len) {
-                id = __ldg(a.ids + beg + i);
-                member = (__ldg(a.bitmap + (id >> 5)) >> (id & 31)) & 1u;
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, member);
-            if (lane == 0) s_warp[wid] = __popc(bal);
-            __syncthreads();
-            int before = base + __popc(bal & ((1u << lane) - 1));
-            int tot = 0;
-            for (int w2 = 0; w2 < RII_THREADS / 32; ++w2) {
-                int c = s_warp[w2];
-                if (w2 < wid) before += c;
-                tot += c;
-            }
-            if (member && before < limit) {
-                float d = adc_row<M_T, false>(s.lut, a.Ks, a.M, a.codes + (size_t)id * a.M);
-                if (__float_as_uint(d) <= thr_hi) {
-                    u64 key = pack_key(d, (uint32_t)id);
-                    if (key < thr_key) s.tk.push(key);
-                }
-            }
-            base += tot;
-            __syncthreads();  // s_warp reused next iteration
+    const int *cum = a.cum + (size_t)b * a.w_eff, *ranked = a.ranked + (size_t)b * a.w_eff;
+    const int total = J ? cum[J - 1] : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ncand[b] = total;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = J - 1;  // first segment with cum > p
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] > p) hi = mid; else lo = mid + 1;
+        }
+        const int id = __ldg(a.ids + a.offsets[ranked[lo]] + (p - (lo ? cum[lo - 1] : 0)));
+        keys[(size_t)b * stride + p] = pack_key(adc_row<M_T, false>(lut, a.Ks, a.M, a.codes + (size_t)id * a.M), (uint32_t)id);
+    }
+}
+
+// out[i] = Q[idx[i]] (rows of D floats); and the way back for results
+__global__ void k_gather_queries(const float *__restrict__ Q, const int *__restrict__ idx, int n, int D, float *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * D) return;
+    out[i] = Q[(size_t)idx[i / D] * D + i % D];
+}
+__global__ void k_scatter_results(const int *__restrict__ idx, int n, int k, const long long *__restrict__ ids, const float *__restrict__ d,
+                                  const int *__restrict__ c, long long *__restrict__ out_ids, float *__restrict__ out_d, int *__restrict__ out_c)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * k) return;
+    const int r = (int)(i / k), j = (int)(i % k), b = idx[r];
+    if (j < c[r]) {
+        out_ids[(size_t)b * k + j] = ids[i];
+        out_d[(size_t)b * k + j] = d[i];
+    }
+    if (j == 0) out_c[b] = c[r];
+}
+
+// seg[b] = b * stride, seg_end[b] = b * stride + count[b] (count null: n)
+__global__ void k_seg_bounds(int B, long long stride, const int *__restrict__ count, long long n, long long *__restrict__ beg, long long *__restrict__ end)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    beg[b] = (long long)b * stride;
+    end[b] = (long long)b * stride + (count ? count[b] : n);
+}
+
+// the first min(k, valid) keys of every sorted segment -> outputs.  grid (blocks, B)
+__global__ void k_take_sorted(const u64 *__restrict__ sorted, long long stride, const int *__restrict__ count, long long n, int k, TopkOut out)
+{
+    const int b = blockIdx.y;
+    const long long c = count ? count[b] : n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k && i < c; i += gridDim.x * blockDim.x) {
+        const u64 key = sorted[(size_t)b * stride + i];
+        if (key != RII_KEY_MAX) {
+            out.out_ids[(size_t)b * k + i] = out.id_map ? out.id_map[key_id(key)] : out.id_base + (long long)key_id(key);
+            out.out_dists[(size_t)b * k + i] = key_dist(key);
         }
     }
-    emit_topk(s.tk, a.out, b, blockIdx.x, gridDim.x);
-}
-
-// membership bitmap over local ids from (sorted or unsorted) global target ids
-__global__ void k_bitmap_set(const long long *__restrict__ tids, long long S, long long id_base, long long N,
-                             uint32_t *bitmap)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    long long id = tids[i] - id_base;
-    if (id >= 0 && id < N) atomicOr(bitmap + (id >> 5), 1u << (id & 31));
-}
-
-// filtered length of every ranked list.  grid (w_eff, B)
-__global__ void __launch_bounds__(RII_THREADS) k_count_members(const long long *__restrict__ offsets,
-                                                               const int *__restrict__ ids,
-                                                               const int *__restrict__ ranked, int w_eff,
-                                                               const uint32_t *__restrict__ bitmap, int *filt_cnt)
-{
-    const int b = blockIdx.y, j = blockIdx.x;
-    const int no = ranked[(size_t)b * w_eff + j];
-    const long long beg = offsets[no];
-    const int len = (int)(offsets[no + 1] - beg);
-    int c = 0;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        int id = __ldg(ids + beg + i);
-        c += (__ldg(bitmap + (id >> 5)) >> (id & 31)) & 1u;
-    }
-    __shared__ int red[RII_THREADS / 32];
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < RII_THREADS / 32; ++i) t += red[i];
-        filt_cnt[(size_t)b * w_eff + j] = t;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // keys are ascending and RII_KEY_MAX pads: count = index of the first pad
+        long long lo = 0, hi = c < k ? c : k;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (sorted[(size_t)b * stride + mid] == RII_KEY_MAX) hi = mid; else lo = mid + 1;
+        }
+        out.out_counts[b] = (int)lo;
     }
 }
 

@@ -38,6 +38,6 @@ struct SortTmp { void *p = nullptr; size_t cap = 0; };   // grow-only temporary 
 int dev_sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, long long n,
                        int end_bit, SortTmp *tmp, cudaStream_t st);
 int dev_sort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, SortTmp *tmp, cudaStream_t st);
-// nseg segments [seg_off[i], seg_off[i + 1]) of u64 keys, each sorted ascending
-int dev_segsort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, int nseg, const long long *d_seg_off,
-                         SortTmp *tmp, cudaStream_t st);
+// nseg segments [seg_beg[i], seg_end[i]) of u64 keys, each sorted ascending
+int dev_segsort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, int nseg, const long long *d_seg_beg,
+                         const long long *d_seg_end, SortTmp *tmp, cudaStream_t st);

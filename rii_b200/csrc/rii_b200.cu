@@ -95,9 +95,9 @@ int host_l2_variant()
 int rii_fail(int code, const std::string &msg) { return fail(code, msg); }
 void rii_count_launch() { LAUNCHED(); }
 
-enum { PK_DTABLE = 0, PK_SCAN_LINEAR, PK_MERGE, PK_COARSE, PK_COUNT, PK_PLAN, PK_SCAN_IVF, PK_ASSIGN, PK_N };
-static const char *PK_NAMES[PK_N] = {"dtable", "scan_linear", "merge", "coarse_rank", "count_members", "plan",
-                                      "scan_ivf", "assign"};
+enum { PK_DTABLE = 0, PK_SCAN_LINEAR, PK_MERGE, PK_COARSE, PK_SUBSET, PK_PLAN, PK_SCAN_IVF, PK_ASSIGN, PK_SORT, PK_N };
+static const char *PK_NAMES[PK_N] = {"dtable", "scan_linear", "merge", "coarse_rank", "subset_build", "plan",
+                                      "scan_ivf", "assign", "sort"};
 struct ProfRec { int kind; cudaEvent_t a, b; };
 
 struct rii_index {
@@ -140,6 +140,13 @@ struct rii_index {
     // scratch (grow only)
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
         tmp2, tmp3;
+    // sub-index of a subset search (target_ids): (list, row) pairs, their sorted form = CSR of the members, skew64 copy
+    DevBuf sub_keys, sub_rows, sub_keys_s, sub_rows_s, sub_bounds, sub_len, sub_off, sub_skew, sub_glob, sub_pre;
+    long long sub_S = -1;     // two-phase sharded subset search: target count of the prepared sub-index (-1: none)
+    // general (global-memory) path: candidate keys and their sorted copy, segment bounds, candidate counts
+    DevBuf gen_keys, gen_sorted, gen_seg, gen_cnt;
+    // batched re-run of flagged queries
+    DevBuf redo_idx, redo_q, redo_ids, redo_d, redo_c;
 
     DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
     int opt_debug_clocks = 0;
@@ -553,274 +560,508 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
 }
 
 // ---- the query pipeline on device buffers -----------------------------------------------------------
-struct QueryCfg {
-    int topk;
-    long long S, L;
-    int method;
+// What a posting-list scan walks: the index's own lists, or the temporary sub-index of a subset search.
+struct ListsView {
+    const long long *offsets = nullptr;  // device CSR (nlist + 1)
+    const int *ids = nullptr;            // device: local row ids grouped by list, ascending per list
+    const int *loc_len = nullptr, *glob_len = nullptr, *pre_len = nullptr;  // device (nlist); pre_len null: single shard
+    const uint8_t *skew = nullptr;       // skew64 segment per list (streaming engine), or null
+    const long long *skew_off = nullptr;
+    long long cap_local = 0;             // upper bound of the ids listed locally
 };
 
-// phase (IVF + target_ids on a shard, SURVEY 8e "one exchange step"): 0 = the whole pipeline; 1 = stop after the
-// per-list member counts (left in h->filt, (B, w_eff)); 2 = resume from the plan with the all-shard counts `ext_glob` and
-// the lower ranks' counts `ext_pre` (both (B, w_eff) device int32)
-int run_chunk(rii_index *h, const float *d_Q, int B, const QueryCfg &c, const long long *d_tids, long long *d_out_ids,
-              float *d_out_dists, int *d_out_counts, cudaStream_t st, int w, int w_eff, bool *checked_flags, int phase = 0,
-              const int *ext_glob = nullptr, const int *ext_pre = nullptr)
+int make_tables(rii_index *h, const float *d_Q, int B, cudaStream_t st)  // K1 for the natural-layout / general kernels
+{
+    const int lutf = h->M * h->Ks;
+    CKR(h->T.ensure((size_t)B * lutf * 4));
+    Prof pr(h, st, PK_DTABLE);
+    dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
+    k_dtable<<<grid, RII_THREADS, 0, st>>>(d_Q, h->d_cw, h->T.as<float>(), h->M, h->Ks, h->Ds, h->variant);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_merge(rii_index *h, int B, int parts, int topk, TopkOut out, cudaStream_t st)
+{
+    const int mcap = next_pow2(topk + RII_THREADS);
+    const size_t msmem = scan_smem_bytes(0, mcap, 0);
+    CKR(set_smem(k_merge, msmem));
+    Prof pr(h, st, PK_MERGE);
+    k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, topk, mcap, out);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// sort nseg segments of `stride` slots each (the first count[b] / n of them are keys): long segments one by one with
+// the device-wide sort, short ones with the segmented sort (one CTA per segment)
+int sort_segments(rii_index *h, int nseg, long long stride, const int *d_count, long long n, cudaStream_t st)
+{
+    Prof pr(h, st, PK_SORT);
+    if (stride >= 32768 || nseg == 1) {
+        if (d_count) {  // sort the whole slot range: unused slots hold RII_KEY_MAX and stay at the end
+            for (int b = 0; b < nseg; ++b)
+                CKR(dev_sort_keys_u64(h->gen_keys.as<u64>() + (size_t)b * stride, h->gen_sorted.as<u64>() + (size_t)b * stride, stride, &h->sort_tmp, st));
+        } else {
+            for (int b = 0; b < nseg; ++b)
+                CKR(dev_sort_keys_u64(h->gen_keys.as<u64>() + (size_t)b * stride, h->gen_sorted.as<u64>() + (size_t)b * stride, n, &h->sort_tmp, st));
+        }
+        return 0;
+    }
+    CKR(h->gen_seg.ensure((size_t)nseg * 16));
+    long long *beg = h->gen_seg.as<long long>(), *end = beg + nseg;
+    k_seg_bounds<<<(nseg + 255) / 256, 256, 0, st>>>(nseg, stride, d_count, n, beg, end);
+    LAUNCHED();
+    return dev_segsort_keys_u64(h->gen_keys.as<u64>(), h->gen_sorted.as<u64>(), (long long)nseg * stride, nseg, beg, end, &h->sort_tmp, st);
+}
+
+// General linear scan: every candidate's (dist, id) key goes to HBM, a radix sort orders them (any M, any topk).
+int general_linear(rii_index *h, const float *d_Q, int B, int topk, const long long *d_tids, long long S, long long *d_out_ids,
+                   float *d_out_dists, int *d_out_counts, cudaStream_t st)
 {
     const int M = h->M, Ks = h->Ks, lutf = M * Ks;
-    // K1: the v2 scan kernels and the coarse kernel build their tables in-kernel from (Q, codewords); only the
-    // natural-layout (v1) scan kernels read tables from HBM, so k_dtable runs lazily.
-    bool have_T = false;
-    auto ensure_T = [&]() -> int {
-        if (have_T) return 0;
-        CKR(h->T.ensure((size_t)B * lutf * 4));
-        Prof pr(h, st, PK_DTABLE);
-        dim3 grid((lutf + RII_THREADS - 1) / RII_THREADS, B);
-        k_dtable<<<grid, RII_THREADS, 0, st>>>(d_Q, h->d_cw, h->T.as<float>(), M, Ks, h->Ds, h->variant);
-        LAUNCHED();
-        CK(cudaGetLastError());
-        have_T = true;
-        return 0;
-    };
-    const int round = RII_THREADS * RII_ROWS_PER_THREAD;
-    const int cap = next_pow2(c.topk + round);
-    TopkOut out{};
-    out.out_ids = d_out_ids;
-    out.out_dists = d_out_dists;
-    out.out_counts = d_out_counts;
-    out.id_base = h->id_base;
-    const int max_parts = std::max(1, 592 / B);
-    const long long per_cta = B >= 148 ? 8192 : 1024;
-
-    if (c.method == RII_METHOD_LINEAR) {
-        const long long ncand = c.S ? c.S : h->N;
-        int parts = (int)std::min<long long>(max_parts, std::max<long long>(1, (ncand + per_cta - 1) / per_cta));
-        out.final = parts == 1;
-        if (!out.final) {
-            CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
-            out.partial = h->partial.as<u64>();
-        }
+    const long long ncand = S ? S : h->N;
+    if ((size_t)lutf * 4 > SMEM_MAX) return fail(RII_ERR_LIMIT, "M * Ks * 4 bytes exceed the shared memory of a CTA");
+    const int Bc = (int)std::max<long long>(1, std::min<long long>(B, (1ll << 27) / std::max<long long>(1, ncand)));
+    CKR(h->gen_keys.ensure((size_t)Bc * ncand * 8));
+    CKR(h->gen_sorted.ensure((size_t)Bc * ncand * 8));
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = std::min(Bc, B - b0);
+        CKR(make_tables(h, d_Q + (size_t)b0 * M * h->Ds, bc, st));
         LinearArgs a{};
-        a.codes = h->d_codes;
-        a.tids = c.S ? d_tids : nullptr;
-        a.S = c.S;
-        a.N = h->N;
-        a.id_base = h->id_base;
-        a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
-        a.out = out;
-        const size_t smem = scan_smem_bytes(lutf, cap, 0);
-        // v2 (skewed, bank-conflict-free) for M == 32 full scans with enough rows per warp; v1 otherwise
-        const int capw = std::max(64, next_pow2(c.topk + 32));
-        int nw = 0, shape = 0;
-        size_t smem4 = 0;
-        if (h->rb) shape = stream_pick(h->rb, false, false, capw, 0, 0, &nw, &smem4);
-        const bool v2_ok = shape > 0 && c.S == 0 && c.topk <= SK_MAX_K;
-        const bool use_v2 = v2_ok && (h->opt_scan_kernel == 4 || (h->opt_scan_kernel == 0 && h->N >= (1ll << 21)));
-        if (h->opt_scan_kernel == 4 && !v2_ok) return fail(RII_ERR_LIMIT, "scan_kernel=4 needs 12 <= M <= 64, no target_ids and topk <= 224");
-        if (use_v2) {
-            parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
-                                             std::max<long long>(1, h->N / (nw * SK_TILE_ROWS * 4)));
-            out.final = parts == 1;
-            if (!out.final) {
-                CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
-                out.partial = h->partial.as<u64>();
-            }
-            SkewArgs sa{};
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
-            sa.codes = a.codes; sa.N = h->N; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw; sa.out = out;
-            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
-            sa.smem_bytes = SK_DYN_SMEM;
-            CKR(ensure_skew_lin(h, st));
-            sa.codes = h->skew_lin.as<uint8_t>();
-            Prof pr(h, st, PK_SCAN_LINEAR);
-            CKR(launch_stream(shape, false, sa, parts, B, smem4, st));
-        } else {
-            CKR(ensure_T());
-            a.T = h->T.as<float>();
+        a.T = h->T.as<float>(); a.codes = h->d_codes; a.tids = S ? d_tids : nullptr; a.S = S; a.N = h->N; a.id_base = h->id_base;
+        a.M = M; a.Ks = Ks;
+        const unsigned gx = (unsigned)std::min<long long>(1184, (ncand + RII_THREADS - 1) / RII_THREADS);
+        {
             Prof pr(h, st, PK_SCAN_LINEAR);
             DISPATCH_M(M, {
-                CKR(set_smem(k_scan_linear<MT>, smem));
-                k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+                CKR(set_smem(k_keys_linear<MT>, (size_t)lutf * 4));
+                k_keys_linear<MT><<<dim3(gx, bc), RII_THREADS, (size_t)lutf * 4, st>>>(a, h->gen_keys.as<u64>(), ncand);
             });
             LAUNCHED();
             CK(cudaGetLastError());
         }
+        CKR(sort_segments(h, bc, ncand, nullptr, ncand, st));
+        TopkOut out{};
+        out.out_ids = d_out_ids + (size_t)b0 * topk; out.out_dists = d_out_dists + (size_t)b0 * topk; out.out_counts = d_out_counts + b0;
+        out.id_base = h->id_base; out.final = 1;
+        k_take_sorted<<<dim3((topk + 255) / 256, bc), 256, 0, st>>>(h->gen_sorted.as<u64>(), ncand, nullptr, ncand, topk, out);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// K2/K3 (src/rii.h:195-242).  tids_state: 1 = ascending and inside this index, 0 = not, -1 = unknown (checked on the device)
+int run_linear(rii_index *h, const float *d_Q, int B, int topk, const long long *d_tids, long long S, int tids_state,
+               long long *d_out_ids, float *d_out_dists, int *d_out_counts, cudaStream_t st)
+{
+    const int M = h->M, Ks = h->Ks, lutf = M * Ks;
+    const long long ncand = S ? S : h->N;
+    TopkOut out{};
+    out.out_ids = d_out_ids; out.out_dists = d_out_dists; out.out_counts = d_out_counts; out.id_base = h->id_base;
+    // ---- streaming engine: the skew64 copy of the codes, or of the target rows (subset) ----
+    const int capw = std::max(64, next_pow2(topk + 32));
+    int nw = 0, shape = 0;
+    size_t smem4 = 0;
+    if (h->rb && topk <= SK_MAX_K && h->opt_scan_kernel != 1) shape = stream_pick(h->rb, false, false, capw, 0, 0, &nw, &smem4);
+    bool use4 = shape > 0 && (h->opt_scan_kernel == 4 || (S == 0 ? (h->N >= (1ll << 21) || (B >= 16 && h->N >= 65536)) : ncand * B >= (1ll << 22)));
+    long long i0 = 0, cnt = S;
+    if (use4 && S) {
+        if (tids_state < 0 || h->N_total >= 0) {  // ascending?  which run of it lies in this shard?
+            CKR(h->d_flag.ensure(32));
+            int *fl = h->d_flag.as<int>() + 4;
+            CK(cudaMemsetAsync(fl, 0, 12, st));
+            k_tids_scan<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(d_tids, S, h->id_base, h->id_base + h->N, fl);
+            LAUNCHED();
+            int hf[3];
+            CK(cudaMemcpyAsync(hf, fl, 12, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (tids_state < 0) tids_state = (hf[0] == 0 && (h->N_total >= 0 || hf[1] + hf[2] == 0)) ? 1 : 0;
+            i0 = hf[1];
+            cnt = S - hf[1] - hf[2];
+        }
+        if (tids_state != 1) use4 = false;
+    }
+    if (h->opt_scan_kernel == 4 && !use4) return fail(RII_ERR_LIMIT, "scan_kernel=4 needs 12 <= M <= 64, topk <= 224 and ascending target_ids");
+    if (use4) {
+        SkewArgs sa{};
+        sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
+        sa.Ks = Ks; sa.k = topk; sa.cap = capw;
+        if (S) {  // compact skew64 copy of the target rows (in the given order; repeated ids stay repeated, src/rii.h:222-227)
+            if (cnt <= 0) {  // nothing of the subset lives in this shard
+                CK(cudaMemsetAsync(d_out_counts, 0, (size_t)B * 4, st));
+                return 0;
+            }
+            Prof pr(h, st, PK_SUBSET);
+            const long long prows = skew64_rows(cnt, h->rb / 32);
+            CKR(h->sub_rows.ensure((size_t)cnt * 4));
+            CKR(h->sub_skew.ensure((size_t)prows * 32));
+            CKR(h->sub_off.ensure(32));
+            k_tids_to_rows<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_tids + i0, cnt, h->id_base, h->sub_rows.as<int>());
+            LAUNCHED();
+            const long long hoff[2] = {0, prows};
+            CK(cudaMemcpyAsync(h->sub_off.p, hoff, 16, cudaMemcpyHostToDevice, st));
+            CKR(skew_build(h->d_codes, h->sub_rows.as<int>(), nullptr, h->sub_off.as<long long>(), 1, cnt, prows, h->sub_skew.as<uint8_t>(),
+                           M, h->rb, st));
+            sa.codes = h->sub_skew.as<uint8_t>();
+            sa.N = cnt;
+            out.id_map = d_tids + i0;
+        } else {
+            CKR(ensure_skew_lin(h, st));
+            sa.codes = h->skew_lin.as<uint8_t>();
+            sa.N = h->N;
+        }
+        const int parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)), std::max<long long>(1, sa.N / (nw * SK_TILE_ROWS * 4)));
+        out.final = parts == 1;
         if (!out.final) {
-            const int mcap = next_pow2(c.topk + RII_THREADS);
-            const size_t msmem = scan_smem_bytes(0, mcap, 0);
-            CKR(set_smem(k_merge, msmem));
-            Prof pr(h, st, PK_MERGE);
-            k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
+            CKR(h->partial.ensure((size_t)B * parts * topk * 8));
+            out.partial = h->partial.as<u64>();
+        }
+        sa.out = out;
+        if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
+        {
+            Prof pr(h, st, PK_SCAN_LINEAR);
+            CKR(launch_stream(shape, false, sa, parts, B, smem4, st));
+        }
+        if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+        return 0;
+    }
+    // ---- natural-layout kernel: keys of the CTA in shared memory ----
+    const int cap = next_pow2(topk + RII_THREADS * RII_ROWS_PER_THREAD);
+    const size_t smem = scan_smem_bytes(lutf, cap, 0);
+    if (smem > SMEM_MAX) return general_linear(h, d_Q, B, topk, d_tids, S, d_out_ids, d_out_dists, d_out_counts, st);
+    const int max_parts = std::max(1, 592 / B);
+    const long long per_cta = B >= 148 ? 8192 : 1024;
+    const int parts = (int)std::min<long long>(max_parts, std::max<long long>(1, (ncand + per_cta - 1) / per_cta));
+    out.final = parts == 1;
+    if (!out.final) {
+        CKR(h->partial.ensure((size_t)B * parts * topk * 8));
+        out.partial = h->partial.as<u64>();
+    }
+    CKR(make_tables(h, d_Q, B, st));
+    LinearArgs a{};
+    a.T = h->T.as<float>(); a.codes = h->d_codes; a.tids = S ? d_tids : nullptr; a.S = S; a.N = h->N; a.id_base = h->id_base;
+    a.M = M; a.Ks = Ks; a.k = topk; a.cap = cap; a.out = out;
+    {
+        Prof pr(h, st, PK_SCAN_LINEAR);
+        DISPATCH_M(M, {
+            CKR(set_smem(k_scan_linear<MT>, smem));
+            k_scan_linear<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
+        });
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+    return 0;
+}
+
+int ensure_centers_skew(rii_index *h, cudaStream_t st);
+int ensure_skew_lists(rii_index *h, cudaStream_t st);
+
+int main_view(rii_index *h, cudaStream_t st, ListsView *v)
+{
+    if (h->rb && h->opt_scan_kernel != 1 && h->h_offsets.back() > 0) {
+        CKR(ensure_skew_lists(h, st));
+        v->skew = h->skew_lists.as<uint8_t>();
+        v->skew_off = h->skew_off.as<long long>();
+    }
+    v->offsets = h->offsets.as<long long>();
+    v->ids = h->ids.as<int>();
+    v->loc_len = h->loc_len.as<int>();
+    v->glob_len = h->has_global ? h->glob_len.as<int>() : h->loc_len.as<int>();
+    v->pre_len = h->has_global ? h->pre_len.as<int>() : nullptr;
+    v->cap_local = h->h_offsets.back();
+    return 0;
+}
+
+// Sub-index of a subset search (src/rii.h:294): the members of every posting list, ascending in id.  Device only, no
+// host round trip: the sizes are bounded by S.
+int build_subview(rii_index *h, const long long *d_tids, long long S, cudaStream_t st, ListsView *v)
+{
+    if (h->N_assigned != h->N)
+        return fail(RII_ERR_STATE, "subset search: codes were added without updating the posting lists (reconfigure or add with update)");
+    Prof pr(h, st, PK_SUBSET);
+    const int nlist = h->nlist, H = std::max(1, h->rb / 32);
+    CKR(h->sub_keys.ensure((size_t)S * 4));
+    CKR(h->sub_rows.ensure((size_t)S * 4));
+    CKR(h->sub_keys_s.ensure((size_t)S * 4));
+    CKR(h->sub_rows_s.ensure((size_t)S * 4));
+    CKR(h->sub_bounds.ensure((size_t)(nlist + 2) * 8));
+    CKR(h->sub_len.ensure((size_t)nlist * 4));
+    CKR(h->sub_off.ensure((size_t)(nlist + 2) * 8));
+    k_sub_keys<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(d_tids, S, h->id_base, h->N, h->assign.as<int>(), h->sub_keys.as<uint32_t>(),
+                                                            h->sub_rows.as<uint32_t>());
+    LAUNCHED();
+    int bits = 1;
+    while ((1ll << bits) <= nlist) ++bits;
+    CKR(dev_sort_pairs_u32(h->sub_keys.as<uint32_t>(), h->sub_keys_s.as<uint32_t>(), h->sub_rows.as<uint32_t>(), h->sub_rows_s.as<uint32_t>(), S,
+                           bits, &h->sort_tmp, st));
+    k_list_bounds<<<(nlist + 1 + 255) / 256, 256, 0, st>>>(h->sub_keys_s.as<uint32_t>(), S, nlist, h->sub_bounds.as<long long>());
+    LAUNCHED();
+    k_sub_layout<<<1, 1024, 0, st>>>(h->sub_bounds.as<long long>(), nlist, H, h->sub_len.as<int>(), h->sub_off.as<long long>());
+    LAUNCHED();
+    CK(cudaGetLastError());
+    v->offsets = h->sub_bounds.as<long long>();
+    v->ids = h->sub_rows_s.as<int>();
+    v->loc_len = v->glob_len = h->sub_len.as<int>();
+    v->pre_len = nullptr;
+    v->cap_local = std::min<long long>(S, h->N);
+    if (h->rb && h->opt_scan_kernel != 1) {
+        const long long cap_rows = (v->cap_local + 128ll * nlist) * H;  // every list: its groups + one drain group + rounding
+        CKR(h->sub_skew.ensure((size_t)cap_rows * 32));
+        CKR(skew_build(h->d_codes, v->ids, v->offsets, h->sub_off.as<long long>(), nlist, 0, cap_rows, h->sub_skew.as<uint8_t>(), h->M, h->rb, st));
+        v->skew = h->sub_skew.as<uint8_t>();
+        v->skew_off = h->sub_off.as<long long>();
+    }
+    return 0;
+}
+
+// General posting-list search through HBM: coarse keys -> sort -> plan -> candidate keys -> sort -> top-k.
+int general_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const ListsView &v, int w, int w_eff, long long *d_out_ids,
+                float *d_out_dists, int *d_out_counts, cudaStream_t st)
+{
+    const int M = h->M, Ks = h->Ks, lutf = M * Ks, nlist = h->nlist;
+    if ((size_t)lutf * 4 > SMEM_MAX) return fail(RII_ERR_LIMIT, "M * Ks * 4 bytes exceed the shared memory of a CTA");
+    const long long lcap = std::max<long long>(1, std::min<long long>(L, v.cap_local));
+    const long long stride = std::max<long long>(nlist, lcap);
+    const int Bc = (int)std::max<long long>(1, std::min<long long>(B, (1ll << 27) / stride));
+    CKR(h->gen_keys.ensure((size_t)Bc * stride * 8));
+    CKR(h->gen_sorted.ensure((size_t)Bc * stride * 8));
+    CKR(h->gen_cnt.ensure((size_t)Bc * 4));
+    CKR(h->filt.ensure((size_t)Bc * w_eff * 4 * 3));
+    int *f = h->filt.as<int>(), *pre = f + (size_t)Bc * w_eff, *loc = pre + (size_t)Bc * w_eff;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = std::min(Bc, B - b0);
+        CKR(make_tables(h, d_Q + (size_t)b0 * M * h->Ds, bc, st));
+        {
+            Prof pr(h, st, PK_COARSE);
+            const unsigned gx = (unsigned)std::min(296, (nlist + RII_THREADS - 1) / RII_THREADS);
+            DISPATCH_M(M, {
+                CKR(set_smem(k_coarse_keys<MT>, (size_t)lutf * 4));
+                k_coarse_keys<MT><<<dim3(gx, bc), RII_THREADS, (size_t)lutf * 4, st>>>(h->T.as<float>(), h->centers.as<uint8_t>(), nlist, M, Ks,
+                                                                                     h->gen_keys.as<u64>());
+            });
             LAUNCHED();
             CK(cudaGetLastError());
         }
-        return 0;
+        CKR(sort_segments(h, bc, nlist, nullptr, nlist, st));
+        PlanArgs p{};
+        p.glob_len = v.glob_len; p.pre_len = v.pre_len; p.loc_len = v.loc_len;
+        p.filt_cnt = f; p.filt_pre = v.pre_len ? pre : nullptr; p.filt_loc = loc;
+        p.L = L; p.topk = topk; p.w = w; p.w_eff = w_eff; p.nlist = nlist;
+        p.ranked = h->ranked.as<int>() + (size_t)b0 * w_eff; p.cum = h->cum.as<int>() + (size_t)b0 * w_eff;
+        p.take_last = h->take_last.as<int>() + b0; p.J = h->J.as<int>() + b0; p.flags = h->flags.as<int>() + b0;
+        {
+            Prof pr(h, st, PK_PLAN);
+            k_rank_gather<<<dim3((w_eff + 255) / 256, bc), 256, 0, st>>>(h->gen_sorted.as<u64>(), nlist, w_eff, v.glob_len, v.pre_len, v.loc_len, p.ranked,
+                                                                        f, pre, loc);
+            LAUNCHED();
+            k_plan<<<(bc + 127) / 128, 128, 0, st>>>(p, bc);
+            LAUNCHED();
+            CK(cudaGetLastError());
+        }
+        IvfArgs a{};
+        a.T = h->T.as<float>(); a.codes = h->d_codes; a.offsets = v.offsets; a.ids = v.ids;
+        a.ranked = p.ranked; a.cum = p.cum; a.J = p.J; a.flags = p.flags; a.take_last = p.take_last; a.w_eff = w_eff;
+        a.M = M; a.Ks = Ks; a.k = topk;
+        {
+            Prof pr(h, st, PK_SCAN_IVF);
+            CK(cudaMemsetAsync(h->gen_keys.p, 0xff, (size_t)bc * lcap * 8, st));  // unused slots = RII_KEY_MAX
+            const unsigned gx = (unsigned)std::min<long long>(1184, (lcap + RII_THREADS - 1) / RII_THREADS);
+            DISPATCH_M(M, {
+                CKR(set_smem(k_ivf_keys<MT>, (size_t)lutf * 4));
+                k_ivf_keys<MT><<<dim3(gx, bc), RII_THREADS, (size_t)lutf * 4, st>>>(a, h->gen_keys.as<u64>(), lcap, h->gen_cnt.as<int>());
+            });
+            LAUNCHED();
+            CK(cudaGetLastError());
+        }
+        CKR(sort_segments(h, bc, lcap, h->gen_cnt.as<int>(), lcap, st));
+        TopkOut out{};
+        out.out_ids = d_out_ids + (size_t)b0 * topk; out.out_dists = d_out_dists + (size_t)b0 * topk; out.out_counts = d_out_counts + b0;
+        out.id_base = h->id_base; out.final = 1;
+        k_take_sorted<<<dim3((topk + 255) / 256, bc), 256, 0, st>>>(h->gen_sorted.as<u64>(), lcap, h->gen_cnt.as<int>(), lcap, topk, out);
+        LAUNCHED();
+        CK(cudaGetLastError());
     }
+    return 0;
+}
 
-    // ---- IVF ----
-    const bool subset = c.S != 0;
+// K4 + K5 (src/rii.h:244-326) over `v`.  mode 0: the whole search; 1: coarse ranking only -> d_ranked (B, w_eff);
+// 2: scan with the given ranking d_ranked.  The per-query plan flags are left in h->flags (B).
+int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const ListsView &v, int w, int w_eff, long long *d_out_ids,
+            float *d_out_dists, int *d_out_counts, cudaStream_t st, int mode = 0, int *d_ranked = nullptr)
+{
+    const int M = h->M, Ks = h->Ks, lutf = M * Ks, nlist = h->nlist;
     CKR(h->ranked.ensure((size_t)B * w_eff * 4));
     CKR(h->cum.ensure((size_t)B * w_eff * 4));
     CKR(h->take_last.ensure((size_t)B * 4));
     CKR(h->J.ensure((size_t)B * 4));
     CKR(h->flags.ensure((size_t)B * 4));
     PlanArgs p{};
-    p.glob_len = h->has_global ? h->glob_len.as<int>() : h->loc_len.as<int>();
-    p.pre_len = h->has_global ? h->pre_len.as<int>() : nullptr;
-    p.loc_len = h->loc_len.as<int>();
-    p.filt_cnt = nullptr;
-    p.L = c.L;
-    p.topk = c.topk;
-    p.w = w;
-    p.w_eff = w_eff;
-    p.nlist = h->nlist;
-    p.ranked = h->ranked.as<int>();
-    p.cum = h->cum.as<int>();
-    p.take_last = h->take_last.as<int>();
-    p.J = h->J.as<int>();
-    p.flags = h->flags.as<int>();
-    if (subset && phase != 2) {
-        const size_t words = (size_t)(h->N + 31) / 32 + 1;
-        CKR(h->bitmap.ensure(words * 4));
-        CK(cudaMemsetAsync(h->bitmap.p, 0, words * 4, st));
-        k_bitmap_set<<<(unsigned)((c.S + 255) / 256), 256, 0, st>>>(d_tids, c.S, h->id_base, h->N, h->bitmap.as<uint32_t>());
-        LAUNCHED();
-        CKR(h->filt.ensure((size_t)B * w_eff * 4));
+    p.glob_len = v.glob_len; p.pre_len = v.pre_len; p.loc_len = v.loc_len;
+    p.L = L; p.topk = topk; p.w = w; p.w_eff = w_eff; p.nlist = nlist;
+    p.ranked = d_ranked ? d_ranked : h->ranked.as<int>();
+    p.cum = h->cum.as<int>(); p.take_last = h->take_last.as<int>(); p.J = h->J.as<int>(); p.flags = h->flags.as<int>();
+    TopkOut out{};
+    out.out_ids = d_out_ids; out.out_dists = d_out_dists; out.out_counts = d_out_counts; out.id_base = h->id_base;
+
+    // ---- streaming engine.  nlist <= 1024: every coarse distance stays in shared memory (any w_eff); larger nlist: the
+    // warps' top-k lists rank the centers and must hold max(topk, w_eff) keys
+    const bool big_nlist = nlist > 1024;
+    const int capw = std::max(64, next_pow2((big_nlist ? std::max(topk, w_eff) : topk) + 32));
+    const size_t pool = !big_nlist ? (size_t)nlist * 4 : 0;
+    bool use4 = h->rb && v.skew && topk <= SK_MAX_K && (!big_nlist || w_eff <= SK_MAX_K) && h->opt_scan_kernel != 1;
+    int nw = 0, shape = 0, nw_c = 0, shape_c = 0;
+    size_t smem4 = 0, smem_c = 0;
+    const bool two = B >= 148 && h->opt_stream_ctas != 1;
+    if (use4) {
+        shape_c = stream_pick(h->rb, true, two, capw, w_eff, pool, &nw_c, &smem_c);  // with the coarse pass
+        shape = stream_pick(h->rb, true, two, std::max(64, next_pow2(topk + 32)), w_eff, 0, &nw, &smem4);  // scan only
+        use4 = shape > 0 && shape_c > 0;
     }
-    // v2 (skewed, bank-conflict-free) posting-list scan when it applies: M == 32, no target_ids, small topk, plan
-    // fits shared memory.  With one CTA per query (parts == 1) the coarse ranking and the plan are fused into the
-    // same kernel (two passes of one engine): no k_coarse_rank launch at all.
-    // (v4 with nlist > 1024 ranks the centers in the warps' top-k lists: they must hold max(topk, w_eff) keys)
-    const bool big_nlist = h->nlist > 1024;
-    const int capw2 = std::max(64, next_pow2((big_nlist ? std::max(c.topk, w_eff) : c.topk) + 32));
-    int nw2 = 0, shape2 = 0;
-    size_t smem42 = 0;
-    // (the fused coarse pass keeps nlist distances in shared memory: sized for it whenever fusing is possible)
-    const size_t pool4 = h->opt_fuse_coarse && !big_nlist ? (size_t)h->nlist * 4 : 0;
-    if (h->rb) shape2 = stream_pick(h->rb, true, B >= 148 && h->opt_stream_ctas != 1, capw2, w_eff, pool4, &nw2, &smem42);
-    const bool v2_ok = shape2 > 0 && !subset && c.topk <= SK_MAX_K && w_eff <= SK_MAX_K && h->h_offsets.back() > 0;
-    const bool use_v2 = v2_ok && h->opt_scan_kernel != 1;
-    if (h->opt_scan_kernel == 4 && !v2_ok && !subset) return fail(RII_ERR_LIMIT, "scan_kernel=4 (ivf) needs 12 <= M <= 64, topk <= 224 and a short list plan");
-    const int parts_v2 = use_v2 ? (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
-                                                           std::max<long long>(1, (c.L + nw2 * SK_TILE_ROWS - 1) / (nw2 * SK_TILE_ROWS)))
-                                : 0;
-    // fused coarse pass: the nlist distances live in the (idle) per-warp key buffers, the worst-case full sort in the regions
-    const bool fuse = use_v2 && parts_v2 == 1 && h->opt_fuse_coarse;
-    if (use_v2) {
-        CKR(ensure_skew_lists(h, st));
-        if (fuse) CKR(ensure_centers_skew(h, st));
+    if (h->opt_scan_kernel == 4 && !use4) return fail(RII_ERR_LIMIT, "scan_kernel=4 (ivf) needs 12 <= M <= 64, topk <= 224 and a list plan that fits shared memory");
+    if (!use4 && mode != 0) return fail(RII_ERR_LIMIT, "the split coarse / scan phases need the streaming engine (12 <= M <= 64, topk <= 224)");
+    if (use4) {
+        int parts = mode == 1 ? 1 : (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
+                                                            std::max<long long>(1, (L + nw * SK_TILE_ROWS - 1) / (nw * SK_TILE_ROWS)));
+        const bool fuse = mode == 0 && parts == 1 && h->opt_fuse_coarse;
+        SkewArgs sa{};
+        sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
+        sa.codes = v.skew; sa.offsets = v.offsets; sa.ids = v.ids; sa.skew_off = v.skew_off;
+        sa.w_eff = w_eff; sa.Ks = Ks; sa.k = topk; sa.nlist = nlist; sa.plan = p;
+        if (fuse || mode == 1 || mode == 0) CKR(ensure_centers_skew(h, st));
+        if (fuse) {
+            sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; sa.coarse_mode = 0;
+            sa.cap = capw; out.final = 1; sa.out = out;
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)B * 64)); sa.dbg = h->dbg.as<long long>(); }
+            Prof pr(h, st, PK_SCAN_IVF);
+            return launch_stream(shape_c, true, sa, 1, B, smem_c, st);
+        }
+        if (mode != 2) {  // coarse pass on its own: one CTA per query ranks the lists
+            SkewArgs sc = sa;
+            sc.centers = h->centers_skew.as<uint8_t>(); sc.coarse_lists = big_nlist ? 1 : 0; sc.coarse_mode = 1; sc.cap = capw;
+            Prof pr(h, st, PK_COARSE);
+            CKR(launch_stream(shape_c, true, sc, 1, B, smem_c, st));
+            if (mode == 1) return 0;
+        }
+        sa.centers = nullptr; sa.coarse_mode = 2; sa.cap = std::max(64, next_pow2(topk + 32));
+        out.final = parts == 1;
+        if (!out.final) {
+            CKR(h->partial.ensure((size_t)B * parts * topk * 8));
+            out.partial = h->partial.as<u64>();
+        }
+        sa.out = out;
+        if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
+        {
+            Prof pr(h, st, PK_SCAN_IVF);
+            CKR(launch_stream(shape, true, sa, parts, B, smem4, st));
+        }
+        if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+        return 0;
     }
-    if (!fuse && phase != 2) {
+    // ---- natural-layout kernels: coarse keys and candidate keys of a CTA in shared memory ----
+    const int cap = next_pow2(topk + RII_THREADS * RII_ROWS_PER_THREAD);
+    const int ccap = next_pow2(w_eff + RII_THREADS);
+    const size_t smem_coarse = scan_smem_bytes(lutf, ccap, (size_t)w_eff * 12), smem_scan = scan_smem_bytes(lutf, cap, (size_t)w_eff * 8);
+    if (smem_coarse > SMEM_MAX || smem_scan > SMEM_MAX)
+        return general_ivf(h, d_Q, B, topk, L, v, w, w_eff, d_out_ids, d_out_dists, d_out_counts, st);
+    {
         CoarseArgs a{};
         a.T = nullptr; a.Q = d_Q; a.cw = h->d_cw; a.Ds = h->Ds; a.variant = h->variant;
         a.centers = h->centers.as<uint8_t>();
-        a.M = M; a.Ks = Ks; a.nlist = h->nlist;
-        a.cap = next_pow2(w_eff + RII_THREADS);
-        a.do_plan = subset ? 0 : 1;
-        a.plan = p;
-        const size_t smem = scan_smem_bytes(lutf, a.cap, (size_t)w_eff * 12);
+        a.M = M; a.Ks = Ks; a.nlist = nlist; a.cap = ccap; a.do_plan = 1; a.plan = p;
         Prof pr(h, st, PK_COARSE);
         DISPATCH_M(M, {
-            CKR(set_smem(k_coarse_rank<MT>, smem));
-            k_coarse_rank<MT><<<B, RII_THREADS, smem, st>>>(a);
+            CKR(set_smem(k_coarse_rank<MT>, smem_coarse));
+            k_coarse_rank<MT><<<B, RII_THREADS, smem_coarse, st>>>(a);
         });
         LAUNCHED();
         CK(cudaGetLastError());
     }
-    if (subset) {
-        if (phase != 2) {
-            Prof pr(h, st, PK_COUNT);
-            k_count_members<<<dim3(w_eff, B), RII_THREADS, 0, st>>>(h->offsets.as<long long>(), h->ids.as<int>(), p.ranked, w_eff,
-                                                                      h->bitmap.as<uint32_t>(), h->filt.as<int>());
-            LAUNCHED();
-        }
-        if (phase == 1) {
-            CK(cudaGetLastError());
-            return 0;
-        }
-        p.filt_cnt = phase == 2 ? ext_glob : h->filt.as<int>();
-        p.filt_pre = phase == 2 ? ext_pre : nullptr;
-        p.filt_loc = phase == 2 ? h->filt.as<int>() : nullptr;
-        {
-            Prof pr(h, st, PK_PLAN);
-            k_plan<<<(B + 127) / 128, 128, 0, st>>>(p, B);
-        }
+    const int max_parts = std::max(1, 592 / B);
+    const long long per_cta = B >= 148 ? 8192 : 1024;
+    const int parts = (int)std::min<long long>(max_parts, std::max<long long>(1, (L + per_cta - 1) / per_cta));
+    out.final = parts == 1;
+    if (!out.final) {
+        CKR(h->partial.ensure((size_t)B * parts * topk * 8));
+        out.partial = h->partial.as<u64>();
+    }
+    CKR(make_tables(h, d_Q, B, st));
+    IvfArgs a{};
+    a.T = h->T.as<float>(); a.codes = h->d_codes; a.offsets = v.offsets; a.ids = v.ids;
+    a.ranked = p.ranked; a.cum = p.cum; a.J = p.J; a.flags = p.flags; a.take_last = p.take_last; a.w_eff = w_eff;
+    a.M = M; a.Ks = Ks; a.k = topk; a.cap = cap; a.out = out;
+    {
+        Prof pr(h, st, PK_SCAN_IVF);
+        DISPATCH_M(M, {
+            CKR(set_smem(k_scan_ivf<MT>, smem_scan));
+            k_scan_ivf<MT><<<dim3(parts, B), RII_THREADS, smem_scan, st>>>(a);
+        });
         LAUNCHED();
         CK(cudaGetLastError());
     }
-    {
-        int parts = subset ? std::min(max_parts, std::max(1, w_eff))
-                           : (int)std::min<long long>(max_parts, std::max<long long>(1, (c.L + per_cta - 1) / per_cta));
-        out.final = parts == 1;
-        if (!out.final) {
-            CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
-            out.partial = h->partial.as<u64>();
+    if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+    return 0;
+}
+
+// src/rii.h:267-277
+int ivf_width(const rii_index *h, long long S, long long L)
+{
+    size_t ww = (size_t)std::round((double)L * h->nlist / (double)(S == 0 ? h->n_total() : S));
+    ww += 3;
+    if ((size_t)h->nlist < ww) ww = h->nlist;
+    return (int)ww;
+}
+
+// IVF over `v` for B queries, in chunks; queries whose plan comes back flagged 1 (fewer than topk candidates in the
+// first w lists: the reference walks on through ALL lists, src/rii.h:309-322) are gathered and re-run as one
+// batch with the full ranking.  d_flags_out (optional): the final flags (bit 1: empty result).
+int ivf_batches(rii_index *h, const float *d_Q, int B, int topk, long long L, const ListsView &v, int w, bool may_flag,
+                long long *d_out_ids, float *d_out_dists, int *d_out_counts, cudaStream_t st)
+{
+    const int D = h->M * h->Ds;
+    const int CH = 32768;  // queries per launch: long grids keep the tail (last partial wave of CTAs) small
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int bc = std::min(CH, B - b0);
+        CKR(run_ivf(h, d_Q + (size_t)b0 * D, bc, topk, L, v, w, w, d_out_ids + (size_t)b0 * topk, d_out_dists + (size_t)b0 * topk,
+                    d_out_counts + b0, st));
+        if (!may_flag || w >= h->nlist) continue;
+        std::vector<int> flags(bc);
+        CK(cudaMemcpyAsync(flags.data(), h->flags.p, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<int> redo;
+        for (int i = 0; i < bc; ++i)
+            if (flags[i] & 1) redo.push_back(b0 + i);
+        if (redo.empty()) continue;
+        const int nr = (int)redo.size();
+        CKR(h->redo_idx.ensure((size_t)nr * 4));
+        CKR(h->redo_q.ensure((size_t)nr * D * 4));
+        CKR(h->redo_ids.ensure((size_t)nr * topk * 8));
+        CKR(h->redo_d.ensure((size_t)nr * topk * 4));
+        CKR(h->redo_c.ensure((size_t)nr * 4));
+        CK(cudaMemcpyAsync(h->redo_idx.p, redo.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+        k_gather_queries<<<(unsigned)(((long long)nr * D + 255) / 256), 256, 0, st>>>(d_Q, h->redo_idx.as<int>(), nr, D, h->redo_q.as<float>());
+        LAUNCHED();
+        CK(cudaStreamSynchronize(st));  // (redo is a host vector read by the async copy above)
+        const int RC = 2048;
+        for (int r0 = 0; r0 < nr; r0 += RC) {
+            const int rc = std::min(RC, nr - r0);
+            CKR(run_ivf(h, h->redo_q.as<float>() + (size_t)r0 * D, rc, topk, L, v, w, h->nlist, h->redo_ids.as<long long>() + (size_t)r0 * topk,
+                        h->redo_d.as<float>() + (size_t)r0 * topk, h->redo_c.as<int>() + r0, st));
         }
-        IvfArgs a{};
-        a.codes = h->d_codes;
-        a.offsets = h->offsets.as<long long>();
-        a.ids = h->ids.as<int>();
-        a.ranked = p.ranked; a.cum = p.cum; a.J = p.J; a.flags = p.flags; a.take_last = p.take_last;
-        a.bitmap = subset ? h->bitmap.as<uint32_t>() : nullptr;
-        a.w_eff = w_eff;
-        a.M = M; a.Ks = Ks; a.k = c.topk; a.cap = cap;
-        a.out = out;
-        SkewArgs sa{};
-        if (use_v2) {
-            parts = parts_v2;
-            out.final = parts == 1;
-            if (!out.final) {
-                CKR(h->partial.ensure((size_t)B * parts * c.topk * 8));
-                out.partial = h->partial.as<u64>();
-            }
-            sa.T = nullptr; sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
-            sa.codes = h->skew_lists.as<uint8_t>(); sa.offsets = a.offsets; sa.ids = a.ids; sa.ranked = a.ranked; sa.cum = a.cum;
-            sa.J = a.J; sa.flags = a.flags; sa.w_eff = w_eff; sa.Ks = Ks; sa.k = c.topk; sa.cap = capw2; sa.out = out;
-            if (fuse) { sa.centers = h->centers.as<uint8_t>(); sa.nlist = h->nlist; sa.plan = p; }
-            sa.skew_off = h->skew_off.as<long long>();
-            if (fuse) { sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; }
-            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
-        }
-        if (!use_v2) {
-            CKR(ensure_T());
-            a.T = h->T.as<float>();
-        }
-        {
-        Prof pr(h, st, PK_SCAN_IVF);
-        if (use_v2) {
-            sa.smem_bytes = SK_DYN_SMEM;
-            CKR(launch_stream(shape2, true, sa, parts, B, smem42, st));
-        } else if (subset) {
-            const size_t smem = scan_smem_bytes(lutf, cap, 64);
-            DISPATCH_M(M, {
-                CKR(set_smem(k_scan_ivf_subset<MT>, smem));
-                k_scan_ivf_subset<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
-            });
-        } else {
-            const size_t smem = scan_smem_bytes(lutf, cap, (size_t)w_eff * 8);
-            DISPATCH_M(M, {
-                CKR(set_smem(k_scan_ivf<MT>, smem));
-                k_scan_ivf<MT><<<dim3(parts, B), RII_THREADS, smem, st>>>(a);
-            });
-        }
-        }
-        if (!use_v2) LAUNCHED();
+        k_scatter_results<<<(unsigned)(((long long)nr * topk + 255) / 256), 256, 0, st>>>(h->redo_idx.as<int>(), nr, topk, h->redo_ids.as<long long>(),
+                                                                                          h->redo_d.as<float>(), h->redo_c.as<int>(), d_out_ids,
+                                                                                          d_out_dists, d_out_counts);
+        LAUNCHED();
         CK(cudaGetLastError());
-        if (!out.final) {
-            const int mcap = next_pow2(c.topk + RII_THREADS);
-            const size_t msmem = scan_smem_bytes(0, mcap, 0);
-            CKR(set_smem(k_merge, msmem));
-            Prof pr(h, st, PK_MERGE);
-            k_merge<<<B, RII_THREADS, msmem, st>>>(h->partial.as<u64>(), parts, c.topk, mcap, out);
-            LAUNCHED();
-            CK(cudaGetLastError());
-        }
     }
-    if (checked_flags) *checked_flags = true;
     return 0;
 }
 
 int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *d_tids, long long S, long long L,
-              int method, long long *d_out_ids, float *d_out_dists, int *d_out_counts, cudaStream_t st)
+              int method, long long *d_out_ids, float *d_out_dists, int *d_out_counts, cudaStream_t st, int tids_state = -1)
 {
     if (B <= 0) return 0;
     if (h->N <= 0 && h->n_total() <= 0) return fail(RII_ERR_STATE, "query on an empty index");
@@ -829,50 +1070,41 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
     const long long Ntot = h->n_total();
     if (S < 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 <= len(target_ids) <= N");            // src/rii.h:220
     if ((long long)topk > (S ? S : Ntot)) return fail(RII_ERR_ARG, "need topk <= N (and topk <= len(target_ids))");  // :200,:219
-    QueryCfg c{topk, S, L, method};
-    int w = 0, w_eff = 0;
-    bool may_flag = false;
-    if (method == RII_METHOD_IVF) {
-        if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
-        if (h->N_total >= 0 && h->N_total != h->N && !h->has_global)
-            return fail(RII_ERR_STATE, "IVF query on a shard whose list lengths were not exchanged: call rii_set_global_lengths");
-        if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");           // src/rii.h:251
-        // src/rii.h:267-277
-        size_t ww = (size_t)std::round((double)L * h->nlist / (double)(S == 0 ? Ntot : S));
-        ww += 3;
-        if ((size_t)h->nlist < ww) ww = h->nlist;
-        w = w_eff = (int)ww;
-        // can sum of the first w ranked lists fall short of topk?  (only then the walk continues beyond w)
-        may_flag = S != 0 || (w < h->nlist && h->len_sorted_prefix.size() > (size_t)w && h->len_sorted_prefix[w] < topk &&
-                              h->len_sorted_prefix[w] < L);
-        if (S != 0 && h->has_global)
-            return fail(RII_ERR_STATE, "IVF + target_ids on a shard needs the per-list counts of the other shards: use "
-                                       "rii_ivf_subset_counts_dev / rii_ivf_subset_scan_dev (rii_b200.sharded.sharded_query_subset)");
-    } else if (method != RII_METHOD_LINEAR) {
-        return fail(RII_ERR_ARG, "unknown method");
-    }
+    if (S > 0 && !d_tids) return fail(RII_ERR_ARG, "target_ids is null but S > 0");
     const int D = h->M * h->Ds;
-    const int CH = 32768;  // queries per launch: long grids keep the tail (last partial wave of CTAs) small
-    for (int b0 = 0; b0 < B; b0 += CH) {
-        const int bc = std::min(CH, B - b0);
-        bool ran_ivf = false;
-        CKR(run_chunk(h, d_Q + (size_t)b0 * D, bc, c, d_tids, d_out_ids + (size_t)b0 * topk, d_out_dists + (size_t)b0 * topk,
-                      d_out_counts + b0, st, w, w_eff, &ran_ivf));
-        if (method == RII_METHOD_IVF && may_flag && w < h->nlist) {
-            // SURVEY A.3, 3rd bullet: fewer than topk candidates in the first w lists -> the reference walks on
-            // through the remaining lists.  Re-run exactly those queries with the full (dist, id) ranking.
-            std::vector<int> flags(bc);
-            CK(cudaMemcpyAsync(flags.data(), h->flags.p, (size_t)bc * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            for (int i = 0; i < bc; ++i) {
-                if (!(flags[i] & 1)) continue;
-                bool dummy;
-                CKR(run_chunk(h, d_Q + (size_t)(b0 + i) * D, 1, c, d_tids, d_out_ids + (size_t)(b0 + i) * topk,
-                              d_out_dists + (size_t)(b0 + i) * topk, d_out_counts + b0 + i, st, w, h->nlist, &dummy));
-            }
+    if (method == RII_METHOD_LINEAR) {
+        if (h->N <= 0) {  // an empty shard of a larger index
+            CK(cudaMemsetAsync(d_out_counts, 0, (size_t)B * 4, st));
+            return 0;
         }
+        const int CH = 32768;
+        for (int b0 = 0; b0 < B; b0 += CH) {
+            const int bc = std::min(CH, B - b0);
+            CKR(run_linear(h, d_Q + (size_t)b0 * D, bc, topk, d_tids, S, tids_state, d_out_ids + (size_t)b0 * topk, d_out_dists + (size_t)b0 * topk,
+                           d_out_counts + b0, st));
+        }
+        return 0;
     }
-    return 0;
+    if (method != RII_METHOD_IVF) return fail(RII_ERR_ARG, "unknown method");
+    if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
+    if (h->N_total >= 0 && h->N_total != h->N && !h->has_global)
+        return fail(RII_ERR_STATE, "IVF query on a shard whose list lengths were not exchanged: call rii_set_global_lengths");
+    if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");           // src/rii.h:251
+    const int w = ivf_width(h, S, L);
+    ListsView v;
+    bool may_flag;
+    if (S != 0) {
+        if (h->has_global)
+            return fail(RII_ERR_STATE, "IVF + target_ids on a shard needs the member counts of the other shards: use rii_subset_begin_dev / "
+                                       "rii_subset_set_global_dev / rii_subset_query_dev (rii_b200.sharded.sharded_query_subset)");
+        CKR(build_subview(h, d_tids, S, st, &v));
+        may_flag = true;
+    } else {
+        CKR(main_view(h, st, &v));
+        // can the first w ranked lists hold fewer than topk candidates?  (only then the walk continues beyond w)
+        may_flag = w < h->nlist && h->len_sorted_prefix.size() > (size_t)w && h->len_sorted_prefix[w] < topk && h->len_sorted_prefix[w] < L;
+    }
+    return ivf_batches(h, d_Q, B, topk, L, v, w, may_flag, d_out_ids, d_out_dists, d_out_counts, st);
 }
 
 int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tids, int64_t S, int64_t L, int method,
@@ -889,16 +1121,21 @@ int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tid
     CKR(h->o_dists.ensure((size_t)B * topk * 4));
     CKR(h->o_counts.ensure((size_t)B * 4));
     CK(cudaMemcpyAsync(h->q.p, Q, (size_t)B * D * 4, cudaMemcpyHostToDevice, st));
+    int tids_state = -1;
     if (S > 0) {
-        if (h->N_total < 0) {  // single shard: the reference indexes codes[tid] unchecked (src/rii.h:225); we refuse
-            for (int64_t i = 0; i < S; ++i)
-                if (tids[i] < 0 || tids[i] >= h->N) return fail(RII_ERR_ARG, "target_ids contains an id outside [0, N)");
+        // one pass over the host ids: the reference indexes codes[tid] unchecked (src/rii.h:225), we refuse ids outside the
+        // index; ascending ids (what Rii.query passes, rii/rii.py:296) take the streaming engine
+        bool asc = true;
+        for (int64_t i = 0; i < S; ++i) {
+            if (h->N_total < 0 && (tids[i] < 0 || tids[i] >= h->N)) return fail(RII_ERR_ARG, "target_ids contains an id outside [0, N)");
+            if (i && tids[i - 1] > tids[i]) asc = false;
         }
+        tids_state = asc ? 1 : 0;
         CKR(h->tids.ensure((size_t)S * 8));
         CK(cudaMemcpyAsync(h->tids.p, tids, (size_t)S * 8, cudaMemcpyHostToDevice, st));
     }
     CKR(query_dev(h, h->q.as<float>(), B, topk, h->tids.as<long long>(), S, L, method, h->o_ids.as<long long>(),
-                  h->o_dists.as<float>(), h->o_counts.as<int>(), st));
+                  h->o_dists.as<float>(), h->o_counts.as<int>(), st, tids_state));
     CK(cudaMemcpyAsync(out_ids, h->o_ids.p, (size_t)B * topk * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_dists, h->o_dists.p, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_counts, h->o_counts.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
@@ -956,7 +1193,10 @@ int rii_destroy(rii_index_t *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
                       &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
-                      &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3, &h->assign, &h->ws_best, &h->ws_arg, &h->d_flag})
+                      &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3, &h->assign, &h->ws_best, &h->ws_arg, &h->d_flag,
+                      &h->sub_keys, &h->sub_rows, &h->sub_keys_s, &h->sub_rows_s, &h->sub_bounds, &h->sub_len, &h->sub_off, &h->sub_skew,
+                      &h->sub_glob, &h->sub_pre, &h->gen_keys, &h->gen_sorted, &h->gen_seg, &h->gen_cnt, &h->redo_idx, &h->redo_q,
+                      &h->redo_ids, &h->redo_d, &h->redo_c})
         b->release();
     if (h->sort_tmp.p) cudaFree(h->sort_tmp.p);
     if (h->d_cw) cudaFree(h->d_cw);
@@ -1186,64 +1426,108 @@ int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
 }
 
 // ---- IVF + target_ids on an id-range shard (the one exchange step) -------------------------------
-// Phase A: coarse ranking + per-list member counts of THIS shard -> d_counts (B, w_eff) int32.  The caller all-gathers
-// the counts of all shards, sums them (global counts) and sums those of the lower ranks (pre counts), then calls
-// phase B on the same handle with the same queries.  full != 0 ranks all nlist lists (the re-run of queries whose plan
-// came back flagged 1: fewer than topk members in the first w lists).  B <= 2048.
-static int subset_w(rii_index *h, int topk, int64_t S, int64_t L, int full, int *w, int *w_eff)
+// The cut after L *member* candidates and the topk test at the w-th list are global, so every shard needs the member
+// counts of the others -- per LIST, not per query: each shard builds the sub-index of its own members once per target
+// set, the per-list member counts are all-gathered (nlist ints per shard), and the queries then run as ordinary sharded
+// IVF searches over the sub-indexes.
+int rii_subset_begin_dev(rii_index_t *h, const int64_t *d_target_ids, int64_t S, int32_t *d_list_counts, void *stream)
 {
-    const long long Ntot = h->n_total();
+    if (!h || !d_target_ids || S <= 0) return fail(RII_ERR_ARG, "bad arguments");
     if (h->nlist <= 0) return fail(RII_ERR_STATE, "query_ivf before reconfigure(): no posting lists");
-    if (S <= 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 < len(target_ids) <= N");
+    if (S > h->n_total()) return fail(RII_ERR_ARG, "need len(target_ids) <= N");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ListsView v;
+    h->sub_S = -1;
+    CKR(build_subview(h, (const long long *)d_target_ids, S, st, &v));
+    if (d_list_counts) CK(cudaMemcpyAsync(d_list_counts, h->sub_len.p, (size_t)h->nlist * 4, cudaMemcpyDeviceToDevice, st));
+    CKR(h->sub_glob.ensure((size_t)h->nlist * 4));
+    CKR(h->sub_pre.ensure((size_t)h->nlist * 4));
+    CK(cudaMemcpyAsync(h->sub_glob.p, h->sub_len.p, (size_t)h->nlist * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(h->sub_pre.p, 0, (size_t)h->nlist * 4, st));
+    h->sub_S = S;
+    return 0;
+}
+
+int rii_subset_set_global_dev(rii_index_t *h, const int32_t *d_counts_all, const int32_t *d_counts_lower, void *stream)
+{
+    if (!h || !d_counts_all || !d_counts_lower) return fail(RII_ERR_ARG, "bad arguments");
+    if (h->sub_S < 0) return fail(RII_ERR_STATE, "rii_subset_begin_dev first");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->sub_glob.p, d_counts_all, (size_t)h->nlist * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->sub_pre.p, d_counts_lower, (size_t)h->nlist * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int rii_subset_query_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, int64_t *d_out_ids, float *d_out_dists,
+                         int32_t *d_out_counts, void *stream)
+{
+    if (!h || !d_queries || !d_out_ids || !d_out_dists || !d_out_counts || B < 1) return fail(RII_ERR_ARG, "bad arguments");
+    if (h->sub_S < 0) return fail(RII_ERR_STATE, "rii_subset_begin_dev first");
+    if (h->shard_stale) return fail(RII_ERR_STATE, "codes were added to / cleared from this shard: call rii_set_shard again");
+    const long long S = h->sub_S, Ntot = h->n_total();
     if (topk < 1 || topk > S) return fail(RII_ERR_ARG, "need 1 <= topk <= len(target_ids)");
     if (!(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need topk <= L <= N");
-    size_t ww = (size_t)std::round((double)L * h->nlist / (double)S) + 3;  // src/rii.h:267-277
-    if ((size_t)h->nlist < ww) ww = h->nlist;
-    *w = (int)ww;
-    *w_eff = full ? h->nlist : (int)ww;
-    return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ListsView v;
+    v.offsets = h->sub_bounds.as<long long>();
+    v.ids = h->sub_rows_s.as<int>();
+    v.loc_len = h->sub_len.as<int>();
+    v.glob_len = h->sub_glob.as<int>();
+    v.pre_len = h->sub_pre.as<int>();
+    v.cap_local = std::min<long long>(S, h->N);
+    if (h->rb && h->opt_scan_kernel != 1) { v.skew = h->sub_skew.as<uint8_t>(); v.skew_off = h->sub_off.as<long long>(); }
+    return ivf_batches(h, d_queries, B, topk, L, v, ivf_width(h, S, L), true, (long long *)d_out_ids, d_out_dists, d_out_counts, st);
 }
 
-int rii_ivf_subset_width(rii_index_t *h, int topk, int64_t S, int64_t L, int full)
+// ---- coarse phase split from the scan (sharded batches: every rank ranks the lists for its share of the queries, the
+// rankings are all-gathered, every rank scans its shard for all queries) ----------------------------------------
+int rii_coarse_width(rii_index_t *h, int64_t L)
 {
     if (!h) return fail(RII_ERR_ARG, "null index");
-    int w = 0, w_eff = 0;
-    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
-    return w_eff;
+    if (h->nlist <= 0) return fail(RII_ERR_STATE, "no posting lists");
+    return ivf_width(h, 0, L);
 }
 
-int rii_ivf_subset_counts_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids, int64_t S,
-                              int64_t L, int full, int32_t *d_counts, void *stream)
+int rii_coarse_rank_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, int32_t *d_ranked, void *stream)
 {
-    if (!h || !d_queries || !d_target_ids || !d_counts) return fail(RII_ERR_ARG, "null argument");
-    if (B < 1 || B > 2048) return fail(RII_ERR_ARG, "need 1 <= B <= 2048");
-    int w = 0, w_eff = 0;
-    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
+    if (!h || !d_queries || !d_ranked || B < 1) return fail(RII_ERR_ARG, "bad arguments");
+    if (h->nlist <= 0) return fail(RII_ERR_STATE, "no posting lists");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    QueryCfg c{topk, S, L, RII_METHOD_IVF};
-    bool dummy;
-    CKR(run_chunk(h, d_queries, B, c, (const long long *)d_target_ids, nullptr, nullptr, nullptr, st, w, w_eff, &dummy, 1));
-    CK(cudaMemcpyAsync(d_counts, h->filt.p, (size_t)B * w_eff * 4, cudaMemcpyDeviceToDevice, st));
+    ListsView v;
+    CKR(main_view(h, st, &v));
+    const int w = ivf_width(h, 0, L);
+    const int D = h->M * h->Ds, CH = 32768;
+    for (int b0 = 0; b0 < B; b0 += CH)
+        CKR(run_ivf(h, d_queries + (size_t)b0 * D, std::min(CH, B - b0), topk, L, v, w, w, nullptr, nullptr, nullptr, st, 1, d_ranked + (size_t)b0 * w));
     return 0;
 }
 
-int rii_ivf_subset_scan_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t S, int64_t L, int full,
-                            const int32_t *d_counts_all, const int32_t *d_counts_lower, int64_t *d_out_ids, float *d_out_dists,
-                            int32_t *d_out_counts, int32_t *d_flags, void *stream)
+int rii_query_ranked_dev(rii_index_t *h, const float *d_queries, int B, int topk, int64_t L, const int32_t *d_ranked, int64_t *d_out_ids,
+                         float *d_out_dists, int32_t *d_out_counts, int32_t *d_flags, void *stream)
 {
-    if (!h || !d_queries || !d_counts_all || !d_counts_lower || !d_out_ids || !d_out_dists || !d_out_counts)
-        return fail(RII_ERR_ARG, "null argument");
-    if (B < 1 || B > 2048) return fail(RII_ERR_ARG, "need 1 <= B <= 2048");
-    int w = 0, w_eff = 0;
-    CKR(subset_w(h, topk, S, L, full, &w, &w_eff));
+    if (!h || !d_queries || !d_ranked || !d_out_ids || !d_out_dists || !d_out_counts || B < 1) return fail(RII_ERR_ARG, "bad arguments");
+    if (h->nlist <= 0) return fail(RII_ERR_STATE, "no posting lists");
+    if (h->shard_stale) return fail(RII_ERR_STATE, "codes were added to / cleared from this shard: call rii_set_shard again");
+    if (h->N_total >= 0 && h->N_total != h->N && !h->has_global)
+        return fail(RII_ERR_STATE, "IVF query on a shard whose list lengths were not exchanged: call rii_set_global_lengths");
+    const long long Ntot = h->n_total();
+    if (topk < 1 || !(topk <= L && L <= Ntot)) return fail(RII_ERR_ARG, "need 1 <= topk <= L <= N");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    QueryCfg c{topk, S, L, RII_METHOD_IVF};
-    bool dummy;
-    CKR(run_chunk(h, d_queries, B, c, nullptr, (long long *)d_out_ids, d_out_dists, d_out_counts, st, w, w_eff, &dummy, 2,
-                  d_counts_all, d_counts_lower));
-    if (d_flags) CK(cudaMemcpyAsync(d_flags, h->flags.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    ListsView v;
+    CKR(main_view(h, st, &v));
+    const int w = ivf_width(h, 0, L);
+    const int D = h->M * h->Ds, CH = 32768;
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int bc = std::min(CH, B - b0);
+        CKR(run_ivf(h, d_queries + (size_t)b0 * D, bc, topk, L, v, w, w, (long long *)d_out_ids + (size_t)b0 * topk, d_out_dists + (size_t)b0 * topk,
+                    d_out_counts + b0, st, 2, const_cast<int *>(d_ranked) + (size_t)b0 * w));
+        if (d_flags) CK(cudaMemcpyAsync(d_flags + b0, h->flags.p, (size_t)bc * 4, cudaMemcpyDeviceToDevice, st));
+    }
     return 0;
 }
 

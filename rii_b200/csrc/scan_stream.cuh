@@ -270,23 +270,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     const bool fused = IVF && a.centers != nullptr;
     int J = 0;  // segments of the current pass (after dropping empty ones)
 
-    // lane 0 of warp 0: turn (s_cum = inclusive local take counts, s_off, s_prow by rank) into the compact segment list
-    auto compact_segments = [&](int Jp) -> int {
-        int jj = 0, g = 0, prev = 0;
-        for (int j = 0; j < Jp; ++j) {
-            const int take = s_cum[j] - prev;
-            prev = s_cum[j];
-            if (take > 0) {
-                g += (take + 63) >> 6;
-                s_gcum[jj] = g;
-                s_take[jj] = take;
-                s_off[jj] = s_off[j];
-                s_prow[jj] = s_prow[j];
-                ++jj;
-            }
-        }
-        return jj;
-    };
     if constexpr (IVF) {
         if (!fused && a.coarse_mode == 2) {
             // the ranking comes from a separate coarse-only launch (possibly of another GPU: the coarse phase of a sharded
@@ -305,16 +288,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take, blockIdx.x == 0);
                 if (lane == 0) s_plan[0] = jc;
             }
-        } else if (!fused) {
-            const int Jp = (a.flags[b] != 0) ? 0 : a.J[b];
-            for (int j = threadIdx.x; j < Jp; j += blockDim.x) {
-                const int no = a.ranked[(size_t)b * a.w_eff + j];
-                s_cum[j] = a.cum[(size_t)b * a.w_eff + j];
-                s_off[j] = a.offsets[no];
-                s_prow[j] = a.skew_off[no];
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_plan[0] = compact_segments(Jp);
         } else if (use_pool) {
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         }

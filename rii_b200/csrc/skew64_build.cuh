@@ -11,7 +11,7 @@ __global__ void k_skew64_build(const uint8_t *__restrict__ codes, const int *__r
 {
     const long long i = prow0 * 2 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the table
     const long long prow = i >> 1;
-    if (prow >= prow1) return;
+    if (prow >= prow1 || prow >= skew_off[nseg]) return;  // (prow1 may be an upper bound when the offsets only exist on the device)
     int lo = 0, hi = nseg - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;

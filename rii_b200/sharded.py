@@ -119,60 +119,69 @@ def sharded_query(engine, Q, topk, L, method, dist, world):
     """One batch on every shard, all-gather of the per-shard top-k, merge under (distance, id).
     `engine.query_local` returns torch tensors (ids int64 (B,k) global ids, dists float32 (B,k), counts int32 (B))
     on the engine's device; `engine.merge` takes the gathered (G,B,k)/(G,B) tensors."""
-    import torch
     ids, d, c = engine.query_local(Q, topk, L, method)
+    return _gather_merge(engine, ids, d, c, dist, world)
+
+
+def _gather_merge(engine, ids, d, c, dist, world):
+    """all-gather of the per-shard top-k -- ONE collective: ids, distance bits and counts travel packed as int64 -- and the
+    merge under (distance, id)."""
+    import torch
     if world == 1:
         return ids, d, c
     B, k = ids.shape
-    g_ids = torch.empty((world, B, k), dtype=ids.dtype, device=ids.device)
-    g_d = torch.empty((world, B, k), dtype=d.dtype, device=d.device)
-    g_c = torch.empty((world, B), dtype=c.dtype, device=c.device)
-    dist.all_gather_into_tensor(g_ids.view(-1), ids.contiguous().view(-1))
-    dist.all_gather_into_tensor(g_d.view(-1), d.contiguous().view(-1))
-    dist.all_gather_into_tensor(g_c.view(-1), c.contiguous().view(-1))
+    pack = torch.empty((B, 2 * k + 1), dtype=torch.int64, device=ids.device)
+    pack[:, :k] = ids
+    pack[:, k:2 * k] = d.view(torch.int32).to(torch.int64)
+    pack[:, 2 * k] = c
+    g = torch.empty((world, B, 2 * k + 1), dtype=torch.int64, device=ids.device)
+    dist.all_gather_into_tensor(g.view(-1), pack.view(-1))
+    g_ids = g[:, :, :k].contiguous()
+    g_d = g[:, :, k:2 * k].to(torch.int32).view(torch.float32).contiguous()
+    g_c = g[:, :, 2 * k].to(torch.int32).contiguous()
     return engine.merge(g_ids, g_d, g_c)
+
+
+def sharded_query_split(engine, Q, topk, L, dist, world, rank):
+    """Sharded IVF batch with the coarse phase split over the ranks (what large nlist needs: ranking 65536 centers costs
+    as much as scanning a shard's candidates).  Rank r ranks the lists for queries [r*B/G, (r+1)*B/G), the (B, w) rankings
+    are all-gathered, every rank scans its shard for all B queries, per-shard top-k are all-gathered and merged.  Queries
+    whose plan is flagged (walk beyond w) are re-run through the unsplit path.  B must divide by world."""
+    import torch
+    B = Q.shape[0]
+    assert B % world == 0
+    Bl = B // world
+    ranked_l = engine.coarse_rank(Q[rank * Bl:(rank + 1) * Bl], topk, L)           # (Bl, w) int32
+    if world > 1:
+        ranked = torch.empty((B, ranked_l.shape[1]), dtype=ranked_l.dtype, device=ranked_l.device)
+        dist.all_gather_into_tensor(ranked.view(-1), ranked_l.contiguous().view(-1))
+    else:
+        ranked = ranked_l
+    ids, d, c, flags = engine.query_ranked(Q, topk, L, ranked)
+    redo = torch.nonzero(flags & 1).flatten()   # the plan is global: the same queries on every rank
+    if redo.numel():
+        i2, d2, c2 = engine.query_local(Q[redo].contiguous(), topk, L, "ivf")
+        ids[redo], d[redo], c[redo] = i2, d2, c2
+    return _gather_merge(engine, ids, d, c, dist, world)
 
 
 def sharded_query_subset(engine, Q, topk, L, tids, dist, world, rank):
     """IVF + target_ids on id-range shards (the one exchange step; src/rii.h:286-322 with the
-    binary_search filter of :294).  Phase A: every shard counts, per ranked list, its own members of `tids`;
-    all-gather of the (B, w) counts; phase B: every shard plans with the global counts (the cut after L filtered
-    candidates and the topk test at the w-th list are global), scans its own members and returns its top-k;
-    all-gather + merge as for any sharded query.  Queries whose plan is flagged (fewer than topk members in the first w
-    lists: the reference walks on through ALL lists) are re-run with the full ranking.
-    `tids`: sorted global int64 ids (a tensor on the engine's device).  <= 2048 queries per call."""
+    binary_search filter of :294).  Every shard builds the sub-index of its own members of `tids` (the members of every
+    posting list, ascending in id) and reports its per-list member counts; one all-gather of nlist counts; then the
+    queries are ordinary sharded IVF searches over the sub-indexes -- the cut after L member candidates and the topk test
+    at the w-th list are planned from the global counts, identically on every rank.
+    `tids`: sorted global int64 ids (a tensor on the engine's device)."""
     import torch
-
-    def one_round(Qr, full):
-        cnt = engine.subset_counts(Qr, topk, tids, L, full)               # (B, w_eff) int32, this shard
-        if world > 1:
-            g = torch.empty((world,) + tuple(cnt.shape), dtype=cnt.dtype, device=cnt.device)
-            dist.all_gather_into_tensor(g.view(-1), cnt.contiguous().view(-1))
-        else:
-            g = cnt[None]
-        glob = g.sum(0, dtype=torch.int32)
-        pre = g[:rank].sum(0, dtype=torch.int32) if rank > 0 else torch.zeros_like(cnt)
-        ids, d, c, flags = engine.subset_scan(Qr, topk, tids, L, full, glob.contiguous(), pre.contiguous())
-        if world > 1:
-            B, k = ids.shape
-            g_ids = torch.empty((world, B, k), dtype=ids.dtype, device=ids.device)
-            g_d = torch.empty((world, B, k), dtype=d.dtype, device=d.device)
-            g_c = torch.empty((world, B), dtype=c.dtype, device=c.device)
-            dist.all_gather_into_tensor(g_ids.view(-1), ids.contiguous().view(-1))
-            dist.all_gather_into_tensor(g_d.view(-1), d.contiguous().view(-1))
-            dist.all_gather_into_tensor(g_c.view(-1), c.contiguous().view(-1))
-            ids, d, c = engine.merge(g_ids, g_d, g_c)
-        return ids, d, c, flags
-
-    ids, d, c, flags = one_round(Q, 0)
-    redo = torch.nonzero(flags & 1).flatten()      # the plan is global: the same queries on every rank
-    if redo.numel():
-        i2, d2, c2, _ = one_round(Q[redo].contiguous(), 1)
-        ids[redo], d[redo], c[redo] = i2, d2, c2
-    empty = torch.nonzero((flags & 2) != 0).flatten()
-    if empty.numel():
-        c[empty] = 0
-    return ids, d, c
+    cnt = engine.subset_begin(tids)                                       # (nlist,) int32, this shard
+    if world > 1:
+        g = torch.empty((world,) + tuple(cnt.shape), dtype=cnt.dtype, device=cnt.device)
+        dist.all_gather_into_tensor(g.view(-1), cnt.contiguous().view(-1))
+        glob = g.sum(0, dtype=torch.int32).contiguous()
+        pre = (g[:rank].sum(0, dtype=torch.int32) if rank > 0 else torch.zeros_like(cnt)).contiguous()
+        engine.subset_set_global(glob, pre)
+    ids, d, c = engine.subset_query(Q, topk, L)
+    return _gather_merge(engine, ids, d, c, dist, world)
 
 
 def _cuda_query_local(self, Q, topk, L, method):
@@ -202,36 +211,62 @@ def _cuda_merge(self, g_ids, g_d, g_c):
     return ids, d, c
 
 
-def _cuda_subset_counts(self, Q, topk, tids, L, full):
+def _st():
     import torch
-    B, S = Q.shape[0], tids.numel()
-    w = self.lib.rii_ivf_subset_width(self.e._h, topk, S, int(L), int(full))
-    self.check(w)
-    cnt = torch.empty((B, w), dtype=torch.int32, device=Q.device)
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    self.check(self.lib.rii_ivf_subset_counts_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, C.c_void_p(tids.data_ptr()), S,
-                                                  int(L), int(full), C.c_void_p(cnt.data_ptr()), st))
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_subset_begin(self, tids):
+    import torch
+    cnt = torch.empty((self.e.nlist,), dtype=torch.int32, device=tids.device)
+    self.check(self.lib.rii_subset_begin_dev(self.e._h, C.c_void_p(tids.data_ptr()), tids.numel(), C.c_void_p(cnt.data_ptr()), _st()))
     return cnt
 
 
-def _cuda_subset_scan(self, Q, topk, tids, L, full, glob, pre):
+def _cuda_subset_set_global(self, glob, pre):
+    self.check(self.lib.rii_subset_set_global_dev(self.e._h, C.c_void_p(glob.data_ptr()), C.c_void_p(pre.data_ptr()), _st()))
+
+
+def _cuda_subset_query(self, Q, topk, L):
+    import torch
+    B, dev = Q.shape[0], Q.device
+    ids = torch.empty((B, topk), dtype=torch.int64, device=dev)
+    d = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    c = torch.empty((B,), dtype=torch.int32, device=dev)
+    self.check(self.lib.rii_subset_query_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, int(L), C.c_void_p(ids.data_ptr()),
+                                             C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()), _st()))
+    return ids, d, c
+
+
+def _cuda_coarse_rank(self, Q, topk, L):
+    import torch
+    w = self.check(self.lib.rii_coarse_width(self.e._h, int(L)))
+    ranked = torch.empty((Q.shape[0], w), dtype=torch.int32, device=Q.device)
+    if Q.shape[0]:
+        self.check(self.lib.rii_coarse_rank_dev(self.e._h, C.c_void_p(Q.data_ptr()), Q.shape[0], topk, int(L),
+                                                C.c_void_p(ranked.data_ptr()), _st()))
+    return ranked
+
+
+def _cuda_query_ranked(self, Q, topk, L, ranked):
     import torch
     B, dev = Q.shape[0], Q.device
     ids = torch.empty((B, topk), dtype=torch.int64, device=dev)
     d = torch.empty((B, topk), dtype=torch.float32, device=dev)
     c = torch.empty((B,), dtype=torch.int32, device=dev)
     flags = torch.empty((B,), dtype=torch.int32, device=dev)
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    self.check(self.lib.rii_ivf_subset_scan_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, tids.numel(), int(L), int(full),
-                                                C.c_void_p(glob.data_ptr()), C.c_void_p(pre.data_ptr()),
-                                                C.c_void_p(ids.data_ptr()), C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()),
-                                                C.c_void_p(flags.data_ptr()), st))
+    self.check(self.lib.rii_query_ranked_dev(self.e._h, C.c_void_p(Q.data_ptr()), B, topk, int(L), C.c_void_p(ranked.data_ptr()),
+                                             C.c_void_p(ids.data_ptr()), C.c_void_p(d.data_ptr()), C.c_void_p(c.data_ptr()),
+                                             C.c_void_p(flags.data_ptr()), _st()))
     return ids, d, c, flags
 
 
 CudaShardEngine.query_local = _cuda_query_local
-CudaShardEngine.subset_counts = _cuda_subset_counts
-CudaShardEngine.subset_scan = _cuda_subset_scan
+CudaShardEngine.subset_begin = _cuda_subset_begin
+CudaShardEngine.subset_set_global = _cuda_subset_set_global
+CudaShardEngine.subset_query = _cuda_subset_query
+CudaShardEngine.coarse_rank = _cuda_coarse_rank
+CudaShardEngine.query_ranked = _cuda_query_ranked
 CudaShardEngine.merge = _cuda_merge
 
 
@@ -284,29 +319,33 @@ class LocalShardGroup(object):
         return self._merge(outs)
 
     def query_subset(self, Q, topk, L, tids):
-        """IVF + target_ids over the shards (two-phase: per-list member counts of every shard, then the scans)."""
+        """IVF + target_ids over the shards: sub-index per shard, exchange of the per-list member counts, sharded IVF."""
         import torch
+        cnts = torch.stack([eng.subset_begin(tids) for eng in self.engines])
+        glob = cnts.sum(0, dtype=torch.int32).contiguous()
+        outs = []
+        for r, eng in enumerate(self.engines):
+            pre = (cnts[:r].sum(0, dtype=torch.int32) if r else torch.zeros_like(glob)).contiguous()
+            if self.G > 1:
+                eng.subset_set_global(glob, pre)
+            outs.append(eng.subset_query(Q, topk, L))
+        torch.cuda.synchronize()
+        return self._merge(outs)
 
-        def one_round(Qr, full):
-            cnts = [eng.subset_counts(Qr, topk, tids, L, full) for eng in self.engines]
-            g = torch.stack(cnts)
-            glob = g.sum(0, dtype=torch.int32).contiguous()
-            outs, flags = [], None
-            for r, eng in enumerate(self.engines):
-                pre = (g[:r].sum(0, dtype=torch.int32) if r else torch.zeros_like(cnts[0])).contiguous()
-                # phase B must follow phase A of the SAME handle with the same queries (it reuses the ranking)
-                eng.subset_counts(Qr, topk, tids, L, full)
-                ids, d, c, flags = eng.subset_scan(Qr, topk, tids, L, full, glob, pre)
-                outs.append((ids, d, c))
-            ids, d, c = self._merge(outs)
-            return ids, d, c, flags
-
-        ids, d, c, flags = one_round(Q, 0)
-        redo = torch.nonzero(flags & 1).flatten()
-        if redo.numel():
-            i2, d2, c2, _ = one_round(Q[redo].contiguous(), 1)
-            ids[redo], d[redo], c[redo] = i2, d2, c2
-        empty = torch.nonzero((flags & 2) != 0).flatten()
-        if empty.numel():
-            c[empty] = 0
-        return ids, d, c
+    def query_split(self, Q, topk, L):
+        """The coarse / scan split of sharded_query_split with the G handles of this process."""
+        import torch
+        B = Q.shape[0]
+        assert B % self.G == 0
+        Bl = B // self.G
+        ranked = torch.cat([eng.coarse_rank(Q[r * Bl:(r + 1) * Bl].contiguous(), topk, L) for r, eng in enumerate(self.engines)])
+        outs = []
+        for eng in self.engines:
+            ids, d, c, flags = eng.query_ranked(Q, topk, L, ranked)
+            redo = torch.nonzero(flags & 1).flatten()
+            if redo.numel():
+                i2, d2, c2 = eng.query_local(Q[redo].contiguous(), topk, L, "ivf")
+                ids[redo], d[redo], c[redo] = i2, d2, c2
+            outs.append((ids, d, c))
+        torch.cuda.synchronize()
+        return self._merge(outs)

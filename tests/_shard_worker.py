@@ -81,51 +81,89 @@ class OracleShardEngine(object):
             return None
         return np.concatenate(cand).astype(np.int64) if cand else np.zeros(0, np.int64)
 
-    # ---- IVF + target_ids, two phases (restated in numpy independently of the CUDA pipeline) ----
-    def _rank_lists(self, q, topk, S, L, full):
-        nlist = self.centers.shape[0]
-        T = O.dtable(q, self.cw, 16)
-        cd = O.adist_all(T, self.centers)
-        order = np.lexsort((np.arange(nlist), cd))
-        w = min(int(np.floor(L * nlist / S + 0.5)) + 3, nlist)
-        return T, order[: (nlist if full else w)], w
-
-    def subset_counts(self, Q, topk, tids, L, full):
-        t = tids.numpy() - self.lo
+    # ---- IVF + target_ids: sub-index of the members + exchange of per-list member counts (restated in numpy
+    # independently of the CUDA pipeline) ----
+    def subset_begin(self, tids):
+        t = np.unique(tids.numpy()) - self.lo
+        t = t[(t >= 0) & (t < len(self.codes))]
         member = np.zeros(len(self.codes), bool)
-        member[t[(t >= 0) & (t < len(self.codes))]] = True
-        self._member = member
-        out = []
-        for q in Q.numpy():
-            _, order, _ = self._rank_lists(q, topk, len(tids), L, full)
-            out.append([int(member[self.ids[self.offsets[no]:self.offsets[no + 1]]].sum()) for no in order])
-        return torch.tensor(out, dtype=torch.int32)
+        member[t] = True
+        self._S = len(tids)
+        self._sub = [self.ids[self.offsets[no]:self.offsets[no + 1]] for no in range(self.centers.shape[0])]
+        self._sub = [m[member[m]] for m in self._sub]
+        cnt = np.array([len(m) for m in self._sub], np.int32)
+        self._sglob, self._spre = cnt.copy(), np.zeros_like(cnt)
+        return torch.from_numpy(cnt)
 
-    def subset_scan(self, Q, topk, tids, L, full, glob, pre):
+    def subset_set_global(self, glob, pre):
+        self._sglob, self._spre = glob.numpy(), pre.numpy()
+
+    def subset_query(self, Q, topk, L):
+        B = Q.shape[0]
+        ids = np.full((B, topk), -1, np.int64)
+        d = np.full((B, topk), np.inf, np.float32)
+        c = np.zeros(B, np.int32)
+        nlist = self.centers.shape[0]
+        for b, q in enumerate(Q.numpy()):
+            T = O.dtable(q, self.cw, 16)
+            cd = O.adist_all(T, self.centers)
+            order = np.lexsort((np.arange(nlist), cd))
+            w = min(int(np.floor(L * nlist / self._S + 0.5)) + 3, nlist)
+            # the reference's sequential walk (src/rii.h:286-322): stop at L, or after the w-th list with >= topk found
+            P, cand, done = 0, [], False
+            for j, no in enumerate(order):
+                f = int(self._sglob[no])
+                take = f
+                if P + f >= L:
+                    take, done = L - P, True
+                P += take
+                lt = int(np.clip(take - int(self._spre[no]), 0, len(self._sub[no])))
+                cand.append(self._sub[no][:lt])
+                if done or (j == w - 1 and P >= topk):
+                    done = True
+                    break
+            if not done:
+                continue  # src/rii.h:325: empty result
+            cand = np.concatenate(cand).astype(np.int64) if cand else np.zeros(0, np.int64)
+            dd = O.adist_all(T, self.codes[cand]) if len(cand) else np.zeros(0, np.float32)
+            o = np.lexsort((cand, dd))[:topk]
+            ids[b, :len(o)], d[b, :len(o)], c[b] = cand[o] + self.lo, dd[o], len(o)
+        return torch.from_numpy(ids), torch.from_numpy(d), torch.from_numpy(c)
+
+    # ---- coarse phase split from the scan ----
+    def coarse_rank(self, Q, topk, L):
+        nlist = self.centers.shape[0]
+        w = min(int(np.floor(L * nlist / self.n_total + 0.5)) + 3, nlist)
+        out = np.zeros((Q.shape[0], w), np.int32)
+        for b, q in enumerate(Q.numpy()):
+            cd = O.adist_all(O.dtable(q, self.cw, 16), self.centers)
+            out[b] = np.lexsort((np.arange(nlist), cd))[:w]
+        return torch.from_numpy(out)
+
+    def query_ranked(self, Q, topk, L, ranked):
         B = Q.shape[0]
         ids = np.full((B, topk), -1, np.int64)
         d = np.full((B, topk), np.inf, np.float32)
         c = np.zeros(B, np.int32)
         flags = np.zeros(B, np.int32)
         nlist = self.centers.shape[0]
+        w = ranked.shape[1]
         for b, q in enumerate(Q.numpy()):
-            T, order, w = self._rank_lists(q, topk, len(tids), L, full)
+            T = O.dtable(q, self.cw, 16)
             P, cand, done = 0, [], False
-            for j, no in enumerate(order):
-                f = int(glob[b, j])
+            for j, no in enumerate(ranked[b].numpy()):
+                f = int(self.glob[no])
                 take = f
                 if P + f >= L:
                     take, done = L - P, True
                 P += take
-                mem = self.ids[self.offsets[no]:self.offsets[no + 1]]
-                mem = mem[self._member[mem]]
-                lt = int(np.clip(take - int(pre[b, j]), 0, len(mem)))
-                cand.append(mem[:lt])
+                lt = int(np.clip(take - self.pre[no], 0, self.offsets[no + 1] - self.offsets[no]))
+                cand.append(self.ids[self.offsets[no]:self.offsets[no] + lt])
                 if done or (j == w - 1 and P >= topk):
                     done = True
                     break
             if not done:
-                flags[b] = 2 if len(order) >= nlist else 1
+                flags[b] = 2 if w >= nlist else 1
                 continue
             cand = np.concatenate(cand).astype(np.int64) if cand else np.zeros(0, np.int64)
             dd = O.adist_all(T, self.codes[cand]) if len(cand) else np.zeros(0, np.float32)
@@ -181,6 +219,14 @@ def main():
             n = int(gc[bq])
             assert n == len(exp[0]), (method, topk, L, n, len(exp[0]))
             assert np.array_equal(gi[bq, :n].numpy(), exp[0]) and np.array_equal(gd[bq, :n].numpy().view(np.uint32), exp[1].view(np.uint32)), (method, topk, L)
+    # the coarse phase split over the ranks (each rank ranks the lists for its half of the queries)
+    for topk, L in [(1, 250), (10, 1500), (40, 45), (7, N)]:
+        gi, gd, gc = sharded.sharded_query_split(eng, Qt, topk, L, dist, world, rank)
+        for bq, q in enumerate(Q):
+            exp = O.query_ivf(O.dtable(q, cw, 16), codes, centers, offsets, ids, topk, L)
+            n = int(gc[bq])
+            assert n == len(exp[0]), ("split", topk, L, n, len(exp[0]))
+            assert np.array_equal(gi[bq, :n].numpy(), exp[0]) and np.array_equal(gd[bq, :n].numpy().view(np.uint32), exp[1].view(np.uint32)), ("split", topk, L)
     # IVF + target_ids across shards: uniform subset, a subset concentrated in few lists far from the queries (walk
     # beyond w -> flagged re-run with the full ranking), and one where L is never reached (empty result)
     rng = np.random.default_rng(5)

@@ -347,8 +347,9 @@ def test_skew_kernel_matches_oracle(N, sk):
         for b, q in enumerate(Q):
             exp = O.query_linear(O.dtable(q, cw, 16), codes, 10)
             assert_same_result(bi[b], bd[b], exp[0], exp[1], "skew batch")
-    with pytest.raises(Exception):
-        e.query_linear(Q[0], 1, np.arange(1, dtype=np.int64))  # v2 has no target_ids path when forced
+    if N >= 10:  # forced streaming engine + unsorted target ids: refused (ascending ids run on a compact copy of the rows)
+        with pytest.raises(Exception):
+            e.query_linear(Q[0], 1, np.array([5, 2], dtype=np.int64))
 
 
 @pytest.mark.parametrize("sk", SKEW_KERNELS)
@@ -686,14 +687,17 @@ def test_id_range_shards_on_one_gpu(G):
     Qd = torch.from_numpy(Q).to(dev)
     for method, topk, L in [("linear", 1, 0), ("linear", 50, 0), ("ivf", 1, 2000), ("ivf", 10, 6400), ("ivf", 100, 150),
                             ("ivf", 5, N), ("ivf", 3, 1666)]:
-        gi, gd, gc = grp.query(Qd, topk, L, method)
-        torch.cuda.synchronize()
-        gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
-        for bq, q in enumerate(Q):
-            T = O.dtable(q, cw, 16)
-            exp = O.query_linear(T, codes, topk) if method == "linear" else O.query_ivf(T, codes, oc, offsets, ids, topk, L)
-            n = int(gc[bq])
-            assert_same_result(gi[bq, :n], gd[bq, :n], exp[0], exp[1], "shards G=%d %s k=%d L=%d" % (G, method, topk, L))
+        runs = [("", grp.query(Qd, topk, L, method))]
+        if method == "ivf":  # the coarse phase split over the shards' handles (rii_coarse_rank_dev / rii_query_ranked_dev)
+            runs.append(("split ", grp.query_split(Qd, topk, L)))
+        for tag, (gi, gd, gc) in runs:
+            torch.cuda.synchronize()
+            gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+            for bq, q in enumerate(Q):
+                T = O.dtable(q, cw, 16)
+                exp = O.query_linear(T, codes, topk) if method == "linear" else O.query_ivf(T, codes, oc, offsets, ids, topk, L)
+                n = int(gc[bq])
+                assert_same_result(gi[bq, :n], gd[bq, :n], exp[0], exp[1], "shards G=%d %s%s k=%d L=%d" % (G, tag, method, topk, L))
     rng = np.random.default_rng(5)
     far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), oc))[-5:]
     far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
@@ -761,3 +765,116 @@ def test_assign_stream_engine_vs_natural_and_oracle(M, N, K):
     Dm = O.sym_matrices(cw)
     oa, od = O.assign(Dm, codes[:n_chk], centers, return_dist=True)
     assert np.array_equal(res[0][0][:n_chk], oa) and np.array_equal(bits(res[0][1][:n_chk]), bits(od))
+
+
+@pytest.mark.parametrize("M", [32, 64, 20])
+def test_subset_search_on_the_streaming_engine(M):
+    """target_ids on the streaming engine (src/rii.h:218-228,294): linear over a compact skew64 copy of
+    the target rows, IVF over the sub-index of the members -- against the oracle and the natural-layout kernels; sparse
+    and dense subsets, repeated ids, many ranked lists (w > 224), subsets concentrated in far lists (walk beyond w), and
+    the empty result."""
+    D, Ks, N, nlist = 4 * M, 256, 60000, 300
+    cw, codes, Q = synth(D, M, Ks, N, 5, seed=500 + M)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    rng = np.random.default_rng(11)
+    far = np.argsort(O.adist_all(O.dtable(Q[0], cw, 16), centers))[-6:]
+    far_ids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+    dup = np.sort(np.concatenate([rng.choice(N, 3000, replace=False), np.arange(100, 140)])).astype(np.int64)
+    dup = np.sort(np.concatenate([dup, dup[:500]]))
+    cases = [(np.sort(rng.choice(N, 6000, replace=False)).astype(np.int64), 10, 1000),      # w = 53
+             (np.sort(rng.choice(N, 6000, replace=False)).astype(np.int64), 3, 5000),       # w = 253 > 224 ranked lists
+             (np.sort(rng.choice(N, 30000, replace=False)).astype(np.int64), 1, 30000),     # L = S: every member
+             (np.sort(rng.choice(N, 200, replace=False)).astype(np.int64), 5, 150),
+             (dup, 7, 800), (far_ids, 3, 30), (far_ids[:5], 5, 5), (np.arange(N, dtype=np.int64), 10, 2000)]
+    for tids, topk, L in cases:
+        for q in Q[:3]:
+            T = O.dtable(q, cw, 16)
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L, tids)
+            for sk in (4, 1):
+                e.set_option("scan_kernel", sk)
+                try:
+                    g = e.query_ivf(q, topk, tids, L)
+                except Exception:
+                    if sk == 4 and int(round(L * nlist / len(tids))) + 3 >= nlist:
+                        continue  # the forced engine cannot re-rank every list when nlist is large; auto falls back
+                    raise
+                assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "subset ivf M=%d sk=%d S=%d k=%d L=%d" % (M, sk, len(tids), topk, L))
+            expl = O.query_linear(T, codes, topk, tids)
+            for sk in (4, 1):
+                e.set_option("scan_kernel", sk)
+                g = e.query_linear(q, topk, tids)
+                if len(np.unique(tids)) == len(tids):
+                    assert_same_result(g[0], np.array(g[1], np.float32), expl[0], expl[1], "subset linear M=%d sk=%d S=%d k=%d" % (M, sk, len(tids), topk))
+                else:  # repeated ids give repeated results (order among equal keys is free): compare as multisets of keys
+                    assert sorted(zip(np.array(g[1], np.float32).tolist(), g[0])) == sorted(zip(expl[1].tolist(), expl[0].tolist()))
+    # unsorted ids (linear only; src/rii.h:218-228 takes them in the given order): natural-layout kernel, same result set
+    e.set_option("scan_kernel", 0)
+    t = rng.permutation(N)[:5000].astype(np.int64)
+    g = e.query_linear(Q[0], 20, t)
+    exp = O.query_linear(O.dtable(Q[0], cw, 16), codes, 20, t)
+    assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "unsorted subset")
+    # batch entry: one sub-index serves the whole batch
+    tids = cases[0][0]
+    Qb = np.ascontiguousarray(np.tile(Q, (40, 1)))
+    bi, bd, bc = e.query_batch(Qb, 4, target_ids=tids, L=1000, method="ivf")
+    li, ld, lc = e.query_batch(Qb, 4, target_ids=tids, method="linear")
+    for b in range(0, 200, 23):
+        T = O.dtable(Qb[b], cw, 16)
+        exp = O.query_ivf(T, codes, centers, offsets, ids, 4, 1000, tids)
+        assert_same_result(bi[b][:bc[b]], bd[b][:bc[b]], exp[0], exp[1], "subset batch ivf")
+        exp = O.query_linear(T, codes, 4, tids)
+        assert_same_result(li[b][:lc[b]], ld[b][:lc[b]], exp[0], exp[1], "subset batch linear")
+
+
+@pytest.mark.parametrize("M,Ks", [(32, 256), (8, 64), (72, 256)])
+def test_any_topk_and_any_number_of_ranked_lists(M, Ks):
+    """The reference allows 1 <= topk <= N (rii/rii.py:280-281: topk=None means N) and re-ranks ALL lists when the first
+    w hold too few candidates; shapes whose keys do not fit shared memory take the global-memory path (keys in HBM + radix
+    sort).  ADVICE r1: large topk, and nlist >= 8192."""
+    D, N = 4 * M, 40000
+    cw, codes, Q = synth(D, M, Ks, N, 2, seed=900 + M)
+    e = engine(cw, codes)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (300, 20000, N):
+            g = e.query_linear(q, topk, EMPTY)
+            assert_same_result(g[0], np.array(g[1], np.float32), *O.query_linear(T, codes, topk), "large topk linear M=%d k=%d" % (M, topk))
+        tids = np.arange(0, N, 3, dtype=np.int64)
+        g = e.query_linear(q, len(tids), tids)
+        assert_same_result(g[0], np.array(g[1], np.float32), *O.query_linear(T, codes, len(tids), tids), "large topk subset")
+    nlist = 9000 if M == 32 else 500
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk, L in [(300, 4000), (5000, 5000), (N, N), (2, 10)]:
+            g = e.query_ivf(q, topk, EMPTY, L)
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
+            assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "large topk ivf M=%d k=%d L=%d" % (M, topk, L))
+        # a subset concentrated in the farthest lists: fewer than topk members in the first w lists -> every list is ranked
+        far = np.argsort(O.adist_all(T, centers))[-8:]
+        tids = np.sort(np.concatenate([ids[offsets[no]:offsets[no + 1]] for no in far])).astype(np.int64)
+        if len(tids) >= 3:
+            g = e.query_ivf(q, 3, tids, min(len(tids), 12))
+            exp = O.query_ivf(T, codes, centers, offsets, ids, 3, min(len(tids), 12), tids)
+            assert_same_result(g[0], np.array(g[1], np.float32), exp[0], exp[1], "full re-ranking M=%d nlist=%d" % (M, nlist))
+
+
+def test_reconfigure_with_large_nlist_sets_a_threshold():
+    """Rii.reconfigure() with nlist >= 8192 must finish with a usable threshold function."""
+    from rii_b200 import Rii, pq
+    rng = np.random.default_rng(1)
+    D, M, N = 64, 16, 70000
+    X = rng.random((N, D), dtype=np.float32)
+    codec = pq.PQ(M=M, Ks=256, verbose=False).fit(X[:3000], iter=3, seed=123)
+    e = Rii(codec)
+    e.add_configure(X, nlist=8200, iter=1)
+    assert e.threshold is not None and e.nlist == 8200
+    q = X[17]
+    ids, d = e.query(q, topk=3)
+    ids2, d2 = e.query(q, topk=3, method="linear")
+    assert ids2[0] == ids[0] or d[0] >= d2[0]
