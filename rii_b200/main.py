@@ -176,6 +176,54 @@ class RiiCpp(object):
         check(_capi.lib().rii_set_state(self._h, _ptr(centers, C.c_uint8), centers.shape[0], _ptr(codes, C.c_uint8),
                                         codes.shape[0], _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
 
+    # ---- exchange with the reference (src/main.cpp:35-54) ------------------------------------------
+    def to_reference_state(self):
+        """The reference's own pickle state, exactly: (codewords, verbose, coarse_centers, flattened_codes,
+        posting_lists) as nested Python lists -- what `main.RiiCpp.__setstate__` of matsui528/rii casts from."""
+        return (self._codewords.tolist(), bool(self.verbose), self.coarse_centers, self.flattened_codes, self.posting_lists)
+
+    def dumps_reference(self):
+        """Pickle bytes that the UNMODIFIED reference loads with `pickle.loads` into its own `main.RiiCpp`."""
+        return reference_pickle_bytes(*self.to_reference_state())
+
+    # ---- flat, memory-mappable state for large indexes (SURVEY 8f rank 3) -----------------------------
+    def save_flat(self, path):
+        """Directory of raw arrays + meta.json.  The code table is written through a memory map (no second host copy),
+        so 1e8-1e9 codes need only page cache."""
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        np.save(os.path.join(path, "codewords.npy"), self._codewords)
+        N, M, nlist = self.N, self.M, self.nlist
+        codes = np.lib.format.open_memmap(os.path.join(path, "codes.npy"), mode="w+", dtype=np.uint8, shape=(N, M))
+        if N:
+            check(_capi.lib().rii_copy_codes(self._h, _ptr(codes, C.c_uint8)))
+        codes.flush()
+        del codes
+        np.save(os.path.join(path, "coarse_centers.npy"), self.coarse_centers_array())
+        offsets, ids = self.posting_lists_csr()
+        np.save(os.path.join(path, "posting_offsets.npy"), offsets)
+        np.save(os.path.join(path, "posting_ids.npy"), ids)
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump({"format": "rii_b200-flat-1", "N": N, "M": M, "Ks": self.Ks, "Ds": self.Ds, "nlist": nlist,
+                       "verbose": bool(self.verbose), "l2_variant": self._l2_variant}, f)
+
+    @classmethod
+    def load_flat(cls, path, device=0):
+        """Load a save_flat() directory: the arrays are memory-mapped, never materialised on the host heap."""
+        import json
+        import os
+        meta = json.load(open(os.path.join(path, "meta.json")))
+        assert meta["format"] == "rii_b200-flat-1"
+        e = cls(np.load(os.path.join(path, "codewords.npy")), meta["verbose"], device=device, l2_variant=meta["l2_variant"])
+        codes = np.load(os.path.join(path, "codes.npy"), mmap_mode="r")  # pages are read as the copy engine pulls them
+        centers = np.ascontiguousarray(np.load(os.path.join(path, "coarse_centers.npy")), np.uint8).reshape(-1, meta["M"])
+        offsets = np.ascontiguousarray(np.load(os.path.join(path, "posting_offsets.npy")), np.int64)
+        ids = np.load(os.path.join(path, "posting_ids.npy"), mmap_mode="r")
+        check(_capi.lib().rii_set_state(e._h, _ptr(centers, C.c_uint8), centers.shape[0], _ptr(codes, C.c_uint8), meta["N"],
+                                        _ptr(offsets, C.c_int64), _ptr(ids, C.c_int32)))
+        return e
+
     def encode(self, vecs):
         """GPU PQ encoder: float32 (n, D) -> uint8 (n, M) (nearest codeword per sub-space, first minimum wins)."""
         X = np.ascontiguousarray(vecs, np.float32)
@@ -214,3 +262,14 @@ class RiiCpp(object):
         out = np.empty((self.M, self.Ks, self.Ks), np.float32)
         check(_capi.lib().rii_sym_matrices(self._h, _ptr(out, C.c_float)))
         return out
+
+
+def reference_pickle_bytes(codewords, verbose, coarse_centers, flattened_codes, posting_lists):
+    """A protocol-2 pickle stream of the reference's class `main.RiiCpp` (pybind11 pickles through copyreg.__newobj__ +
+    __setstate__, src/main.cpp:35-54) carrying the given 5-tuple.  Written opcode by opcode because the class `main.RiiCpp`
+    need not be importable where the index lives."""
+    import pickle
+    state = pickle.dumps((codewords, bool(verbose), coarse_centers, flattened_codes, posting_lists), protocol=2)
+    assert state[:2] == b"\x80\x02" and state[-1:] == b"."
+    #       PROTO 2      GLOBAL main.RiiCpp   EMPTY_TUPLE NEWOBJ   <state>      BUILD STOP
+    return b"\x80\x02" + b"cmain\nRiiCpp\n" + b")" + b"\x81" + state[2:-1] + b"b" + b"."

@@ -4,12 +4,12 @@ Same properties, methods, argument meaning, assertions and return dtypes; the on
 `rii_b200.main.RiiCpp` (CUDA, via the C ABI).  Additions are opt-in: `query_batch`, `device=`.
 """
 import copy
-import time
 
 import numpy as np
 
 from . import main
 from . import pq as _pq
+from .cost_model import CostModel, Threshold
 
 
 class Rii(object):
@@ -86,8 +86,7 @@ class Rii(object):
             nlist = int(np.sqrt(self.N))
         assert 0 < nlist
         self.impl_cpp.reconfigure(nlist, iter)
-        self.threshold = estimate_best_threshold_function(
-            e=self, queries=self.fine_quantizer.decode(self.codes[:min(100, self.N)]))
+        self.threshold = estimate_best_threshold_function(e=self)
 
     def add(self, vecs, update_posting_lists="auto", gpu_encode=False):
         """rii/rii.py:152-186.  gpu_encode=True (opt-in, not in the reference) encodes on the GPU (rii_encode) instead
@@ -146,7 +145,7 @@ class Rii(object):
         topk, L, tids, len_target_ids = self._prepare(topk, L, target_ids, sort_target_ids)
         q_ = self.fine_quantizer.rotate(q) if _pq.is_opq(self.fine_quantizer) else q
         if method == "auto":
-            method = "linear" if self._use_linear(len_target_ids, L) else "ivf"
+            method = "linear" if self._use_linear(len_target_ids, L, subset=target_ids is not None) else "ivf"
         if method == "linear":
             ids, dists = self.impl_cpp.query_linear(q_, topk, tids)
         else:
@@ -156,10 +155,13 @@ class Rii(object):
     def query_batch(self, Q, topk=1, L=None, target_ids=None, sort_target_ids=True, method="ivf"):
         """Batch form of :func:`query` (not in the reference): Q (B, D) float32 ->
         ids (B, topk) int64 (-1 padded), dists (B, topk) float64 (inf padded), counts (B,) int32."""
-        assert method in ["linear", "ivf"]
+        assert method in ["auto", "linear", "ivf"]
         assert Q.ndim == 2 and Q.dtype == np.float32
         topk, L, tids, _ = self._prepare(topk, L, target_ids, sort_target_ids)
         Q_ = self.fine_quantizer.rotate(Q) if _pq.is_opq(self.fine_quantizer) else Q
+        if method == "auto":
+            method = "linear" if self._use_linear(len(tids) if target_ids is not None else self.N, L,
+                                                   subset=target_ids is not None, batch=Q.shape[0]) else "ivf"
         ids, dists, counts = self.impl_cpp.query_batch(np.ascontiguousarray(Q_, np.float32), topk, tids, L, method)
         return ids, dists.astype(np.float64), counts
 
@@ -186,15 +188,21 @@ class Rii(object):
             print("_multiple_of_L0_covering_topk(topk={}): {}".format(topk, L))
         print("threshold function thre_{|S|}=f(L):", self.threshold)
         for S in [10 ** (2 + n) for n in range(5)]:
-            use_linear = None if self.threshold is None else self._use_linear(S, self.L0)
+            use_linear = None if self.threshold is None else self._use_linear(S, self.L0, subset=True)
             print("_use_linear({S}, L={L0}): {use_linear}".format(S=S, L0=self.L0, use_linear=use_linear))
 
     # ---- helpers, rii/rii.py:374-400 --------------------------------------------------------
     def _multiple_of_L0_covering_topk(self, topk):
         return min((topk // self.L0 + 1) * self.L0, self.N)
 
-    def _use_linear(self, len_target_ids, L):
-        return bool(len_target_ids <= self.threshold(L))
+    def _use_linear(self, len_target_ids, L, subset=None, batch=1):
+        """rii/rii.py:383-392 (`len_target_ids <= threshold(L)`), decided by the cost model: with target_ids the
+        comparison is |S| against the crossover thre(L); without, N candidates against nlist + L."""
+        if subset is None:
+            subset = len_target_ids != self.N
+        if not subset:
+            return bool(self.threshold.model.use_linear(self.N, L, False, batch))
+        return bool(len_target_ids <= self.threshold(L, batch))
 
     def _resolve_update_posting_lists_flag(self, flag):
         assert flag in ["auto", True, False]
@@ -203,60 +211,15 @@ class Rii(object):
         return flag
 
 
-def estimate_best_threshold_function(e, queries):
-    """Fit threshold(L) = |S| at which linear scan and inverted-index search cost the same (rii/rii.py:403-486):
-    for a few L, double |S| until ivf beats linear, bisect 5 times, then fit a line through (L, |S|).
-    Wall-clock driven like the reference, so `method='auto'` is not deterministic; parity tests pass an
-    explicit method."""
-    topk = 1
-    queries = np.ascontiguousarray(queries, np.float32)
-
-    def cost(method, Q, s, L):
-        tids = np.arange(s, dtype=np.int64)
-        t0 = time.time()
-        for q in Q:
-            if method == "linear":
-                e.impl_cpp.query_linear(q, topk, tids)
-            else:
-                e.impl_cpp.query_ivf(q, topk, tids, L)
-        return (time.time() - t0) / Q.shape[0]
-
-    def crossover(L):
-        if e.N <= 128:
-            return e.N
-        sizes = [128]
-        while sizes[-1] * 2 < e.N:
-            sizes.append(sizes[-1] * 2)
-        sizes.append(e.N)
-        for s in sizes:
-            if cost("ivf", queries[:3], s, L) < cost("linear", queries[:3], s, L):
-                if s == 128:
-                    return 128
-                lo, hi = s // 2, s
-                for _ in range(5):
-                    mid = int(np.round((lo + hi) / 2))
-                    if cost("ivf", queries, mid, L) < cost("linear", queries, mid, L):
-                        hi = mid
-                    else:
-                        lo = mid
-                return lo
-        return e.N
-
+def estimate_best_threshold_function(e, queries=None):
+    """thre_{|S|} = f(L): the |S| at which a linear scan over target_ids and the inverted-index search cost the same
+    (rii/rii.py:403-486).  The reference measures wall-clock times of both methods and fits a line; here the crossover
+    comes from a bytes-and-launches cost model (rii_b200/cost_model.py), so it is deterministic and costs no queries.
+    `queries` is accepted for signature compatibility and ignored."""
+    t = Threshold(CostModel(e.N, e.nlist, e.M))
     if e.verbose:
         print("===== Threshold selection ====")
-    xs, ys = [], []
-    for L in [k * e._multiple_of_L0_covering_topk(k) for k in [1, 2, 4, 8, 16]]:
-        if e.N < L:
-            continue
-        xs.append(L)
-        ys.append(crossover(L))
-        if ys[-1] == e.N:
-            break
-    z = [0, ys[0]] if len(xs) == 1 else np.polyfit(xs, ys, 1)
-    p = np.poly1d(z)
-    if e.verbose:
-        print("L:", xs)
-        print("threshold:", ys)
-        print("polyfit coeff:", z)
-        print("resultant func:", p)
-    return p
+        Ls = [k * e._multiple_of_L0_covering_topk(k) for k in [1, 2, 4, 8, 16] if k * e._multiple_of_L0_covering_topk(k) <= e.N]
+        print("L:", Ls)
+        print("threshold:", [t(L) for L in Ls])
+    return t

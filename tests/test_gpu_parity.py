@@ -878,3 +878,45 @@ def test_reconfigure_with_large_nlist_sets_a_threshold():
     ids, d = e.query(q, topk=3)
     ids2, d2 = e.query(q, topk=3, method="linear")
     assert ids2[0] == ids[0] or d[0] >= d2[0]
+
+
+def test_state_exchange_formats(tmp_path):
+    """(1) the flat memory-mappable format round-trips an index bit for bit; (2) the reference's own
+    5-tuple pickle state (src/main.cpp:35-54) exported from the GPU index loads in the unmodified reference (when its build
+    travelled with the repo) and answers like us."""
+    import os
+    import pickle
+    import subprocess
+    import sys
+    from rii_b200 import main
+    from oracle import ref as R
+    cw, codes, Q = synth(64, 16, 256, 5000, 3, seed=8)
+    e = engine(cw, codes)
+    e.reconfigure(30, 2)
+    d = str(tmp_path / "flat")
+    e.save_flat(d)
+    e2 = main.RiiCpp.load_flat(d)
+    assert e2.N == e.N and e2.nlist == e.nlist
+    assert np.array_equal(e2.codes_array(), codes) and np.array_equal(e2.coarse_centers_array(), e.coarse_centers_array())
+    o1, i1 = e.posting_lists_csr()
+    o2, i2 = e2.posting_lists_csr()
+    assert np.array_equal(o1, o2) and np.array_equal(i1, i2)
+    tids = np.arange(0, 5000, 7, dtype=np.int64)
+    for q in Q:
+        assert e.query_ivf(q, 5, EMPTY, 700) == e2.query_ivf(q, 5, EMPTY, 700)
+        assert e.query_ivf(q, 5, tids, 300) == e2.query_ivf(q, 5, tids, 300)  # (the row -> list map is rebuilt on load)
+    # our own pickle (arrays) still round-trips
+    e3 = pickle.loads(pickle.dumps(e))
+    assert e3.query_linear(Q[0], 4, EMPTY) == e.query_linear(Q[0], 4, EMPTY)
+    st = e.to_reference_state()
+    assert len(st) == 5 and isinstance(st[3], list) and len(st[3]) == 5000 * 16 and isinstance(st[4][0], list)
+    so_dir = R.variant_dir("strict")
+    if so_dir is None:
+        return
+    f = str(tmp_path / "ref.pkl")
+    open(f, "wb").write(e.dumps_reference())
+    np.save(str(tmp_path / "q.npy"), Q[0])
+    code = ("import sys, pickle, numpy as np; sys.path.insert(0, %r); import main; e = pickle.load(open(%r, 'rb'));"
+            "q = np.load(%r); print(e.query_ivf(q, 3, np.array([], np.int64), 700)[0])" % (so_dir, f, str(tmp_path / "q.npy")))
+    out = subprocess.check_output([sys.executable, "-c", code], stderr=subprocess.STDOUT).decode()
+    assert str(e.query_ivf(Q[0], 3, EMPTY, 700)[0]) in out, out

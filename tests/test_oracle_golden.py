@@ -59,3 +59,36 @@ def test_reconfigure(path):
     offsets, ids = O.assign_to_lists(assign, g["nlist"])
     assert np.array_equal(offsets, g["offsets"])
     assert np.array_equal(ids, g["ids"])
+
+
+def test_reference_pickle_stream_loads_in_the_unmodified_reference():
+    """SURVEY 8f rank 3 / src/main.cpp:35-54: the 5-tuple state our index exports (RiiCpp.to_reference_state /
+    dumps_reference) must unpickle into the reference's own main.RiiCpp and answer queries there."""
+    import os
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+    from oracle import ref as R
+    from rii_b200.main import reference_pickle_bytes
+    if not R.available("strict"):
+        import pytest
+        pytest.skip("oracle/_ref is not built here")
+    g = load_golden(golden_files("strict_v4")[0] if golden_files("strict_v4") else golden_files("strict_v3")[0])
+    centers, codes = g["centers"], g["codes"]
+    offsets, ids = g["offsets"], g["ids"]
+    pl = [ids[offsets[i]:offsets[i + 1]].tolist() for i in range(len(offsets) - 1)]
+    blob = reference_pickle_bytes(g["cw"].tolist(), False, centers.tolist(), codes.reshape(-1).tolist(), pl)
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "idx.pkl")
+        open(f, "wb").write(blob)
+        so_dir = R.variant_dir("strict")
+        code = ("import sys, pickle, numpy as np; sys.path.insert(0, %r); import main; e = pickle.load(open(%r, 'rb'));"
+                "assert type(e).__name__ == 'RiiCpp' and e.N == %d and e.nlist == %d;"
+                "q = np.load(%r); r = e.query_linear(q, 3, np.array([], np.int64)); print(r[0])"
+                % (so_dir, f, codes.shape[0], len(pl), os.path.join(td, "q.npy")))
+        np.save(os.path.join(td, "q.npy"), np.ascontiguousarray(g["Q"][0], np.float32))
+        out = subprocess.check_output([sys.executable, "-c", code], stderr=subprocess.STDOUT).decode()
+    T = O.dtable(g["Q"][0], g["cw"], g["variant"])
+    exp = O.query_linear(T, codes, 3)
+    assert str(exp[0].tolist()) in out, out
