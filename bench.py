@@ -137,6 +137,201 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ ours ----
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def kernel_ms(lib, e, name):
+    m_, n_ = C.c_double(0), C.c_int64(0)
+    lib.rii_profile_get(e._h, name.encode(), C.byref(m_), C.byref(n_))
+    return m_.value, n_.value
+
+
+class PackedOut(object):
+    """One byte buffer [ids int64 (B, k) | dists float32 (B, k) | counts int32 (B)] per rank: the library writes its three
+    outputs straight into it and ONE all-gather moves everything (three NCCL launches per step were 9 % of it)."""
+
+    def __init__(self, torch, B, k, dev, world):
+        self.B, self.k = B, k
+        self.nbytes = (B * k * 12 + B * 4 + 7) // 8 * 8
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        self.ids = self.buf[:B * k * 8].view(torch.int64).view(B, k)
+        self.d = self.buf[B * k * 8:B * k * 12].view(torch.float32).view(B, k)
+        self.c = self.buf[B * k * 12:B * k * 12 + B * 4].view(torch.int32)
+        self.gathered = torch.zeros((world, self.nbytes), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def rank_ids(self, torch, r):
+        return self.gathered[r, :self.B * self.k * 8].view(torch.int64).view(self.B, self.k)
+
+
+def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, peak, cfg, steps, warmup, flush):
+    """BASELINE configs C4 / C5 at their real per-GPU size (weak scaling: every GPU holds Nl codes, N_total = Nl * G; at
+    G = 8 this IS C4 / C5).  Codes are drawn as randint (throughput-only runs); list assignment is drawn too
+    -- K6 over 65536 centers is an index-build cost (tools/build_large.py measures the real build), the scan does not care
+    which rows sit in a list.  Every rank ranks the lists for its B / G queries, the rankings are all-gathered, every rank
+    scans its shard for all B queries, per-shard top-k are all-gathered (one packed collective) and merged."""
+    D, M, Ks, nlist, Nl, B, k = cfg["D"], cfg["M"], 256, cfg["nlist"], cfg["Nl"], cfg["B"], cfg["topk"]
+    N_total = Nl * world
+    L0 = int(round(N_total / nlist))
+    L = min(32 * L0, N_total)
+    rng = np.random.default_rng(2024)
+    cw = rng.random((M, Ks, D // M), dtype=np.float32)
+    centers = rng.integers(0, Ks, (nlist, M), dtype=np.uint8)
+    Q = torch.from_numpy(rng.random((4 * B, D), dtype=np.float32)).to(dev)
+    e = main.RiiCpp(cw, False, device=dev.index, l2_variant=16)
+    t0 = time.time()
+    _capi.check(lib.rii_reserve(e._h, Nl))
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    keep = []  # (first row, codes) of the chunks kept for the parity check
+    chunk = 1 << 23
+    for s0 in range(0, Nl, chunk):
+        c = min(chunk, Nl - s0)
+        t = torch.randint(0, 256, (c, M), dtype=torch.uint8, device=dev, generator=gen)
+        _capi.check(lib.rii_add_codes_dev(e._h, _ptr(t), c, 0))
+        if s0 == 0:
+            keep.append((0, t))
+    assign = torch.randint(0, nlist, (Nl,), dtype=torch.int32, device=dev, generator=gen)
+    _capi.check(lib.rii_set_shard(e._h, rank * Nl, N_total))
+    _capi.check(lib.rii_set_lists_dev(e._h, centers.ctypes.data_as(C.POINTER(C.c_uint8)), nlist, _ptr(assign)))
+    lens = torch.bincount(assign, minlength=nlist).to(torch.int32)
+    if world > 1:
+        g = torch.empty((world, nlist), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(g.view(-1), lens)
+    else:
+        g = lens[None]
+    glob = g.sum(0, dtype=torch.int32).cpu().numpy()
+    pre = (g[:rank].sum(0, dtype=torch.int32) if rank else torch.zeros_like(lens)).cpu().numpy()
+    _capi.check(lib.rii_set_global_lengths(e._h, glob.ctypes.data_as(C.POINTER(C.c_int32)), pre.ctypes.data_as(C.POINTER(C.c_int32))))
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    w = _capi.check(lib.rii_coarse_width(e._h, L))
+    Bl = B // world
+    ranked_l = torch.empty((Bl, w), dtype=torch.int32, device=dev)
+    ranked = torch.empty((B, w), dtype=torch.int32, device=dev) if world > 1 else ranked_l
+    po = PackedOut(torch, B, k, dev, world)
+    flags = torch.zeros((B,), dtype=torch.int32, device=dev)
+    f_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    f_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+    f_c = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step(i):
+        q = Q[(i % 4) * B:(i % 4 + 1) * B]
+        _capi.check(lib.rii_coarse_rank_dev(e._h, _ptr(q[rank * Bl:(rank + 1) * Bl]), Bl, k, L, _ptr(ranked_l), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(ranked.view(-1), ranked_l.view(-1))
+        _capi.check(lib.rii_query_ranked_dev(e._h, _ptr(q), B, k, L, _ptr(ranked), _ptr(po.ids), _ptr(po.d), _ptr(po.c), _ptr(flags), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(po.gathered.view(-1), po.buf)
+            _capi.check(lib.rii_merge_shards_packed_dev(e._h, _ptr(po.gathered), po.nbytes, world, B, k, _ptr(f_ids), _ptr(f_d), _ptr(f_c), sp))
+            return f_ids
+        return po.ids
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_flagged = int((flags & 1).sum().item())
+    lib.rii_profile_enable(e._h, 1)
+    lib.rii_profile_reset(e._h)
+    evs = []
+    for i in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        step(warmup + i)
+        b.record(st)
+        evs.append((a, b))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    scan_ms, scan_n = kernel_ms(lib, e, "scan_ivf")
+    coarse_ms, coarse_n = kernel_ms(lib, e, "coarse_rank")
+    lib.rii_profile_enable(e._h, 0)
+    per_scan = scan_ms / max(scan_n, 1)
+    # what this rank's scan launch actually streamed: the planned local candidates (ids are read for survivors only)
+    local_rows = float(L) / world
+    alg = B * (local_rows * M + 4 * M * Ks)
+    out = {"workload": "%s: N=%d (%d per GPU x %d) D=%d M=%d nlist=%d IVF L=%d (w=%d lists) topk=%d batch=%d; random codes + random list "
+                       "assignment (throughput only)" % (cfg["name"], N_total, Nl, world, D, M, nlist, L, w, k, B),
+           "ms_per_batch_this_rank": round(ms / steps, 4), "index_build_s": round(t_build, 2), "flagged_queries": n_flagged,
+           "scan_kernel_ms": round(per_scan, 4), "coarse_kernel_ms": round(coarse_ms / max(coarse_n, 1), 4),
+           "scan_algorithmic_bytes": int(alg), "scan_GBps_per_gpu": round(alg / (per_scan * 1e-3) / 1e9, 1) if per_scan > 0 else None,
+           "scan_frac_of_hbm_peak": round(alg / (per_scan * 1e-3) / 1e9 / peak, 4) if per_scan > 0 else None}
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["ms_per_batch"] = round(float(t.item()) / steps, 4)
+    out["queries_per_s"] = round(steps * B / (float(t.item()) * 1e-3), 1)
+    # ---- parity at full scale (rank 0): the shard's part of the answer against a numpy / oracle restatement --------------
+    if rank == 0:
+        try:
+            from oracle import oracle as O
+            q = Q[:B]
+            step(0)
+            torch.cuda.synchronize()
+            got_ids, got_d, got_c = po.ids.cpu().numpy(), po.d.cpu().numpy(), po.c.cpu().numpy()
+            rk = ranked.cpu().numpy()
+            ok = True
+            for bq in (0, B // 2, B - 1):
+                T = O.dtable(q[bq].cpu().numpy(), cw, 16)
+                cd = O.adist_all(T, centers)
+                order = np.lexsort((np.arange(nlist), cd))[:w]
+                ok &= bool(np.array_equal(order, rk[bq]))
+                P, rows = 0, []
+                for j, no in enumerate(order):  # SURVEY A.3 with global lengths, this shard's slice of every list
+                    f = int(glob[no])
+                    take = min(f, L - P)
+                    P += take
+                    mine = torch.nonzero(assign == int(no)).flatten()
+                    lt = int(np.clip(take - int(pre[no]), 0, mine.numel()))
+                    rows.append(mine[:lt])
+                    if P >= L or (j == w - 1 and P >= k):
+                        break
+                rows = torch.cat(rows)
+                # rows of the first chunk only are still at hand on the device: regenerate the others
+                codes_rows = regen_rows(torch, dev, rank, Nl, M, chunk, rows)
+                dd = O.adist_all(T, codes_rows)
+                o = np.lexsort((rows.cpu().numpy(), dd))[:k]
+                exp_ids = rows.cpu().numpy()[o] + rank * Nl
+                ok &= bool(int(got_c[bq]) == len(o) and np.array_equal(got_ids[bq, :len(o)], exp_ids) and
+                           np.array_equal(got_d[bq, :len(o)].view(np.uint32), dd[o].view(np.uint32)))
+            # sampled-shard LINEAR parity: the first 200 000 local rows as target ids == oracle scan of those rows
+            ns = min(200000, Nl)
+            tids = torch.arange(rank * Nl, rank * Nl + ns, dtype=torch.int64, device=dev)
+            li = torch.empty((1, 5), dtype=torch.int64, device=dev)
+            ld = torch.empty((1, 5), dtype=torch.float32, device=dev)
+            lc = torch.empty((1,), dtype=torch.int32, device=dev)
+            lib.rii_set_option(e._h, b"scan_kernel", 4)
+            _capi.check(lib.rii_query_batch_dev(e._h, _ptr(q[:1]), 1, 5, _ptr(tids), ns, 0, 0, _ptr(li), _ptr(ld), _ptr(lc), sp))
+            lib.rii_set_option(e._h, b"scan_kernel", 0)
+            torch.cuda.synchronize()
+            exp = O.query_linear(O.dtable(q[0].cpu().numpy(), cw, 16), keep[0][1][:ns].cpu().numpy(), 5)
+            ok &= bool(np.array_equal(li.cpu().numpy()[0], exp[0] + rank * Nl) and
+                       np.array_equal(ld.cpu().numpy()[0].view(np.uint32), exp[1].view(np.uint32)))
+            out["parity_vs_oracle_at_full_scale"] = "ok (3 IVF queries on this shard: ranking, candidate set, ids and distance bits; " \
+                                                    "linear scan over 200000 sampled rows)" if ok else "MISMATCH"
+        except Exception as ex:
+            out["parity_vs_oracle_at_full_scale"] = "error: " + repr(ex)
+    del e
+    torch.cuda.empty_cache()
+    return out
+
+
+def regen_rows(torch, dev, rank, Nl, M, chunk, rows):
+    """Codes of the given local rows, regenerated chunk by chunk with the generator large_sharded_leg used."""
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    out = torch.empty((rows.numel(), M), dtype=torch.uint8, device=dev)
+    for s0 in range(0, Nl, chunk):
+        c = min(chunk, Nl - s0)
+        t = torch.randint(0, 256, (c, M), dtype=torch.uint8, device=dev, generator=gen)
+        sel = torch.nonzero((rows >= s0) & (rows < s0 + c)).flatten()
+        if sel.numel():
+            out[sel] = t[rows[sel] - s0]
+    return out.cpu().numpy()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -155,8 +350,10 @@ def run_ours(args):
     nq = B * min(4, K + W)  # a few distinct query batches, cycled
     cw, codes, Q, gt = make_data(nq, dev)
     N, M, D = CFG["N"], CFG["M"], CFG["D"]
+    peak, peak_src = peaks()
+    props = torch.cuda.get_device_properties(dev)
 
-    # ---- index: id-range shard per rank -----------------------------------------------------------
+    # ---- index: replicated per rank (the metric's N = 1M fits every GPU many times over); --shard: id-range shards ------
     e = main.RiiCpp(cw, False, device=local, l2_variant=16)
     t_build = time.time()
     shard = bool(args.shard) and world > 1
@@ -174,37 +371,35 @@ def run_ours(args):
     sp = C.c_void_p(st.cuda_stream)
     k, L = CFG["topk"], CFG["L"]
     dQ = torch.from_numpy(Q).to(dev)
-    o_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
-    o_d = torch.empty((B, k), dtype=torch.float32, device=dev)
-    o_c = torch.empty((B,), dtype=torch.int32, device=dev)
-    Bl = B if (world == 1 or shard) else B // world  # queries this rank answers per step
     assert B % world == 0
-    if world > 1:
-        g_ids = torch.empty((world, Bl, k), dtype=torch.int64, device=dev)
-        g_d = torch.empty((world, Bl, k), dtype=torch.float32, device=dev)
-        g_c = torch.empty((world, Bl), dtype=torch.int32, device=dev)
-        f_ids, f_d, f_c = torch.empty_like(o_ids), torch.empty_like(o_d), torch.empty_like(o_c)
+    Bl = B if (world == 1 or shard) else B // world  # queries this rank answers per step
+    po = PackedOut(torch, Bl, k, dev, world)
+    f_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    f_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+    f_c = torch.empty((B,), dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def finish_step():
+        """After this rank's results are in po.buf: the one collective of the step, and what the caller reads."""
+        if world == 1:
+            return po.ids
+        dist.all_gather_into_tensor(po.gathered.view(-1), po.buf)
+        if not shard:  # replicas: rank r answered queries [r * Bl, (r + 1) * Bl): every rank now holds all of them
+            return None
+        _capi.check(lib.rii_merge_shards_packed_dev(e._h, _ptr(po.gathered), po.nbytes, world, B, k, _ptr(f_ids), _ptr(f_d), _ptr(f_c), sp))
+        return f_ids
 
     def step_dev(i):
         q = dQ[(i % (nq // B)) * B:(i % (nq // B) + 1) * B]
-        if world > 1 and not shard:  # replicas: this rank's slice of the batch, then all-gather of the results
+        if world > 1 and not shard:
             q = q[rank * Bl:(rank + 1) * Bl]
-        _capi.check(lib.rii_query_batch_dev(e._h, C.c_void_p(q.data_ptr()), Bl, k, None, 0, L, 1,
-                                            C.c_void_p(o_ids.data_ptr()), C.c_void_p(o_d.data_ptr()),
-                                            C.c_void_p(o_c.data_ptr()), sp))
-        if world > 1:
-            dist.all_gather_into_tensor(g_ids.view(-1), o_ids[:Bl].reshape(-1))
-            dist.all_gather_into_tensor(g_d.view(-1), o_d[:Bl].reshape(-1))
-            dist.all_gather_into_tensor(g_c.view(-1), o_c[:Bl])
-            if not shard:
-                return g_ids.view(B, k)
-            _capi.check(lib.rii_merge_shards_dev(e._h, C.c_void_p(g_ids.data_ptr()), C.c_void_p(g_d.data_ptr()),
-                                                 C.c_void_p(g_c.data_ptr()), world, B, k,
-                                                 C.c_void_p(f_ids.data_ptr()), C.c_void_p(f_d.data_ptr()),
-                                                 C.c_void_p(f_c.data_ptr()), sp))
-            return f_ids
-        return o_ids
+        _capi.check(lib.rii_query_batch_dev(e._h, _ptr(q), Bl, k, None, 0, L, 1, _ptr(po.ids), _ptr(po.d), _ptr(po.c), sp))
+        return finish_step()
+
+    def all_ids(ret):
+        if ret is not None:
+            return ret.clone()
+        return torch.cat([po.rank_ids(torch, r) for r in range(world)]).clone()
 
     def barrier():
         if world > 1:
@@ -226,11 +421,11 @@ def run_ours(args):
         flush.zero_()  # L2 flush, outside the timed events
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st)
-        ids = step_dev(W + i)
+        ret = step_dev(W + i)
         b.record(st)
         evs.append((a, b))
         if i < nq // B:
-            got.append((W + i, ids.clone()))
+            got.append((W + i, all_ids(ret)))
     barrier()
     launches = lib.rii_launch_count() - launches0
     sampler.stop_flag = True
@@ -239,13 +434,11 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    scan_ms, scan_n = C.c_double(0), C.c_int64(0)
-    lib.rii_profile_get(e._h, b"scan_ivf", C.byref(scan_ms), C.byref(scan_n))
+    scan_ms, scan_n = kernel_ms(lib, e, "scan_ivf")
     prof = {}
     for name in ("dtable", "coarse_rank", "scan_ivf", "merge"):
-        m_, n_ = C.c_double(0), C.c_int64(0)
-        lib.rii_profile_get(e._h, name.encode(), C.byref(m_), C.byref(n_))
-        prof[name] = {"ms_total": round(m_.value, 4), "launches": n_.value}
+        m_, n_ = kernel_ms(lib, e, name)
+        prof[name] = {"ms_total": round(m_, 4), "launches": n_}
     lib.rii_profile_enable(e._h, 0)
     sampler.join(timeout=2)
 
@@ -257,10 +450,11 @@ def run_ours(args):
         tot += B
     recall = hit / max(tot, 1)
 
-    # ---- end-to-end arm: host (pinned) buffers through rii_query_batch ------------------------------
-    e2e = None
+    # ---- end-to-end arm: host (pinned) buffers.  1 GPU: the reference-facing C-ABI call rii_query_batch (H2D of the queries
+    # and D2H of ids / dists / counts inside the call).  N GPUs: every rank copies ITS queries in, answers them, the results
+    # are all-gathered on the device and every rank copies the whole batch's results out.
+    hQ = torch.from_numpy(Q).pin_memory()
     if world == 1:
-        hQ = torch.from_numpy(Q).pin_memory()
         h_ids = torch.empty((B, k), dtype=torch.int64).pin_memory()
         h_d = torch.empty((B, k), dtype=torch.float32).pin_memory()
         h_c = torch.empty((B,), dtype=torch.int32).pin_memory()
@@ -271,14 +465,42 @@ def run_ours(args):
                                             C.cast(h_ids.data_ptr(), C.POINTER(C.c_int64)),
                                             C.cast(h_d.data_ptr(), C.POINTER(C.c_float)),
                                             C.cast(h_c.data_ptr(), C.POINTER(C.c_int32))))
-        for i in range(W):
-            step_host(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(K):
-            step_host(W + i)  # synchronous: returns after the D2H of the results
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        h2d, d2h = B * D * 4, B * k * 12 + B * 4
+    else:
+        dq_l = torch.empty((Bl, D), dtype=torch.float32, device=dev)
+        h_all = torch.empty((world, po.nbytes), dtype=torch.uint8).pin_memory()
+        h_fin = torch.empty((B * k * 12 + B * 4,), dtype=torch.uint8).pin_memory()
+
+        def step_host(i):
+            q = hQ[(i % (nq // B)) * B:(i % (nq // B) + 1) * B]
+            if not shard:
+                q = q[rank * Bl:(rank + 1) * Bl]
+            dq_l.copy_(q, non_blocking=True)
+            _capi.check(lib.rii_query_batch_dev(e._h, _ptr(dq_l), Bl, k, None, 0, L, 1, _ptr(po.ids), _ptr(po.d), _ptr(po.c), sp))
+            ret = finish_step()
+            if ret is None:
+                h_all.copy_(po.gathered, non_blocking=True)
+            else:
+                h_fin[:B * k * 8].copy_(f_ids.view(-1).view(torch.uint8), non_blocking=True)
+                h_fin[B * k * 8:B * k * 12].copy_(f_d.view(-1).view(torch.uint8), non_blocking=True)
+                h_fin[B * k * 12:].copy_(f_c.view(torch.uint8), non_blocking=True)
+            st.synchronize()
+        h2d, d2h = Bl * D * 4, (world * po.nbytes if not shard else B * k * 12 + B * 4)
+    for i in range(W):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_host(W + i)  # synchronous: returns after the D2H of the results
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": round(K * B / dt, 1), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "note": "per rank" if world > 1 else "rii_query_batch (C ABI, host buffers)"}
+    if world == 1:
         # single-query latency through the reference's own call shape (query_ivf, one query per call)
         qs = Q[:200]
         for q in qs[:10]:
@@ -286,59 +508,102 @@ def run_ours(args):
         t1 = time.perf_counter()
         for q in qs:
             e.query_ivf(q, k, np.empty(0, np.int64), L)
-        lat = (time.perf_counter() - t1) / len(qs)
-        e2e = {"value": round(K * B / dt, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
-               "d2h_bytes_per_step": B * k * 12 + B * 4, "single_query_call_us": round(lat * 1e6, 1)}
+        e2e["single_query_call_us"] = round((time.perf_counter() - t1) / len(qs) * 1e6, 1)
+
+    # ---- C3 (BASELINE configs[2]): subset search, target_ids = 100k random ids, 256 queries per call -----------------
+    subset = None
+    if world == 1 and not args.quick:
+        try:
+            Bs, S = 256, 100000
+            tids = torch.from_numpy(np.sort(np.random.default_rng(3).choice(N, S, replace=False)).astype(np.int64)).to(dev)
+            so = PackedOut(torch, Bs, k, dev, 1)
+            subset = {"workload": "C3: N=1M M=32 target_ids=100k random (sorted), %d queries per call, topk=1" % Bs}
+            for name, method, Ls in (("linear", 0, 0), ("ivf", 1, L)):
+                ev = []
+                for it in range(13):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(st)
+                    _capi.check(lib.rii_query_batch_dev(e._h, _ptr(dQ[it * Bs:(it + 1) * Bs]), Bs, k, _ptr(tids), S, Ls, method,
+                                                        _ptr(so.ids), _ptr(so.d), _ptr(so.c), sp))
+                    b.record(st)
+                    if it >= 3:
+                        ev.append((a, b))
+                torch.cuda.synchronize()
+                subset[name + "_queries_per_s"] = round(len(ev) * Bs / (sum(a.elapsed_time(b) for a, b in ev) * 1e-3), 1)
+        except Exception as ex:
+            subset = {"error": repr(ex)}
 
     # ---- the HBM-bound side of the same engine: linear PQ-code scan over N >> L2 (north_star's ">= 70 % of the HBM
-    # roofline on the code scan"); random codes (throughput only), 1 query per launch, CUDA events inside the library
+    # roofline on the code scan at N = 1B"); random codes (throughput only), 1 query per launch, CUDA events inside the library
     lin = None
     if world == 1 and args.linear_n > 0:
-        try:
-            e.set_option("fuse_coarse", 1)
-            el = main.RiiCpp(cw, False, device=local, l2_variant=16)
-            nl, chunk = int(args.linear_n), 8000000
-            gen = torch.Generator(device=dev).manual_seed(7)
-            for s0 in range(0, nl, chunk):
-                c = min(chunk, nl - s0)
-                el.add_codes(torch.randint(0, 256, (c, M), dtype=torch.uint8, device=dev, generator=gen).cpu().numpy(), False)
-            lib.rii_profile_enable(el._h, 1)
-            q1 = dQ[:1]
-            li = torch.empty((1, 1), dtype=torch.int64, device=dev)
-            ld = torch.empty((1, 1), dtype=torch.float32, device=dev)
-            lc = torch.empty((1,), dtype=torch.int32, device=dev)
-            for it in range(13):
-                if it == 3:
-                    torch.cuda.synchronize()
-                    lib.rii_profile_reset(el._h)
-                flush.zero_()
-                _capi.check(lib.rii_query_batch_dev(el._h, C.c_void_p(q1.data_ptr()), 1, 1, None, 0, 0, 0,
-                                                    C.c_void_p(li.data_ptr()), C.c_void_p(ld.data_ptr()),
-                                                    C.c_void_p(lc.data_ptr()), sp))
-            torch.cuda.synchronize()
-            m_, n_ = C.c_double(0), C.c_int64(0)
-            lib.rii_profile_get(el._h, b"scan_linear", C.byref(m_), C.byref(n_))
-            lms = m_.value / max(n_.value, 1)
-            lin = {"kernel": "k_scan_stream32<NW=12, linear, 4-stage rings, 1 CTA/SM>", "workload": "linear scan, N=%d M=32 (random codes), topk=1, 1 query/launch" % nl,
-                   "bound": "hbm", "launch_ms": round(lms, 4), "algorithmic_bytes_per_launch": nl * M + 4 * M * CFG["Ks"],
-                   "achieved": round((nl * M + 4 * M * CFG["Ks"]) / (lms * 1e-3) / 1e9, 1), "unit": "GB/s"}
-            del el
-        except Exception as ex:  # never lose the headline line over the side measurement
-            lin = {"error": repr(ex)}
+        for nl in ([int(args.linear_n), 64000000] if int(args.linear_n) > 64000000 else [int(args.linear_n)]):
+            el = None
+            try:
+                el = main.RiiCpp(cw, False, device=local, l2_variant=16)
+                _capi.check(lib.rii_reserve(el._h, nl))
+                chunk = 1 << 24
+                gen = torch.Generator(device=dev).manual_seed(7)
+                for s0 in range(0, nl, chunk):
+                    c = min(chunk, nl - s0)
+                    t = torch.randint(0, 256, (c, M), dtype=torch.uint8, device=dev, generator=gen)
+                    _capi.check(lib.rii_add_codes_dev(el._h, _ptr(t), c, 0))
+                del t
+                lib.rii_profile_enable(el._h, 1)
+                q1 = dQ[:1]
+                lo = PackedOut(torch, 1, 1, dev, 1)
+                for it in range(13):
+                    if it == 3:
+                        torch.cuda.synchronize()
+                        lib.rii_profile_reset(el._h)
+                    flush.zero_()
+                    _capi.check(lib.rii_query_batch_dev(el._h, _ptr(q1), 1, 1, None, 0, 0, 0, _ptr(lo.ids), _ptr(lo.d), _ptr(lo.c), sp))
+                torch.cuda.synchronize()
+                m_, n_ = kernel_ms(lib, el, "scan_linear")
+                lms = m_ / max(n_, 1)
+                lin = {"kernel": "k_scan_stream32<NW=12, linear, 4-stage rings, 1 CTA/SM>",
+                       "workload": "linear scan, N=%d M=32 (random codes), topk=1, 1 query/launch" % nl,
+                       "bound": "hbm", "launch_ms": round(lms, 4), "algorithmic_bytes_per_launch": nl * M + 4 * M * CFG["Ks"],
+                       "achieved": round((nl * M + 4 * M * CFG["Ks"]) / (lms * 1e-3) / 1e9, 1), "unit": "GB/s", "peak": peak}
+                lin["frac"] = round(lin["achieved"] / peak, 4)
+                del el
+                torch.cuda.empty_cache()
+                break
+            except Exception as ex:  # never lose the headline line over the side measurement (e.g. not enough memory for N = 1B)
+                lin = {"error": repr(ex), "N": nl}
+                del el
+                torch.cuda.empty_cache()
+
+    # ---- C4 / C5 at their real per-GPU size, sharded (weak scaling) ------------------------------------------------------
+    large = None
+    if not args.no_large:
+        large = []
+        for cfg in (dict(name="C5", D=96, M=32, nlist=65536, Nl=125000000, B=1024, topk=1),
+                    dict(name="C4", D=128, M=64, nlist=10000, Nl=12500000, B=1024, topk=1)):
+            try:
+                large.append(large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, peak, cfg, max(3, min(K, 10)), 3, flush))
+            except Exception as ex:
+                large.append({"workload": cfg["name"], "error": repr(ex)})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak, peak_src = peaks()
-    # algorithmic bytes of the dominant kernel (posting-list scan), per launch: per query C*M code bytes
-    # (C = L candidates) + 4*M*Ks (its distance table).  SURVEY's V*4 bytes of visited ids are NOT counted: the
-    # kernel streams a list-ordered (skew64) code copy and reads ids only for survivors; the nlist*M center bytes of
-    # the fused coarse pass are not counted either (3 % of C*M at C2).
+    # The dominant kernel (posting-list scan, fused with table build + coarse pass + plan) per launch.  SURVEY 8d's per-query
+    # algorithmic bytes: C*M code bytes (C = L candidates) + 4*M*Ks (its distance table); the V*4 bytes of visited ids are
+    # not counted (the kernel streams a list-ordered skew64 copy and reads ids for survivors only), nor the nlist*M center bytes.
+    # At N = 1M the 32 MB code table is L2-resident, so the binding resource is the shared-memory LOOKUP rate (one 4-byte
+    # lookup per code byte; peak = SMs x 32 lookups / clk), not HBM: the roofline is quoted against that, HBM and L2 beside it.
     frac_scanned = 1.0 / world if shard else 1.0
-    q_per_launch = K * Bl / max(scan_n.value, 1)  # the library processes a step in chunks of <= 32768 queries
+    q_per_launch = K * Bl / max(scan_n, 1)  # the library processes a step in chunks of <= 32768 queries
     alg = q_per_launch * (L * frac_scanned * M + 4 * M * CFG["Ks"])
-    launch_ms = scan_ms.value / max(scan_n.value, 1)
-    achieved = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
+    lookups = q_per_launch * (L * frac_scanned + CFG["nlist"]) * M
+    launch_ms = scan_ms / max(scan_n, 1)
+    clocks = sampler.summary()
+    sm_mhz = clocks.get("sm_max_mhz") or 1965
+    lookup_peak = props.multi_processor_count * 32 * sm_mhz * 1e6 / 1e12
+    achieved_l = lookups / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else None
+    achieved_b = alg / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None
     line = {
         "metric": "queries/sec at recall@1 (N=1M, D=128, M=32)", "value": round(K * B / (ms * 1e-3), 1),
         "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
@@ -348,25 +613,30 @@ def run_ours(args):
                    "arithmetic": "uint8 codes index float32 tables; float32 adds in the reference's order (bit-exact)",
                    "batch_queries_per_step": B, "l2": "flushed between steps (256 MB write)",
                    "parallelism": "1 GPU" if world == 1 else
-                   ("id-range shards x%d + NCCL all-gather of per-shard top-k + merge" % world if shard else
-                    "index replicated x%d, queries split, NCCL all-gather of results" % world),
+                   ("id-range shards x%d + one packed NCCL all-gather of per-shard top-k + merge" % world if shard else
+                    "index replicated x%d, queries split, one packed NCCL all-gather of the results" % world),
                    "index_build_s": round(t_build, 2)},
         "recall_at_1": round(recall, 4),
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-        "roofline": {"kernel": "k_scan_stream32<NW=6, IVF fused (table + coarse + plan + scan), 3-stage rings, 2 CTAs/SM>", "bound": "hbm", "achieved": None if achieved is None else round(achieved, 1),
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": None if achieved is None else round(achieved / peak, 4), "traffic": None,
-                     "algorithmic_bytes_per_launch": int(alg), "queries_per_launch": int(q_per_launch),
-                     "launch_ms": round(launch_ms, 4),
-                     "note": "the 32 MB code table is L2-resident at N=1M: DRAM traffic << algorithmic bytes; the "
-                             "binding resource is the shared-memory lookup rate (1 wavefront per 32 lookups) plus the per-query "
-                             "serial phases; the HBM-bound case of the same engine is roofline_linear_scan (DESIGN.md)"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": "k_scan_stream32<IVF fused: table + coarse pass + select + plan + scan + top-k>",
+                     "bound": "smem-lookup", "achieved": None if achieved_l is None else round(achieved_l, 3), "peak": round(lookup_peak, 3),
+                     "unit": "Tlookup/s", "frac": None if achieved_l is None else round(achieved_l / lookup_peak, 4),
+                     "peak_source": "%d SMs x 32 four-byte shared-memory lookups / clk x %d MHz" % (props.multi_processor_count, sm_mhz),
+                     "traffic": None, "lookups_per_launch": int(lookups), "algorithmic_bytes_per_launch": int(alg),
+                     "queries_per_launch": int(q_per_launch), "launch_ms": round(launch_ms, 4),
+                     "hbm": {"achieved": None if achieved_b is None else round(achieved_b, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                             "frac": None if achieved_b is None else round(achieved_b / peak, 4),
+                             "note": "algorithmic code + table bytes over the launch time; the 32 MB table is L2-resident at N=1M, so "
+                                     "DRAM traffic (`traffic`) is a small fraction of it: the HBM-bound case of the same engine is "
+                                     "roofline_linear_scan and the sharded C4/C5 legs"}},
         "kernel_ms": prof,
     }
     if lin is not None:
-        if "achieved" in lin:
-            lin.update({"peak": peak, "frac": round(lin["achieved"] / peak, 4)})
         line["roofline_linear_scan"] = lin
+    if subset is not None:
+        line["subset_search"] = subset
+    if large is not None:
+        line["sharded_large"] = large
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(cw, codes, Q)
     try:  # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (tools/ncu_summary.py)
@@ -377,7 +647,7 @@ def run_ours(args):
         line["roofline"]["traffic"] = None if t_ivf is None else int(t_ivf * q_per_launch / q_ivf)
         line["roofline"]["traffic_source"] = tr.get("source")
         if lin is not None and "achieved" in lin:
-            lin["traffic"] = tr.get("k_scan_stream32_linear_N64M_bytes_per_launch") if int(args.linear_n) == 64000000 else None
+            lin["traffic"] = tr.get("k_scan_stream32_linear_N64M_bytes_per_launch") if "N=64000000 " in lin["workload"] else None
     except Exception:
         pass
     print(json.dumps(line))
@@ -455,8 +725,11 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="queries per step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--linear-n", type=int, default=64000000,
-                    help="also time the HBM-bound linear scan over this many random codes (0 = skip); 1 GPU only")
+    ap.add_argument("--linear-n", type=int, default=1000000000,
+                    help="also time the HBM-bound linear scan over this many random codes (0 = skip; falls back to 64M if "
+                         "the GPU cannot hold it); 1 GPU only")
+    ap.add_argument("--no-large", action="store_true", help="skip the C4 / C5 sharded legs (weak scaling, 12.5M / 125M codes per GPU)")
+    ap.add_argument("--quick", action="store_true", help="skip the C3 subset leg")
     ap.add_argument("--shard", action="store_true", help="multi-GPU: partition the index by id range instead of replicating it")
     a = ap.parse_args()
     if a.warmup < 3:

@@ -122,6 +122,11 @@ int rii_copy_list_lengths(const rii_index_t *h, int32_t *out);
 /* Global list lengths and the lengths held by lower ranks (both (nlist) int32), from the all-gather. */
 int rii_set_global_lengths(rii_index_t *h, const int32_t *glob_len, const int32_t *pre_len);
 
+/* Posting lists from an EXTERNAL clustering: coarse centers (host, (nlist, M)) and the list of every local row (device
+ * int32 (N), values in [0, nlist)); the lists are built on the device (ascending ids per list), K6 is skipped. */
+int rii_set_lists_dev(rii_index_t *h, const uint8_t *centers, int nlist, const int32_t *d_assign);
+/* Pre-allocate the code table for `rows` codes (large builds: no regrowth copies). */
+int rii_reserve(rii_index_t *h, int64_t rows);
 /* First min(N_total, 100*nlist) ids of the reference's sampling shuffle (src/rii.h:115-124; host only).
  * Call with out_ids == NULL to get the count in *out_n. */
 int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n);
@@ -130,6 +135,11 @@ int rii_sample_ids(int64_t N_total, int nlist, int64_t *out_ids, int64_t *out_n)
  * rii_query_batch_dev outputs produces. */
 int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_dists, const int32_t *d_counts, int G,
                          int B, int k, int64_t *d_out_ids, float *d_out_dists, int32_t *d_out_counts, void *stream);
+
+/* The same merge over ONE packed buffer (a single all-gather): shard g's block starts at g * stride_bytes and holds
+ * [ids int64 (B, k) | dists float32 (B, k) | counts int32 (B)]; stride_bytes must be a multiple of 8. */
+int rii_merge_shards_packed_dev(rii_index_t *h, const void *d_packed, int64_t stride_bytes, int G, int B, int k, int64_t *d_out_ids,
+                                float *d_out_dists, int32_t *d_out_counts, void *stream);
 
 /* IVF + target_ids on an id-range shard (the binary_search filter of src/rii.h:294 with the ids spread over shards):
  * the cut after L member candidates and the topk test at the w-th list are global, so every shard needs the member

@@ -47,6 +47,9 @@ SYMBOLS = {
     "rii_copy_list_lengths": (C.c_int, [_vp, _i32p]),
     "rii_set_global_lengths": (C.c_int, [_vp, _i32p, _i32p]),
     "rii_sample_ids": (C.c_int, [C.c_int64, C.c_int, _i64p, _i64p]),
+    "rii_set_lists_dev": (C.c_int, [_vp, _u8p, C.c_int, _vp]),
+    "rii_reserve": (C.c_int, [_vp, C.c_int64]),
+    "rii_merge_shards_packed_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "rii_merge_shards_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "rii_subset_begin_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "rii_subset_set_global_dev": (C.c_int, [_vp, _vp, _vp, _vp]),

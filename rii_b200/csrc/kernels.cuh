@@ -225,20 +225,24 @@ __global__ void __launch_bounds__(RII_THREADS) k_merge(const u64 *__restrict__ p
 // Cross-shard merge: per query, the G per-shard top-k lists (global 64-bit ids, ascending
 // (dist, id) each) gathered over NVLink are merged into the global top-k.  grid (B); P = pow2 >= G*k.
 __global__ void __launch_bounds__(RII_THREADS) k_merge_shards(const long long *__restrict__ ids, const float *__restrict__ dists,
-                                                              const int *__restrict__ counts, int G, int B, int k, int P,
-                                                              long long *out_ids, float *out_dists, int *out_counts)
+                                                              const int *__restrict__ counts, long long stride_bytes, int G, int B, int k,
+                                                              int P, long long *out_ids, float *out_dists, int *out_counts)
 {
+    // stride_bytes == 0: three contiguous arrays (G, B, k) / (G, B, k) / (G, B).  Otherwise shard g's [ids | dists | counts]
+    // block starts g * stride_bytes after each base pointer (one packed all-gather buffer).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     long long *s_id = reinterpret_cast<long long *>(smem_raw);
     uint32_t *s_d = reinterpret_cast<uint32_t *>(smem_raw + (size_t)P * 8);
     const int b = blockIdx.x;
+    const size_t s_ids = stride_bytes ? (size_t)stride_bytes / 8 : (size_t)B * k, s_dst = stride_bytes ? (size_t)stride_bytes / 4 : (size_t)B * k,
+                 s_cnt = stride_bytes ? (size_t)stride_bytes / 4 : (size_t)B;
     int total = 0;
-    for (int g = 0; g < G; ++g) total += counts[(size_t)g * B + b];
+    for (int g = 0; g < G; ++g) total += counts[g * s_cnt + b];
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         int g = i / k, j = i % k;
-        bool valid = g < G && j < counts[(size_t)g * B + b];
-        s_id[i] = valid ? ids[((size_t)g * B + b) * k + j] : 0x7fffffffffffffffll;
-        s_d[i] = valid ? __float_as_uint(dists[((size_t)g * B + b) * k + j]) : 0xffffffffu;
+        bool valid = g < G && j < counts[g * s_cnt + b];
+        s_id[i] = valid ? ids[g * s_ids + (size_t)b * k + j] : 0x7fffffffffffffffll;
+        s_d[i] = valid ? __float_as_uint(dists[g * s_dst + (size_t)b * k + j]) : 0xffffffffu;
     }
     __syncthreads();
     for (int kk = 2; kk <= P; kk <<= 1)

@@ -351,13 +351,15 @@ int grow_assign(rii_index *h, long long rows)
 // src/rii.h:335-359 UpdatePostingLists(start, num): assign rows [start, start + num) on the GPU and append their ids to
 // the lists, all on the device: a stable radix sort of the (list, id) pairs keeps every list ascending in id (new ids
 // are larger than every id already listed), the per-list segments are merged behind the old lists.
-int update_posting_lists(rii_index *h, long long start, long long num)
+int update_posting_lists(rii_index *h, long long start, long long num, const int *d_given_assign = nullptr)
 {
     if (num <= 0) return finish_lists(h);
     const int nlist = h->nlist;
     CKR(grow_assign(h, start + num));
     int *d_new = h->assign.as<int>() + start;
-    {
+    if (d_given_assign) {  // lists from an external clustering: no K6
+        CK(cudaMemcpyAsync(d_new, d_given_assign, (size_t)num * 4, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
         AssignSrc src;
         DevBuf tmp_skew;
         int rc = make_assign_src(h, h->d_codes + start * h->M, num, &tmp_skew, &src);
@@ -1541,7 +1543,7 @@ int rii_merge_shards_dev(rii_index_t *h, const int64_t *d_ids, const float *d_di
     const size_t smem = (size_t)P * 12;
     CKR(set_smem(k_merge_shards, smem));
     Prof pr(h, st, PK_MERGE);
-    k_merge_shards<<<B, RII_THREADS, smem, st>>>((const long long *)d_ids, d_dists, d_counts, G, B, k, P, (long long *)d_out_ids,
+    k_merge_shards<<<B, RII_THREADS, smem, st>>>((const long long *)d_ids, d_dists, d_counts, 0, G, B, k, P, (long long *)d_out_ids,
                                                  d_out_dists, d_out_counts);
     LAUNCHED();
     CK(cudaGetLastError());
@@ -1746,6 +1748,42 @@ int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total)
     h->id_base = id_base;
     h->N_total = N_total;
     h->shard_stale = false;
+    return 0;
+}
+
+int rii_set_lists_dev(rii_index_t *h, const uint8_t *centers, int nlist, const int32_t *d_assign)
+{
+    if (!h || !centers || nlist <= 0 || !d_assign) return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    CKR(set_centers(h, centers, nlist));
+    return update_posting_lists(h, 0, h->N, d_assign);
+}
+
+int rii_reserve(rii_index_t *h, int64_t rows)
+{
+    if (!h || rows < 0) return fail(RII_ERR_ARG, "bad arguments");
+    if (rows >= (1ll << 31)) return fail(RII_ERR_LIMIT, "a shard holds at most 2^31-1 codes");
+    CK(cudaSetDevice(h->device));
+    return grow_codes(h, rows);
+}
+
+int rii_merge_shards_packed_dev(rii_index_t *h, const void *d_packed, int64_t stride_bytes, int G, int B, int k, int64_t *d_out_ids,
+                                float *d_out_dists, int32_t *d_out_counts, void *stream)
+{
+    if (!h || !d_packed || G <= 0 || B <= 0 || k <= 0 || stride_bytes < (int64_t)B * k * 12 + (int64_t)B * 4)
+        return fail(RII_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = next_pow2(G * k < 2 ? 2 : G * k);
+    const size_t smem = (size_t)P * 12;
+    CKR(set_smem(k_merge_shards, smem));
+    Prof pr(h, st, PK_MERGE);
+    const char *base = (const char *)d_packed;
+    k_merge_shards<<<B, RII_THREADS, smem, st>>>((const long long *)base, (const float *)(base + (size_t)B * k * 8),
+                                                 (const int *)(base + (size_t)B * k * 12), stride_bytes, G, B, k, P, (long long *)d_out_ids,
+                                                 d_out_dists, d_out_counts);
+    LAUNCHED();
+    CK(cudaGetLastError());
     return 0;
 }
 
