@@ -204,6 +204,8 @@ def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, p
     _capi.check(lib.rii_set_global_lengths(e._h, glob.ctypes.data_as(C.POINTER(C.c_int32)), pre.ctypes.data_as(C.POINTER(C.c_int32))))
     torch.cuda.synchronize()
     t_build = time.time() - t0
+    if os.environ.get("RII_LARGE_CTAS"):
+        lib.rii_set_option(e._h, b"stream_ctas", int(os.environ["RII_LARGE_CTAS"]))
     w = _capi.check(lib.rii_coarse_width(e._h, L))
     Bl = B // world
     ranked_l = torch.empty((Bl, w), dtype=torch.int32, device=dev)
@@ -273,12 +275,14 @@ def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, p
             torch.cuda.synchronize()
             got_ids, got_d, got_c = po.ids.cpu().numpy(), po.d.cpu().numpy(), po.c.cpu().numpy()
             rk = ranked.cpu().numpy()
-            ok = True
+            ok, why = True, []
             for bq in (0, B // 2, B - 1):
                 T = O.dtable(q[bq].cpu().numpy(), cw, 16)
                 cd = O.adist_all(T, centers)
                 order = np.lexsort((np.arange(nlist), cd))[:w]
-                ok &= bool(np.array_equal(order, rk[bq]))
+                if not np.array_equal(order, rk[bq]):
+                    ok = False
+                    why.append("ranking of query %d" % bq)
                 P, rows = 0, []
                 for j, no in enumerate(order):  # SURVEY A.3 with global lengths, this shard's slice of every list
                     f = int(glob[no])
@@ -295,8 +299,11 @@ def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, p
                 dd = O.adist_all(T, codes_rows)
                 o = np.lexsort((rows.cpu().numpy(), dd))[:k]
                 exp_ids = rows.cpu().numpy()[o] + rank * Nl
-                ok &= bool(int(got_c[bq]) == len(o) and np.array_equal(got_ids[bq, :len(o)], exp_ids) and
-                           np.array_equal(got_d[bq, :len(o)].view(np.uint32), dd[o].view(np.uint32)))
+                if not (int(got_c[bq]) == len(o) and np.array_equal(got_ids[bq, :len(o)], exp_ids) and
+                        np.array_equal(got_d[bq, :len(o)].view(np.uint32), dd[o].view(np.uint32))):
+                    ok = False
+                    why.append("ivf result of query %d: got %s %s, expected %s %s (%d candidate rows)" % (
+                        bq, got_ids[bq, :int(got_c[bq])].tolist(), got_d[bq, :int(got_c[bq])].tolist(), exp_ids.tolist(), dd[o].tolist(), len(rows)))
             # sampled-shard LINEAR parity: the first 200 000 local rows as target ids == oracle scan of those rows
             ns = min(200000, Nl)
             tids = torch.arange(rank * Nl, rank * Nl + ns, dtype=torch.int64, device=dev)
@@ -308,10 +315,12 @@ def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, p
             lib.rii_set_option(e._h, b"scan_kernel", 0)
             torch.cuda.synchronize()
             exp = O.query_linear(O.dtable(q[0].cpu().numpy(), cw, 16), keep[0][1][:ns].cpu().numpy(), 5)
-            ok &= bool(np.array_equal(li.cpu().numpy()[0], exp[0] + rank * Nl) and
-                       np.array_equal(ld.cpu().numpy()[0].view(np.uint32), exp[1].view(np.uint32)))
+            if not (np.array_equal(li.cpu().numpy()[0], exp[0] + rank * Nl) and
+                    np.array_equal(ld.cpu().numpy()[0].view(np.uint32), exp[1].view(np.uint32))):
+                ok = False
+                why.append("sampled linear scan: got %s, expected %s" % (li.cpu().numpy()[0].tolist(), (exp[0] + rank * Nl).tolist()))
             out["parity_vs_oracle_at_full_scale"] = "ok (3 IVF queries on this shard: ranking, candidate set, ids and distance bits; " \
-                                                    "linear scan over 200000 sampled rows)" if ok else "MISMATCH"
+                                                    "linear scan over 200000 sampled rows)" if ok else "MISMATCH: " + "; ".join(why)
         except Exception as ex:
             out["parity_vs_oracle_at_full_scale"] = "error: " + repr(ex)
     del e
@@ -520,6 +529,8 @@ def run_ours(args):
             subset = {"workload": "C3: N=1M M=32 target_ids=100k random (sorted), %d queries per call, topk=1" % Bs}
             for name, method, Ls in (("linear", 0, 0), ("ivf", 1, L)):
                 ev = []
+                lib.rii_profile_enable(e._h, 1)
+                lib.rii_profile_reset(e._h)
                 for it in range(13):
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(st)
@@ -530,6 +541,10 @@ def run_ours(args):
                         ev.append((a, b))
                 torch.cuda.synchronize()
                 subset[name + "_queries_per_s"] = round(len(ev) * Bs / (sum(a.elapsed_time(b) for a, b in ev) * 1e-3), 1)
+                subset[name + "_ms_per_call"] = round(sum(a.elapsed_time(b) for a, b in ev) / len(ev), 4)
+                subset[name + "_kernel_ms_per_call"] = {kn: round(kernel_ms(lib, e, kn)[0] / 13, 4) for kn in
+                                                        ("subset_build", "scan_linear", "scan_ivf", "coarse_rank", "merge", "sort")}
+                lib.rii_profile_enable(e._h, 0)
         except Exception as ex:
             subset = {"error": repr(ex)}
 

@@ -48,7 +48,8 @@ int rii_destroy(rii_index_t *h);
 
 /* RiiCpp::add_codes(codes, update_flag)  src/main.cpp:16, src/rii.h:158-193.  codes: uint8 (n, M). */
 int rii_add_codes(rii_index_t *h, const uint8_t *codes, int64_t n, int update_flag);
-/* Same with the codes already in DEVICE memory on the index's GPU (index builds at 1e8-1e9 codes: no host round trip). */
+/* Same with the codes already in DEVICE memory on the index's GPU (index builds at 1e8-1e9 codes: no host round trip).
+ * Synchronises the device first (the producer of d_codes may run on any stream), like rii_set_lists_dev. */
 int rii_add_codes_dev(rii_index_t *h, const uint8_t *d_codes, int64_t n, int update_flag);
 /* RiiCpp::reconfigure(nlist, iter)  src/main.cpp:15, src/rii.h:108-156 (+ PQk-means src/pqkmeans.cpp). */
 int rii_reconfigure(rii_index_t *h, int nlist, int iter);

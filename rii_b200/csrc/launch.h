@@ -41,3 +41,7 @@ int dev_sort_keys_u64(const unsigned long long *in, unsigned long long *out, lon
 // nseg segments [seg_beg[i], seg_end[i]) of u64 keys, each sorted ascending
 int dev_segsort_keys_u64(const unsigned long long *in, unsigned long long *out, long long n, int nseg, const long long *d_seg_beg,
                          const long long *d_seg_end, SortTmp *tmp, cudaStream_t st);
+
+// ---- scan_persist.cu: persistent warp-specialised IVF batch kernel (k_scan_persist32) ---------------------------------
+bool persist_fits(int row_bytes, int topk, int w_eff, int nlist, bool fused_coarse);
+int launch_persist(const SkewArgs &a, int B, cudaStream_t st);

@@ -50,6 +50,7 @@ int fail(int code, const std::string &msg)
     } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
+#define PS_CAPW_HOST 64
 const size_t SMEM_MAX = 227 * 1024;  // opt-in shared memory per CTA on sm_100
 
 struct DevBuf {
@@ -152,6 +153,7 @@ struct rii_index {
     int opt_debug_clocks = 0;
     int opt_stream_ctas = 0;  // v4 engine: 1 = always one CTA per SM; otherwise per-query IVF batches run two CTAs per SM
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
+    int opt_persist = 1;        // 0 = never, 1 = auto (batches of >= 296 queries), 2 = whenever the shape fits (tests)
     int opt_assign_kernel = 0;  // 0 auto (streaming engine, two CTAs per SM), 1 natural-layout k_assign, 3 streaming engine with one CTA per SM
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
                               // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
@@ -934,6 +936,18 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
         sa.codes = v.skew; sa.offsets = v.offsets; sa.ids = v.ids; sa.skew_off = v.skew_off;
         sa.w_eff = w_eff; sa.Ks = Ks; sa.k = topk; sa.nlist = nlist; sa.plan = p;
         if (fuse || mode == 1 || mode == 0) CKR(ensure_centers_skew(h, st));
+        // batches of independent queries: the persistent warp-specialised kernel (scan_persist.cuh) when the shape fits
+        const bool pers_shape = persist_fits(h->rb, topk, w_eff, nlist, mode == 0) && (mode == 2 || (mode == 0 && h->opt_fuse_coarse));
+        if (mode != 1 && pers_shape && (h->opt_persist == 2 || (h->opt_persist == 1 && B >= 2 * 148)) && !h->opt_debug_clocks) {
+            SkewArgs sp_ = sa;
+            sp_.centers = mode == 0 ? h->centers_skew.as<uint8_t>() : nullptr;
+            sp_.coarse_mode = mode == 0 ? 0 : 2;
+            sp_.cap = PS_CAPW_HOST;
+            out.final = 1;
+            sp_.out = out;
+            Prof pr(h, st, PK_SCAN_IVF);
+            return launch_persist(sp_, B, st);
+        }
         if (fuse) {
             sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; sa.coarse_mode = 0;
             sa.cap = capw; out.final = 1; sa.out = out;
@@ -1218,6 +1232,7 @@ static int add_codes_impl(rii_index_t *h, const uint8_t *codes, int64_t n, int u
                                    "If this is the first addition, please call add_configure(vecs=X)");
     if (h->N + n >= (1ll << 31)) return fail(RII_ERR_LIMIT, "a shard holds at most 2^31-1 codes (posting lists store int32 ids, src/rii.h:82)");
     CK(cudaSetDevice(h->device));
+    if (kind == cudaMemcpyDeviceToDevice) CK(cudaDeviceSynchronize());  // the producer of d_codes may run on any stream of the caller
     const long long N0 = h->N;
     CKR(grow_codes(h, N0 + n));
     if (n) CK(cudaMemcpyAsync(h->d_codes + N0 * h->M, codes, (size_t)n * h->M, kind, h->stream));
@@ -1357,6 +1372,11 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
         if (value != 0 && value != 1 && value != 4)
             return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural-layout kernels) or 4 (skew64 streaming engine)");
         h->opt_scan_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "persist")) {
+        if (value < 0 || value > 2) return fail(RII_ERR_ARG, "persist must be 0 (off), 1 (auto) or 2 (whenever the shape fits)");
+        h->opt_persist = (int)value;
         return 0;
     }
     if (!strcmp(name, "assign_kernel")) {
@@ -1755,6 +1775,7 @@ int rii_set_lists_dev(rii_index_t *h, const uint8_t *centers, int nlist, const i
 {
     if (!h || !centers || nlist <= 0 || !d_assign) return fail(RII_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());  // the producer of d_assign may run on any stream of the caller
     CKR(set_centers(h, centers, nlist));
     return update_posting_lists(h, 0, h->N, d_assign);
 }

@@ -1,0 +1,435 @@
+// ===================================================================================================
+// K1 + K4 + K5 for per-query IVF batches as a PERSISTENT, WARP-SPECIALISED kernel (rows of 32 bytes).
+//
+// What the phase clocks of k_scan_stream32 show for a batch of independent queries (profiles/r01_micro_ivf_*, r02_phase_*):
+// a query's CTA spends 20-25 % of its cycles outside the scan -- table build (K1), coarse pass + selection + plan (K4),
+// final merge -- and during those phases its warps stream nothing; two co-resident CTAs overlap that only partly, and a
+// grid of one CTA per query pays wave quantisation on top (1024 queries over 296 slots = 4 waves for 3.46 waves of work).
+//
+// Here one CTA per SM stays resident and walks its queries (b = blockIdx.x, += gridDim.x).  11 CONSUMER warps do nothing
+// but stream the planned posting-list segments of query i through their private cp.async rings (the engine of
+// scan_stream.cuh: skew64 layout, conflict-free table lut2[ks][64], packed FFMA2 accumulation -- bit-identical sequential
+// fp32 sums, src/rii.h:386-394).  One PRODUCER warp prepares query i + 1 meanwhile, in the other half of double-buffered
+// shared memory: distance table (src/rii.h:361-373), coarse pass over the skew64 centers with that table, selection of the
+// w nearest lists (histogram select), the candidate plan in prefix-sum form (plan_warp) -- or, when the
+// ranking comes from a separate coarse launch (sharded batches), just table + plan -- and it merges the consumers' top-k
+// lists of query i - 1 into the output.  Hand-over by named barriers (bar.sync / bar.arrive, ids 1-4): FULL[p] (table,
+// segments, key buffers of parity p are ready) and DONE[p] (the consumers' lists of parity p are final).
+//
+// Shared memory (227 KB, absolute addresses; the dynamic window starts at 0x400):
+//   0x00400  segments[2] | key buffers[2] | plan inputs | histogram | coarse distances (nlist <= 1024) | selection keys
+//            | producer ring | 5 consumer rings
+//   0x10000  table of parity 0 (64 KB)        0x20000  table of parity 1 (64 KB)
+//   0x30000  6 consumer rings (3 stages x 2 KB each)                                                   0x39000 end
+// The table's 64 KB-aligned base travels in the upper half of the lane's column register, so the lookup address is still
+// one PRMT (ks into byte 1) + the immediate 4 t.
+// Limits: 12 <= M <= 32, topk <= 16, w_eff <= 64, nlist <= 1024 when the coarse pass is fused.  Everything else runs on
+// k_scan_stream32.
+// ===================================================================================================
+#pragma once
+#include "scan_stream.cuh"
+
+#define PS_NC 11
+#define PS_R 3
+#define PS_WMAX 64
+#define PS_CAPW 64
+#define PS_MAXK 16
+#define PS_NLIST_MAX 1024
+#define PS_T0 0x10000u
+#define PS_RING_BYTES (PS_R * ST_BLOCK_BYTES)
+#define PS_SMEM_BYTES (0x39000 - 0x400)
+#define PS_BAR_FULL 1
+#define PS_BAR_DONE 3
+
+struct PsSeg {  // per-parity query state: written by the producer, read by the consumers
+    long long off[PS_WMAX], prow[PS_WMAX];
+    int gcum[PS_WMAX], take[PS_WMAX];
+    int J, b, plain, pad;
+};
+struct PsKeys {  // per-parity top-k state of the consumers
+    u64 keys[PS_NC * PS_CAPW];
+    u64 cta_thr;
+    u64 thr_w[PS_NC + 1];
+    int cnt[PS_NC + 1];
+};
+// offsets from the start of the dynamic window (absolute 0x400)
+#define PS_OFF_SEG 0
+#define PS_OFF_KEYS (PS_OFF_SEG + 2 * (int)sizeof(PsSeg))
+#define PS_OFF_PLAN (PS_OFF_KEYS + 2 * (int)sizeof(PsKeys))          /* s_f, s_pre, s_loc: 3 x PS_WMAX ints */
+#define PS_OFF_HIST (PS_OFF_PLAN + 3 * PS_WMAX * 4)                   /* 256 + 4 ints */
+#define PS_OFF_POOL (PS_OFF_HIST + 260 * 4)                           /* PS_NLIST_MAX words */
+#define PS_OFF_SELK (((PS_OFF_POOL + PS_NLIST_MAX * 4) + 15) & ~15)   /* 256 keys, followed by the producer ring: 1024 keys for the full-sort fallback */
+#define PS_OFF_PRING (PS_OFF_SELK + 256 * 8)
+#define PS_OFF_RINGS_A (PS_OFF_PRING + PS_RING_BYTES)
+#define PS_RINGS_A 5
+#define PS_OFF_RINGS_B (0x30000 - 0x400)
+static_assert(PS_OFF_RINGS_A + PS_RINGS_A * PS_RING_BYTES <= 0x10000 - 0x400, "the low region overflows into the tables");
+static_assert(PS_OFF_RINGS_B + (PS_NC - PS_RINGS_A) * PS_RING_BYTES <= PS_SMEM_BYTES, "the high region overflows");
+static_assert(sizeof(PsSeg) % 16 == 0 && sizeof(PsKeys) % 8 == 0, "alignment");
+
+__device__ __forceinline__ void ps_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"((PS_NC + 1) * 32) : "memory"); }
+__device__ __forceinline__ void ps_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"((PS_NC + 1) * 32) : "memory"); }
+
+// the w smallest of np (distance bits, index) pairs by ONE warp: 256-bin histogram over [mn, mx], the bin holding the
+// w-th smallest, gather of everything up to that bin as (dist, index) keys, register sort.  Returns the number of keys in
+// `out` (>= w, <= 256) or -1 (more than 256 qualify: heavily tied distances).  (CTA-wide form: cta_select_smallest.)
+__device__ __forceinline__ int warp_select_smallest(const uint32_t *d, int np, int w, u64 *out, int *hist, uint32_t mn, uint32_t mx, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist[8 * lane + j] = 0;
+    __syncwarp();
+    const uint32_t range = mx - mn;
+    const int sh = range >= 256u ? (32 - __clz(range)) - 8 : 0;
+    for (int i = lane; i < np; i += 32) atomicAdd(&hist[(d[i] - mn) >> sh], 1);
+    __syncwarp();
+    int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; tot += c[j]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int excl = incl - tot;
+    const bool mine = excl < w && w <= incl;  // exactly one lane (w <= np)
+    int bin = 0;
+    if (mine) {
+        int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (run + c[j] >= w) { bin = 8 * lane + j; break; }
+            run += c[j];
+        }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, __ffs(__ballot_sync(0xffffffffu, mine)) - 1);
+    int n = 0;
+    for (int i0 = 0; i0 < np; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < np && (int)((d[i] - mn) >> sh) <= bin;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (n + __popc(bal) > 256) return -1;
+        if (ok) out[n + __popc(bal & ((1u << lane) - 1u))] = ((u64)d[i] << 32) | (u64)(uint32_t)i;
+        n += __popc(bal);
+    }
+    warp_sort_any(out, n, lane);
+    return n;
+}
+
+// grid (min(B, SMs)); 12 warps; dynamic shared memory PS_SMEM_BYTES (and no static shared memory: the window must start
+// at absolute shared address 0x400).  a.coarse_mode: 0 = coarse pass fused (a.centers = skew64 of the centers), 2 = the
+// ranking is read from a.plan.ranked.  nq = number of queries.
+__global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs a, int nq)
+{
+    constexpr int H = 1, ST_R = PS_R, ST_D = PS_R - 1;
+    constexpr uint32_t TB = 0;  // the table base is in colreg
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    if (smem_base != 0x400u) __trap();  // the layout above is in absolute shared addresses
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    PsSeg *segs = reinterpret_cast<PsSeg *>(smem_raw + PS_OFF_SEG);
+    PsKeys *keyb = reinterpret_cast<PsKeys *>(smem_raw + PS_OFF_KEYS);
+    const int Mr = a.M;
+    float keep[32], sel[32];  // the per-lane row-boundary constants of the accumulation (scan_stream.cuh)
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        keep[t] = lane == t ? 0.f : 1.f;
+        sel[t] = lane == t ? 1.f : 0.f;
+    }
+    const int n_my = blockIdx.x < nq ? (nq - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (wid < PS_NC) {
+        // =========================================== consumers ===========================================
+        const uint32_t ring = smem_base + (wid < PS_RINGS_A ? PS_OFF_RINGS_A + wid * PS_RING_BYTES : PS_OFF_RINGS_B + (wid - PS_RINGS_A) * PS_RING_BYTES) +
+                              lane * 16;
+        const uint8_t *pc = a.codes;
+#pragma unroll 1
+        for (int qi = 0; qi < n_my; ++qi) {
+            const int p = qi & 1;
+            ps_bar_sync(PS_BAR_FULL + p);
+            PsSeg &sg = segs[p];
+            PsKeys &kb = keyb[p];
+            const int J = sg.J, b = sg.b;
+            const int *s_gcum = sg.gcum, *s_take = sg.take;
+            const long long *s_off = sg.off, *s_prow = sg.prow;
+            u64 *cta_thr = &kb.cta_thr;
+            const float *lut2 = reinterpret_cast<const float *>(smem_raw + (PS_T0 - 0x400u) + p * SK_LUT_BYTES);
+            const uint32_t colreg = (PS_T0 + (uint32_t)p * SK_LUT_BYTES) | (uint32_t)((32 - lane) * 4);
+            WarpTopk wt;
+            wt.keys = kb.keys + wid * PS_CAPW;
+            wt.cap = PS_CAPW;
+            wt.k = a.k;
+            wt.count = 0;
+            wt.thr_w = kb.thr_w;
+            wt.nw = PS_NC;
+            wt.wid = wid;
+            // this warp's slice [f0, f_end) of the query's flattened 64-row groups
+            int f0 = 0, f_end = 0, cur_f = 0, nblk = 0, hb = 0, drain_left = 0;
+            uint32_t d_last0 = 0u;
+            int seg = 0, seg_g0 = 0, seg_gend = 0, seg_take = 0;
+            long long seg_prow = 0;
+            auto seg_of = [&](int f) -> int {
+                int lo = 0, hi = J - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_gcum[mid] > f) hi = mid; else lo = mid + 1;
+                }
+                return lo;
+            };
+            auto load_seg = [&](int j) {
+                seg = j;
+                seg_g0 = j ? s_gcum[j - 1] : 0;
+                seg_gend = s_gcum[j];
+                seg_take = s_take[j];
+                seg_prow = s_prow[j];
+            };
+            {
+                const int G = J ? s_gcum[J - 1] : 0;
+                const int per = (G + PS_NC - 1) / PS_NC;
+                f0 = wid * per;
+                if (f0 > G) f0 = G;
+                f_end = f0 + per < G ? f0 + per : G;
+                cur_f = f0;
+                if (f_end > f0) {
+                    const int sa_ = seg_of(f0), sb_ = seg_of(f_end - 1);
+                    nblk = (f_end - f0) + (sb_ - sa_ + 1);
+                    load_seg(sa_);
+                }
+            }
+            uint32_t dsc[ST_R];
+#pragma unroll
+            for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
+            ST_ISSUE(0, dsc[0], 0 < nblk)
+            ST_ISSUE(1, dsc[1], 1 < nblk)
+            uint32_t thr_hi = 0xffffffffu;
+            auto row_id = [&](int f, int half) -> uint32_t {
+                const int j = seg_of(f);
+                const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + half * 32 + lane;
+                return (uint32_t)__ldg(a.ids + s_off[j] + r);
+            };
+            auto emit2 = [&](float dx, float dy, uint32_t d) {
+                const int f = (int)(d >> 2);
+                thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
+                const bool px = (d & 1u) && __float_as_uint(dx) <= thr_hi;
+                const bool py = (d & 2u) && __float_as_uint(dy) <= thr_hi;
+                if (__any_sync(0xffffffffu, px || py)) {
+                    warp_push(wt, cta_thr, lane, dx, px ? row_id(f, 0) : 0u, px);
+                    warp_push(wt, cta_thr, lane, dy, py ? row_id(f, 1) : 0u, py);
+                }
+            };
+            if (sg.plain) {  // a table with huge / inf / NaN entries: exact per-candidate sums (scan_stream.cuh plain_slice)
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                for (int f = f0; f < f_end; ++f) {
+                    const int j = seg_of(f);
+                    const int g = f - (j ? s_gcum[j - 1] : 0);
+                    float dd[2] = {0.f, 0.f};
+                    uint32_t dsc_ = (uint32_t)f << 2;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int s = half * 32 + lane;
+                        if (g * 64 + s < s_take[j]) {
+                            dsc_ |= 1u << half;
+                            const uint8_t *pp = pc + (size_t)s_prow[j] * 32 + (size_t)g * ST_BLOCK_BYTES + half * 1024 + lane * 16;
+                            float d = 0.f;
+                            for (int m = 0; m < 32; ++m) {
+                                const int x = lane + m;
+                                const uint32_t ks = __ldg(pp + (x >> 5) * ST_BLOCK_BYTES + ((x >> 4) & 1) * 512 + (x & 15));
+                                const float v = lut2[ks * 64 + ((m + 32) & 63)];
+                                d = m ? __fadd_rn(d, v) : v;
+                            }
+                            dd[half] = d;
+                        }
+                    }
+                    emit2(dd[0], dd[1], dsc_);
+                }
+            } else {
+                unsigned long long acc2 = 0ull, out2 = 0ull;
+#pragma unroll 1
+                for (int m = 0; m < nblk; m += ST_R) {
+                    ST_STAGE(0)
+                    ST_STAGE(1)
+                    ST_STAGE(2)
+                }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            warp_compact(wt, cta_thr, lane);
+            if (lane == 0) kb.cnt[wid] = wt.count;
+            __threadfence_block();
+            ps_bar_arrive(PS_BAR_DONE + p);
+        }
+    } else {
+        // =========================================== producer ============================================
+        int *s_f = reinterpret_cast<int *>(smem_raw + PS_OFF_PLAN), *s_pre = s_f + PS_WMAX, *s_loc = s_pre + PS_WMAX;
+        int *hist = reinterpret_cast<int *>(smem_raw + PS_OFF_HIST);
+        uint32_t *pool_d = reinterpret_cast<uint32_t *>(smem_raw + PS_OFF_POOL);
+        u64 *selk = reinterpret_cast<u64 *>(smem_raw + PS_OFF_SELK);
+        const uint32_t ring = smem_base + PS_OFF_PRING + lane * 16;
+        const bool fused = a.coarse_mode == 0;
+
+        // final merge of the consumers' sorted lists of query qi (<= PS_NC * PS_MAXK keys) -> output
+        auto merge = [&](int qi) {
+            const int p = qi & 1, b = (int)blockIdx.x + qi * (int)gridDim.x;
+            const PsKeys &kb = keyb[p];
+            int o = 0;
+            for (int w2 = 0; w2 < PS_NC; ++w2) {
+                const int c = kb.cnt[w2];
+                for (int i = lane; i < c; i += 32) selk[o + i] = kb.keys[w2 * PS_CAPW + i];
+                o += c;
+            }
+            warp_sort_any(selk, o, lane);
+            const int n = o < a.k ? o : a.k;
+            for (int i = lane; i < n; i += 32) {
+                a.out.out_ids[(size_t)b * a.k + i] = a.out.id_base + (long long)key_id(selk[i]);
+                a.out.out_dists[(size_t)b * a.k + i] = key_dist(selk[i]);
+            }
+            if (lane == 0) a.out.out_counts[b] = n;
+            __syncwarp();
+        };
+#pragma unroll 1
+        for (int qi = 0; qi < n_my + 2; ++qi) {
+            if (qi >= 2) {  // the consumers' lists of query qi - 2 (same parity) are final: merge them, freeing the buffers
+                ps_bar_sync(PS_BAR_DONE + (qi & 1));
+                merge(qi - 2);
+            }
+            if (qi >= n_my) continue;
+            // ------------------------------------ prepare query qi ------------------------------------
+            const int p = qi & 1, b = (int)blockIdx.x + qi * (int)gridDim.x;
+            PsSeg &sg = segs[p];
+            PsKeys &kb = keyb[p];
+            float *lut2 = reinterpret_cast<float *>(smem_raw + (PS_T0 - 0x400u) + p * SK_LUT_BYTES);
+            // ---- K1 (src/rii.h:361-373): lane = sub-space, every ks; column c of the table holds sub-space c mod 32 ----
+            int bad = 0;
+            {
+                const int m = lane;
+                const float *qm = a.Q + (size_t)b * Mr * a.Ds + (size_t)m * a.Ds;
+                if (m >= Mr) {
+                    for (int ks = 0; ks < 256; ++ks) {
+                        lut2[ks * 64 + m + 32] = 0.f;
+                        lut2[ks * 64 + m] = 0.f;
+                    }
+                } else if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
+                    const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
+#pragma unroll 16
+                    for (int ks = 0; ks < 256; ++ks) {
+                        const float4 c4 = __ldg(cw4 + ks * Mr);
+                        const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + m + 32] = v;
+                        lut2[ks * 64 + m] = v;
+                    }
+                } else if (a.Ds <= 4) {
+                    float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
+#pragma unroll 16
+                    for (int ks = 0; ks < 256; ++ks) {
+                        float v = 0.f;
+                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds);
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + m + 32] = v;
+                        lut2[ks * 64 + m] = v;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int ks = 0; ks < 256; ++ks) {
+                        float v = 0.f;
+                        if (ks < a.Ks) v = l2sqr_lanes(qm, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds, a.variant);
+                        bad |= !(v <= ST_TABLE_LIMIT);
+                        lut2[ks * 64 + m + 32] = v;
+                        lut2[ks * 64 + m] = v;
+                    }
+                }
+            }
+            const bool plain = __any_sync(0xffffffffu, bad) != 0;  // (also orders the table writes before the lookups below)
+            __syncwarp();
+            int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
+            if (fused) {
+                // ---- K4 coarse pass (src/rii.h:259-265): this warp scans the skew64 centers with the new table ----
+                uint32_t d_lo = 0xffffffffu, d_hi = 0u;
+                const int Gc = (a.nlist + 63) >> 6;
+                if (plain) {
+                    for (int i = lane; i < a.nlist; i += 32) {
+                        const uint8_t *pp = a.centers + (size_t)(i >> 6) * ST_BLOCK_BYTES + ((i >> 5) & 1) * 1024 + (i & 31) * 16;
+                        float d = 0.f;
+                        for (int m = 0; m < 32; ++m) {
+                            const int x = (i & 31) + m;
+                            const uint32_t ks = __ldg(pp + (x >> 5) * ST_BLOCK_BYTES + ((x >> 4) & 1) * 512 + (x & 15));
+                            const float v = lut2[ks * 64 + ((m + 32) & 63)];
+                            d = m ? __fadd_rn(d, v) : v;
+                        }
+                        const uint32_t u = __float_as_uint(d);
+                        pool_d[i] = u;
+                        d_lo = u < d_lo ? u : d_lo;
+                        d_hi = u > d_hi ? u : d_hi;
+                    }
+                } else {
+                    const uint8_t *pc = a.centers;
+                    const uint32_t colreg = (PS_T0 + (uint32_t)p * SK_LUT_BYTES) | (uint32_t)((32 - lane) * 4);
+                    int cur_f = 0, hb = 0, drain_left = 0, seg = 0;
+                    const int f_end = Gc, seg_g0 = 0, seg_gend = Gc, seg_take = a.nlist, nblk = Gc + 1;
+                    const long long seg_prow = 0;
+                    uint32_t d_last0 = 0u;
+                    auto load_seg = [&](int) {};
+                    uint32_t dsc[ST_R];
+#pragma unroll
+                    for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
+                    auto emit2 = [&](float dx, float dy, uint32_t d) {
+                        const int f = (int)(d >> 2);
+                        const uint32_t ux = __float_as_uint(dx), uy = __float_as_uint(dy);
+                        if (d & 1u) { pool_d[f * 64 + lane] = ux; d_lo = ux < d_lo ? ux : d_lo; d_hi = ux > d_hi ? ux : d_hi; }
+                        if (d & 2u) { pool_d[f * 64 + 32 + lane] = uy; d_lo = uy < d_lo ? uy : d_lo; d_hi = uy > d_hi ? uy : d_hi; }
+                    };
+                    ST_ISSUE(0, dsc[0], 0 < nblk)
+                    ST_ISSUE(1, dsc[1], 1 < nblk)
+                    unsigned long long acc2 = 0ull, out2 = 0ull;
+#pragma unroll 1
+                    for (int m = 0; m < nblk; m += ST_R) {
+                        ST_STAGE(0)
+                        ST_STAGE(1)
+                        ST_STAGE(2)
+                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    (void)seg; (void)hb; (void)d_last0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint32_t x = __shfl_xor_sync(0xffffffffu, d_lo, o), y = __shfl_xor_sync(0xffffffffu, d_hi, o);
+                    d_lo = x < d_lo ? x : d_lo;
+                    d_hi = y > d_hi ? y : d_hi;
+                }
+                __syncwarp();
+                // ---- selection of the w nearest lists under (distance, list id): src/rii.h:279-280 ----
+                int np = warp_select_smallest(pool_d, a.nlist, a.w_eff, selk, hist, d_lo, d_hi, lane);
+                if (np < 0) {  // > 256 exact ties at the w-th distance: sort every (dist, index) key (selk + the idle ring: 1024 keys)
+                    const int P = next_pow2(a.nlist);
+                    for (int i = lane; i < P; i += 32) selk[i] = i < a.nlist ? (((u64)pool_d[i] << 32) | (u64)(uint32_t)i) : RII_KEY_MAX;
+                    warp_sort_smem(selk, P, lane);
+                }
+                __syncwarp();
+                for (int j = lane; j < a.w_eff; j += 32) ranked_g[j] = (int)key_id(selk[j]);
+                __syncwarp();
+            }
+            // ---- the plan from the ranking (own, or given) ----
+            for (int j = lane; j < a.w_eff; j += 32) {
+                const int no = fused ? (int)key_id(selk[j]) : ranked_g[j];
+                s_f[j] = a.plan.glob_len[no];
+                s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
+                s_loc[j] = a.plan.loc_len[no];
+                sg.off[j] = a.offsets[no];
+                sg.prow[j] = a.skew_off[no];
+            }
+            __syncwarp();
+            const int jc = plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, sg.off, sg.prow, sg.gcum, sg.take);
+            if (lane == 0) {
+                sg.J = jc;
+                sg.b = b;
+                sg.plain = plain ? 1 : 0;
+                kb.cta_thr = RII_KEY_MAX;
+            }
+            if (lane < PS_NC) kb.thr_w[lane] = RII_KEY_MAX;
+            __syncwarp();
+            __threadfence_block();
+            ps_bar_arrive(PS_BAR_FULL + p);
+        }
+    }
+}

@@ -920,3 +920,78 @@ def test_state_exchange_formats(tmp_path):
             "q = np.load(%r); print(e.query_ivf(q, 3, np.array([], np.int64), 700)[0])" % (so_dir, f, str(tmp_path / "q.npy")))
     out = subprocess.check_output([sys.executable, "-c", code], stderr=subprocess.STDOUT).decode()
     assert str(e.query_ivf(Q[0], 3, EMPTY, 700)[0]) in out, out
+
+
+@pytest.mark.parametrize("M,nlist", [(32, 1500), (64, 1100)])
+def test_split_coarse_phase_with_many_lists(M, nlist):
+    """nlist > 1024: the coarse pass ranks the centers in the warps' top-k lists.  Coarse-only launch
+    (rii_coarse_rank_dev) + scan with the given ranking (rii_query_ranked_dev) over G = 2 id-range shards == oracle."""
+    import torch
+    from rii_b200 import sharded
+    D, Ks, N = 4 * M, 256, 120000
+    cw, codes, Q = synth(D, M, Ks, N, 8, seed=77 + M)
+    grp = sharded.LocalShardGroup([engine(cw) for _ in range(2)])
+    centers = grp.build(codes, nlist, 1)
+    oc, oa = O.reconfigure(cw, codes, nlist, 1)
+    assert np.array_equal(centers, oc)
+    offsets, ids = O.assign_to_lists(oa, nlist)
+    Qd = torch.from_numpy(Q).to("cuda:0")
+    for topk, L in [(1, 2560), (10, 800), (3, 80)]:
+        for tag, (gi, gd, gc) in (("split", grp.query_split(Qd, topk, L)), ("fused", grp.query(Qd, topk, L, "ivf"))):
+            torch.cuda.synchronize()
+            gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+            for bq, q in enumerate(Q):
+                exp = O.query_ivf(O.dtable(q, cw, 16), codes, oc, offsets, ids, topk, L)
+                n = int(gc[bq])
+                assert_same_result(gi[bq, :n], gd[bq, :n], exp[0], exp[1], "%s M=%d nlist=%d k=%d L=%d" % (tag, M, nlist, topk, L))
+
+
+@pytest.mark.parametrize("M,D", [(32, 128), (32, 96), (20, 40)])
+def test_persistent_batch_kernel(M, D):
+    """k_scan_persist32 (one resident CTA per SM, 11 scanning warps + 1 producer warp, double-buffered tables) must return
+    exactly what the per-query kernel and the oracle return: fused coarse pass and given rankings (shards), every batch size
+    around the grid size, topk up to 16, empty / flagged plans, huge tables (exact per-candidate path)."""
+    import torch
+    from rii_b200 import sharded
+    Ks, N, nlist = 256, 70000, 120
+    cw, codes, Q = synth(D, M, Ks, N, 24, seed=31 + D)
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    for B in (1, 2, 3, 147, 149, 300, 613):
+        Qb = np.ascontiguousarray(np.tile(Q, (B // len(Q) + 1, 1))[:B] + np.float32(0.001) * np.arange(B, dtype=np.float32)[:, None])
+        for topk, L in [(1, 5000), (16, 700), (5, 40), (3, N)]:
+            e.set_option("persist", 2)
+            f = e.query_batch(Qb, topk, L=L, method="ivf")
+            e.set_option("persist", 0)
+            u = e.query_batch(Qb, topk, L=L, method="ivf")
+            assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1])), (B, topk, L)
+            for b in range(0, B, max(1, B // 5)):
+                exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
+                n = int(f[2][b])
+                assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "persist B=%d k=%d L=%d b=%d" % (B, topk, L, b))
+    # huge tables: queries ~1e19 away take the exact per-candidate path inside the same kernel
+    Qh = np.ascontiguousarray(np.tile(Q, (13, 1))[:300])
+    Qh[::7] *= np.float32(3e18)
+    e.set_option("persist", 2)
+    f = e.query_batch(Qh, 4, L=3000, method="ivf")
+    e.set_option("persist", 0)
+    u = e.query_batch(Qh, 4, L=3000, method="ivf")
+    assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1]))
+    # given rankings over two id-range shards (the plan uses glob_len / pre_len)
+    if M == 32:
+        grp = sharded.LocalShardGroup([engine(cw) for _ in range(2)])
+        oc = grp.build(codes, nlist, 1)
+        assert np.array_equal(oc, centers)
+        Qd = torch.from_numpy(np.ascontiguousarray(np.tile(Q, (13, 1))[:300])).to("cuda:0")
+        for eng in grp.engines:
+            eng.e.set_option("persist", 2)
+        for topk, L in [(1, 5000), (7, 333)]:
+            gi, gd, gc = grp.query_split(Qd, topk, L)
+            torch.cuda.synchronize()
+            gi, gd, gc = gi.cpu().numpy(), gd.cpu().numpy(), gc.cpu().numpy()
+            for b in range(0, 300, 37):
+                exp = O.query_ivf(O.dtable(Qd[b].cpu().numpy(), cw, 16), codes, centers, offsets, ids, topk, L)
+                n = int(gc[b])
+                assert_same_result(gi[b, :n], gd[b, :n], exp[0], exp[1], "persist shards k=%d L=%d b=%d" % (topk, L, b))
