@@ -117,7 +117,7 @@ struct rii_index {
     cudaStream_t stream = nullptr;
 
     float *d_cw = nullptr;
-    float *d_cw_t = nullptr;  // (Ks, M, Ds) copy of the codewords: sub-space fastest (coalesced in-kernel table build)
+    float *d_cw_t = nullptr;  // (256, M, Dp) copy of the codewords, sub-space fastest, Dp = 4 for Ds <= 4 (coalesced in-kernel table build)
     float *d_Dm = nullptr;
     uint8_t *d_codes = nullptr;
     DevBuf centers, offsets, ids, loc_len, glob_len, pre_len;
@@ -938,8 +938,9 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
         if (fuse || mode == 1 || mode == 0) CKR(ensure_centers_skew(h, st));
         // batches of independent queries: the persistent warp-specialised kernel (scan_persist.cuh) when the shape fits
         const bool pers_shape = persist_fits(h->rb, topk, w_eff, nlist, mode == 0) && (mode == 2 || (mode == 0 && h->opt_fuse_coarse));
-        if (mode != 1 && pers_shape && (h->opt_persist == 2 || (h->opt_persist == 1 && B >= 2 * 148)) && !h->opt_debug_clocks) {
+        if (mode != 1 && pers_shape && (h->opt_persist == 2 || (h->opt_persist == 1 && B >= 2 * 148))) {
             SkewArgs sp_ = sa;
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)std::max(B, 148) * 128)); CK(cudaMemsetAsync(h->dbg.p, 0, (size_t)148 * 128, st)); sp_.dbg = h->dbg.as<long long>(); }
             sp_.centers = mode == 0 ? h->centers_skew.as<uint8_t>() : nullptr;
             sp_.coarse_mode = mode == 0 ? 0 : 2;
             sp_.cap = PS_CAPW_HOST;
@@ -1184,13 +1185,14 @@ int rii_create(const float *codewords, int M, int Ks, int Ds, int verbose, int d
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cw, (size_t)M * Ks * Ds * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cw, codewords, (size_t)M * Ks * Ds * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_cw_t, (size_t)M * Ks * Ds * sizeof(float));
-    if (e == cudaSuccess) {
-        std::vector<float> t((size_t)M * Ks * Ds);
+    {   // sub-space-fastest copy for the in-kernel table build: (256, M, Dp), Dp = 4 for Ds <= 4 (zero padded: 16-byte loads), rows >= Ks zero
+        const int Dp = Ds <= 4 ? 4 : Ds;
+        std::vector<float> t((size_t)256 * M * Dp, 0.f);
         for (int m = 0; m < M; ++m)
             for (int ks = 0; ks < Ks; ++ks)
-                for (int i = 0; i < Ds; ++i) t[((size_t)ks * M + m) * Ds + i] = codewords[((size_t)m * Ks + ks) * Ds + i];
-        e = cudaMemcpy(h->d_cw_t, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+                for (int i = 0; i < Ds; ++i) t[((size_t)ks * M + m) * Dp + i] = codewords[((size_t)m * Ks + ks) * Ds + i];
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_cw_t, t.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_cw_t, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
         delete h;

@@ -136,6 +136,8 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         keep[t] = lane == t ? 0.f : 1.f;
         sel[t] = lane == t ? 1.f : 0.f;
     }
+    long long *dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;  // optional cycle counters per CTA
+    long long c_wait = 0, c_scan = 0;
     const int n_my = blockIdx.x < nq ? (nq - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (wid < PS_NC) {
@@ -146,7 +148,10 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
 #pragma unroll 1
         for (int qi = 0; qi < n_my; ++qi) {
             const int p = qi & 1;
+            long long t0_ = 0;
+            if (dbg) t0_ = clock64();
             ps_bar_sync(PS_BAR_FULL + p);
+            if (dbg) { const long long t1_ = clock64(); c_wait += t1_ - t0_; t0_ = t1_; }
             PsSeg &sg = segs[p];
             PsKeys &kb = keyb[p];
             const int J = sg.J, b = sg.b;
@@ -163,6 +168,11 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             wt.thr_w = kb.thr_w;
             wt.nw = PS_NC;
             wt.wid = wid;
+            wt.ids = a.ids;  // lazy ids: pushes carry positions, warp_compact looks the ids up
+            wt.s_off = s_off;
+            wt.s_gcum = s_gcum;
+            wt.J = J;
+            wt.nres = 0;
             // this warp's slice [f0, f_end) of the query's flattened 64-row groups
             int f0 = 0, f_end = 0, cur_f = 0, nblk = 0, hb = 0, drain_left = 0;
             uint32_t d_last0 = 0u;
@@ -202,11 +212,7 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             ST_ISSUE(0, dsc[0], 0 < nblk)
             ST_ISSUE(1, dsc[1], 1 < nblk)
             uint32_t thr_hi = 0xffffffffu;
-            auto row_id = [&](int f, int half) -> uint32_t {
-                const int j = seg_of(f);
-                const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + half * 32 + lane;
-                return (uint32_t)__ldg(a.ids + s_off[j] + r);
-            };
+            auto row_id = [&](int f, int half) -> uint32_t { return (uint32_t)(f * 64 + half * 32 + lane); };
             auto emit2 = [&](float dx, float dy, uint32_t d) {
                 const int f = (int)(d >> 2);
                 thr_hi = reinterpret_cast<volatile uint32_t *>(cta_thr)[1];
@@ -256,7 +262,9 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             if (lane == 0) kb.cnt[wid] = wt.count;
             __threadfence_block();
             ps_bar_arrive(PS_BAR_DONE + p);
+            if (dbg) c_scan += clock64() - t0_;
         }
+        if (dbg && lane == 0 && (wid == 0 || wid == PS_NC - 1)) { dbg[wid == 0 ? 0 : 2] = c_wait; dbg[wid == 0 ? 1 : 3] = c_scan; }
     } else {
         // =========================================== producer ============================================
         int *s_f = reinterpret_cast<int *>(smem_raw + PS_OFF_PLAN), *s_pre = s_f + PS_WMAX, *s_loc = s_pre + PS_WMAX;
@@ -265,6 +273,7 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         u64 *selk = reinterpret_cast<u64 *>(smem_raw + PS_OFF_SELK);
         const uint32_t ring = smem_base + PS_OFF_PRING + lane * 16;
         const bool fused = a.coarse_mode == 0;
+        long long p_wait = 0, p_merge = 0, p_table = 0, p_coarse = 0, p_select = 0, p_plan = 0;
 
         // final merge of the consumers' sorted lists of query qi (<= PS_NC * PS_MAXK keys) -> output
         auto merge = [&](int qi) {
@@ -287,9 +296,13 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         };
 #pragma unroll 1
         for (int qi = 0; qi < n_my + 2; ++qi) {
+            long long tp_ = 0;
+            if (dbg) tp_ = clock64();
             if (qi >= 2) {  // the consumers' lists of query qi - 2 (same parity) are final: merge them, freeing the buffers
                 ps_bar_sync(PS_BAR_DONE + (qi & 1));
+                if (dbg) { const long long t_ = clock64(); p_wait += t_ - tp_; tp_ = t_; }
                 merge(qi - 2);
+                if (dbg) { const long long t_ = clock64(); p_merge += t_ - tp_; tp_ = t_; }
             }
             if (qi >= n_my) continue;
             // ------------------------------------ prepare query qi ------------------------------------
@@ -307,24 +320,18 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
                         lut2[ks * 64 + m + 32] = 0.f;
                         lut2[ks * 64 + m] = 0.f;
                     }
-                } else if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {
-                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
+                } else if (a.Ds <= 4) {  // the codeword copy is padded to 4 floats per sub-vector (zeros add +0: same sum)
+                    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    q4.x = __ldg(qm);
+                    if (a.Ds > 1) q4.y = __ldg(qm + 1);
+                    if (a.Ds > 2) q4.z = __ldg(qm + 2);
+                    if (a.Ds > 3) q4.w = __ldg(qm + 3);
                     const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
                     for (int ks = 0; ks < 256; ++ks) {
                         const float4 c4 = __ldg(cw4 + ks * Mr);
-                        const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
-                        bad |= !(v <= ST_TABLE_LIMIT);
-                        lut2[ks * 64 + m + 32] = v;
-                        lut2[ks * 64 + m] = v;
-                    }
-                } else if (a.Ds <= 4) {
-                    float qv[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
-#pragma unroll 16
-                    for (int ks = 0; ks < 256; ++ks) {
-                        float v = 0.f;
-                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds);
+                        float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                        v = ks < a.Ks ? v : 0.f;
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + m + 32] = v;
                         lut2[ks * 64 + m] = v;
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             }
             const bool plain = __any_sync(0xffffffffu, bad) != 0;  // (also orders the table writes before the lookups below)
             __syncwarp();
+            if (dbg) { const long long t_ = clock64(); p_table += t_ - tp_; tp_ = t_; }
             int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
             if (fused) {
                 // ---- K4 coarse pass (src/rii.h:259-265): this warp scans the skew64 centers with the new table ----
@@ -398,6 +406,7 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
                     d_hi = y > d_hi ? y : d_hi;
                 }
                 __syncwarp();
+                if (dbg) { const long long t_ = clock64(); p_coarse += t_ - tp_; tp_ = t_; }
                 // ---- selection of the w nearest lists under (distance, list id): src/rii.h:279-280 ----
                 int np = warp_select_smallest(pool_d, a.nlist, a.w_eff, selk, hist, d_lo, d_hi, lane);
                 if (np < 0) {  // > 256 exact ties at the w-th distance: sort every (dist, index) key (selk + the idle ring: 1024 keys)
@@ -408,6 +417,7 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
                 __syncwarp();
                 for (int j = lane; j < a.w_eff; j += 32) ranked_g[j] = (int)key_id(selk[j]);
                 __syncwarp();
+                if (dbg) { const long long t_ = clock64(); p_select += t_ - tp_; tp_ = t_; }
             }
             // ---- the plan from the ranking (own, or given) ----
             for (int j = lane; j < a.w_eff; j += 32) {
@@ -430,6 +440,8 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             __syncwarp();
             __threadfence_block();
             ps_bar_arrive(PS_BAR_FULL + p);
+            if (dbg) p_plan += clock64() - tp_;
         }
+        if (dbg && lane == 0) { dbg[4] = p_wait; dbg[5] = p_merge; dbg[6] = p_table; dbg[7] = p_coarse; dbg[8] = p_select; dbg[9] = p_plan; dbg[10] = n_my; }
     }
 }

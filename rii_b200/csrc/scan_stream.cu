@@ -14,6 +14,10 @@
 int stream_pick(int row_bytes, bool ivf, bool two_ctas, int capw, int w_eff, size_t pool_bytes, int *nw, size_t *smem)
 {
     if (row_bytes == 64) {
+        {   // small top-k / few lists: 10 warps with the tables low in shared memory
+            const size_t b = stream_smem_bytes(ivf, 10, 4, ST_TB4, capw, w_eff, pool_bytes, 2);
+            if (b && b <= SK_DYN_SMEM) { *nw = 10; *smem = b; return 4; }
+        }
         const size_t b = stream_smem_bytes(ivf, 8, 4, ST_TB3, capw, w_eff, pool_bytes, 2);
         if (b && b <= SK_DYN_SMEM) { *nw = 8; *smem = b; return 3; }
         return 0;
@@ -48,6 +52,8 @@ static int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream
 
 int launch_stream(int shape, bool ivf, const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
 {
+    if (shape == 4) return ivf ? launch_stream_t<10, true, 4, 1, ST_TB4, 2>(a, parts, B, smem, st)
+                               : launch_stream_t<10, false, 4, 1, ST_TB4, 2>(a, parts, B, smem, st);
     if (shape == 3) return ivf ? launch_stream_t<8, true, 4, 1, ST_TB3, 2>(a, parts, B, smem, st)
                                : launch_stream_t<8, false, 4, 1, ST_TB3, 2>(a, parts, B, smem, st);
     if (shape == 2) return launch_stream_t<6, true, 3, 2, ST_TB2, 1>(a, parts, B, smem, st);

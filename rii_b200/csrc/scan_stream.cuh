@@ -35,10 +35,11 @@
 //   one CTA per SM:  NW = 12, R = 4, TB = 0x10000 -- long scans (linear), large topk / many lists
 //   two CTAs per SM: NW = 6,  R = 3, TB = 0x3000  -- per-query IVF batches: the serial phases of one query (table build,
 //                    coarse selection, plan, final merge) overlap the scan of the other CTA's query
-//   M = 64:          NW = 8,  R = 4, TB = 0x6000, two tables (128 KB), one CTA per SM
+//   M = 64:          NW = 8,  R = 4, TB = 0x6000, two tables (128 KB), one CTA per SM; NW = 10, TB = 0x2400 when the keys fit
 #define ST_TB1 0x10000u
 #define ST_TB2 0x3000u
 #define ST_TB3 0x6000u
+#define ST_TB4 0x2400u      // rows of 64 bytes, 10 warps: 8 KB of keys / segments below the tables
 #define ST_TABLE_LIMIT 5e36f        // 64 table entries below this cannot overflow fp32 (acc * 0 needs finite acc)
 
 #include "skew64.cuh"
@@ -330,6 +331,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     wt.thr_w = thr_w;
     wt.nw = NW;
     wt.wid = wid;
+    wt.ids = nullptr;  // set for the posting-list pass below
+    wt.s_off = s_off;
+    wt.s_gcum = s_gcum;
+    wt.J = 0;
+    wt.nres = 0;
+    if constexpr (IVF) {
+        if (!fused) {  // scan-only launch (the ranking was given): the one pass walks posting lists
+            wt.ids = a.ids;
+            wt.J = J;
+        }
+    }
 
     auto seg_of = [&](int f) -> int {  // segment holding flattened group f
         int lo = 0, hi = J - 1;
@@ -414,26 +426,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                         lut2[ks * 64 + ((m + 32) & 63)] = 0.f;
                         lutB[ks * 64 + m] = 0.f;
                     }
-                } else if (a.Ds == 4 && a.Ks == 256 && (reinterpret_cast<size_t>(a.Q) & 15) == 0) {  // 16 independent 16-byte loads in flight per lane
-                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm));
+                } else if (a.Ds <= 4) {  // every BASELINE shape: the codeword copy is padded to 4 floats (zeros add +0: same sum), 16
+                                         // independent 16-byte loads in flight per lane
+                    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    q4.x = __ldg(qm);
+                    if (a.Ds > 1) q4.y = __ldg(qm + 1);
+                    if (a.Ds > 2) q4.z = __ldg(qm + 2);
+                    if (a.Ds > 3) q4.w = __ldg(qm + 3);
                     const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
                     for (int i = wid; i < 256; i += NW) {
                         const int ks = (i + rot) & 255;
                         const float4 c4 = __ldg(cw4 + ks * Mr);
-                        const float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
-                        bad |= !(v <= ST_TABLE_LIMIT);
-                        lut2[ks * 64 + ((m + 32) & 63)] = v;
-                        lutB[ks * 64 + m] = v;
-                    }
-                } else if (a.Ds <= 4) {
-                    float qv[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int i = 0; i < a.Ds; ++i) qv[i] = __ldg(qm + i);
-#pragma unroll 8
-                    for (int i = wid; i < 256; i += NW) {
-                        const int ks = (i + rot) & 255;
-                        float v = 0.f;
-                        if (ks < a.Ks) v = l2sqr_small(qv, a.cw_t + ((size_t)ks * Mr + m) * a.Ds, a.Ds);
+                        float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                        v = ks < a.Ks ? v : 0.f;
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + ((m + 32) & 63)] = v;
                         lutB[ks * 64 + m] = v;
@@ -463,17 +469,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     }
     uint32_t thr_hi = 0xffffffffu;
     uint32_t d_lo = 0xffffffffu, d_hi = 0u;  // coarse pass: range of the distances this lane emitted
-    // id of the row `half` (0: x, 1: y) of flattened group f in this lane
-    auto row_id = [&](int f, int half) -> uint32_t {
-        if constexpr (IVF) {
-            if (pass0) return (uint32_t)(f * 64 + half * 32 + lane);  // coarse pass: the center's index
-            const int j = seg_of(f);
-            const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + half * 32 + lane;
-            return (uint32_t)__ldg(a.ids + s_off[j] + r);
-        } else {
-            return (uint32_t)(f * 64 + half * 32 + lane);
-        }
-    };
+    // position of the row `half` (0: x, 1: y) of flattened group f in this lane: the center's index (coarse pass), the id
+    // (linear scan), or what warp_compact turns into an id (posting lists: WarpTopk lazy ids)
+    auto row_id = [&](int f, int half) -> uint32_t { return (uint32_t)(f * 64 + half * 32 + lane); };
     auto emit2 = [&](float dx, float dy, uint32_t d) {
         const int f = (int)(d >> 2);
         if (IVF && direct) {  // coarse pass of the fused kernel: keep every distance (and their range, for the selection)
@@ -599,6 +597,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             wt.k = a.k;
             wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
             wt.count = 0;
+            wt.nres = 0;
+            wt.ids = a.ids;
+            wt.J = J;
             thr_hi = 0xffffffffu;
             set_range(1, 0);  // (also resets the walk state: hb, drain_left, d_last0)
 #pragma unroll

@@ -14,6 +14,15 @@ struct WarpTopk {
     int count;   // warp-uniform
     u64 *thr_w;  // shared [nw]: every warp's ceil(k/nw)-th smallest key (RII_KEY_MAX until it has that many)
     int nw, wid;
+    // Lazy ids (posting-list scans).  A push carries the candidate's POSITION in the pass (flattened 64-row group << 6 | row
+    // of the group); the id is looked up when the list is compacted -- all new entries at once, one memory latency per
+    // compaction instead of one per push on the scanning warp's critical path (ncu: stall_long_sb at every warp_push call
+    // site, profiles/r02_ncu_c5shape_*).  ids == nullptr: positions are ids already (linear scans, center ranking).
+    const int *ids;
+    const long long *s_off;  // CSR offset of every planned segment
+    const int *s_gcum;       // inclusive prefix of the segments' 64-row groups
+    int J;                   // planned segments
+    int nres;                // entries [0, nres) carry ids (kept by the last compaction)
 };
 
 // Bitonic sort of 32*R keys held in registers (element e = r*32 + lane), ascending.  Exchanges at distance >= 32
@@ -78,8 +87,24 @@ static __device__ __noinline__ void warp_sort_any(u64 *keys, int n, int lane)  /
 static __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
 {
     const int n = w.count;  // <= cap <= 256
+    if (w.ids) {  // positions -> ids for everything pushed since the last compaction
+        for (int e = w.nres + lane; e < n; e += 32) {
+            const u64 key = w.keys[e];
+            const uint32_t pos = key_id(key);
+            const int f = (int)(pos >> 6);
+            int lo = 0, hi = w.J - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (w.s_gcum[mid] > f) hi = mid; else lo = mid + 1;
+            }
+            const int r = (f - (lo ? w.s_gcum[lo - 1] : 0)) * 64 + (int)(pos & 63u);
+            w.keys[e] = (key & 0xffffffff00000000ull) | (u64)(uint32_t)__ldg(w.ids + w.s_off[lo] + r);
+        }
+        __syncwarp();
+    }
     warp_sort_any(w.keys, n, lane);
     w.count = n < w.k ? n : w.k;
+    w.nres = w.count;
     // Two valid upper bounds of the CTA's k-th key tighten the shared threshold:
     //  (1) this warp's own k-th key;
     //  (2) the LARGEST, over all warps, of the warps' ceil(k/nw)-th keys: at least nw * ceil(k/nw) >= k keys lie below
@@ -106,7 +131,8 @@ static __device__ __noinline__ void warp_push(WarpTopk &w, u64 *cta_thr, int lan
 {
     const u64 thr = *reinterpret_cast<volatile u64 *>(cta_thr);
     const u64 key = pack_key(dist, id);
-    const bool pass = pre && key < thr;
+    // (with lazy ids the candidate's id is not known yet: everything up to and including the threshold's distance passes)
+    const bool pass = pre && (w.ids ? (uint32_t)(key >> 32) <= (uint32_t)(thr >> 32) : key < thr);
     const unsigned bal = __ballot_sync(0xffffffffu, pass);
     if (!bal) return;
     if (pass) w.keys[w.count + __popc(bal & ((1u << lane) - 1u))] = key;

@@ -29,6 +29,7 @@ def run():
     ap.add_argument("--topk", type=int, default=1)
     ap.add_argument("--split", type=int, default=1)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--persist", type=int, default=1)
     ap.add_argument("--shards", type=int, default=1, help="pretend this GPU holds 1/shards of every list (global lengths = shards x local)")
     a = ap.parse_args()
     lib = _capi.lib()
@@ -52,6 +53,7 @@ def run():
     B, k = a.batch, a.topk
     Q = torch.rand((B, a.d), device=dev)
     e.set_option("stream_ctas", a.ctas)
+    e.set_option("persist", a.persist)
     e.set_option("debug_clocks", 1)
     lib.rii_profile_enable(e._h, 1)
     w = _capi.check(lib.rii_coarse_width(e._h, L))
@@ -72,13 +74,22 @@ def run():
         else:
             _capi.check(lib.rii_query_batch_dev(e._h, p(Q), B, k, None, 0, L, 1, p(oi), p(od), p(oc), sp))
     torch.cuda.synchronize()
-    clk = np.zeros((B, 8), np.int64)
-    _capi.check(lib.rii_debug_clocks(e._h, B, clk.ctypes.data_as(C.POINTER(C.c_int64))))
+    clk = np.zeros((max(B, 296), 8), np.int64)
+    _capi.check(lib.rii_debug_clocks(e._h, max(B, 296), clk.ctypes.data_as(C.POINTER(C.c_int64))))
     out = {"shape": vars(a), "L": L, "w": w}
     for name in ("coarse_rank", "scan_ivf"):
         m_, n_ = C.c_double(0), C.c_int64(0)
         lib.rii_profile_get(e._h, name.encode(), C.byref(m_), C.byref(n_))
         out[name + "_ms"] = round(m_.value / max(n_.value, 1), 4)
+    if a.persist and B >= 296:  # persistent kernel: 16 counters per CTA (2 per 8-word row)
+        c = clk.reshape(-1, 16)[:148]
+        names = ["cons0_wait_full", "cons0_scan", "cons10_wait_full", "cons10_scan", "prod_wait_done", "prod_merge", "prod_table", "prod_coarse",
+                 "prod_select", "prod_plan", "queries_per_cta"]
+        nq = np.maximum(c[:, 10], 1)
+        out["persist_cycles_per_query"] = {n: float((c[:, i] / nq).mean()) for i, n in enumerate(names[:10])}
+        out["scan_GBps"] = round(B * (L / G * a.m + 4 * a.m * 256) / (out["scan_ivf_ms"] * 1e-3) / 1e9, 1)
+        print(json.dumps(out))
+        return
     t0 = clk[:, 0]
     out["cta_cycles_mean"] = {"table_built": float((clk[:, 4] - t0).mean()), "ready_to_scan": float((clk[:, 1] - t0).mean()),
                               "scan": float((clk[:, 2] - clk[:, 1]).mean()), "tail": float((clk[:, 3] - clk[:, 2]).mean()),
