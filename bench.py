@@ -267,12 +267,12 @@ def large_sharded_leg(torch, dist, lib, main, _capi, rank, world, dev, st, sp, p
     out["ms_per_batch"] = round(float(t.item()) / steps, 4)
     out["queries_per_s"] = round(steps * B / (float(t.item()) * 1e-3), 1)
     # ---- parity at full scale (rank 0): the shard's part of the answer against a numpy / oracle restatement --------------
+    step(0)  # (collectives inside: every rank runs it; only rank 0 checks its shard's part below)
+    torch.cuda.synchronize()
     if rank == 0:
         try:
             from oracle import oracle as O
             q = Q[:B]
-            step(0)
-            torch.cuda.synchronize()
             got_ids, got_d, got_c = po.ids.cpu().numpy(), po.d.cpu().numpy(), po.c.cpu().numpy()
             rk = ranked.cpu().numpy()
             ok, why = True, []
@@ -353,7 +353,8 @@ def run_ours(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))  # a lost rank must not hang the box
     lib = _capi.lib()
     B, K, W = args.batch, args.steps, args.warmup
     nq = B * min(4, K + W)  # a few distinct query batches, cycled
