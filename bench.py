@@ -734,6 +734,8 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # before torch / NCCL load: rank 0 prints exactly one line, the JSON
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
