@@ -110,6 +110,11 @@ int rii_sym_matrices(rii_index_t *h, float *out);
  * out_codes uint8 (n, M); nearest codeword per sub-space, fp32 sequential sum, first minimum wins. */
 int rii_encode(rii_index_t *h, const float *vecs, int64_t n, uint8_t *out_codes);
 
+/* OPQ: rotate every query on the device before the distance table is built (rii/rii.py:305-306 does fine_quantizer.rotate
+ * on the host).  R: float32 (D, D) row-major, q' = q @ R; NULL switches it off.  fp32 FMA chain: agrees with a numpy
+ * rotation to rounding (~1e-7 relative), not bit for bit. */
+int rii_set_rotation(rii_index_t *h, const float *R);
+
 /* ---- id-range sharding (one index object per GPU) -------------------------- */
 /* This shard holds global ids [id_base, id_base + N_local) of an index of N_total codes. */
 int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total);

@@ -41,6 +41,7 @@ SYMBOLS = {
     "rii_assign": (C.c_int, [_vp, _u8p, C.c_int64, _u8p, C.c_int, _i32p, _f32p]),
     "rii_sym_matrices": (C.c_int, [_vp, _f32p]),
     "rii_encode": (C.c_int, [_vp, _f32p, C.c_int64, _u8p]),
+    "rii_set_rotation": (C.c_int, [_vp, _f32p]),
     "rii_set_shard": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "rii_set_coarse_centers": (C.c_int, [_vp, _u8p, C.c_int]),
     "rii_fit_coarse": (C.c_int, [_vp, _u8p, C.c_int64, C.c_int, C.c_int, _u8p]),

@@ -580,6 +580,19 @@ __global__ void __launch_bounds__(RII_THREADS) k_ivf_keys(IvfArgs a, u64 *__rest
     }
 }
 
+// OPQ rotation of the queries (rii/rii.py:305-306: fine_quantizer.rotate(q) = q @ R): out[b][j] = sum_i Q[b][i] R[i][j],
+// fp32 FMA chain in i order.  (A D x D contraction per query; tensor cores are deliberately not used: bf16 / tf32 inputs
+// would move the rotated coordinates by ~1e-3 relative, far beyond the 1e-5 contract on the distances.)  grid (ceil(D/128), B)
+__global__ void k_rotate(const float *__restrict__ Q, const float *__restrict__ R, int D, float *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= D) return;
+    const float *q = Q + (size_t)b * D;
+    float acc = 0.f;
+    for (int i = 0; i < D; ++i) acc = fmaf(__ldg(q + i), __ldg(R + (size_t)i * D + j), acc);
+    out[(size_t)b * D + j] = acc;
+}
+
 // out[i] = Q[idx[i]] (rows of D floats); and the way back for results
 __global__ void k_gather_queries(const float *__restrict__ Q, const int *__restrict__ idx, int n, int D, float *__restrict__ out)
 {

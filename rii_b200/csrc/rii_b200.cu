@@ -148,11 +148,20 @@ struct rii_index {
     DevBuf gen_keys, gen_sorted, gen_seg, gen_cnt;
     // batched re-run of flagged queries
     DevBuf redo_idx, redo_q, redo_ids, redo_d, redo_c;
+    // small calls (the reference's one-query-per-call shape, src/main.cpp:17-27): queries and results travel through one
+    // pinned, device-mapped host buffer -- the kernels read the query and write the results over PCIe themselves, so a call
+    // is launches + one stream synchronisation, no cudaMemcpy
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+    // OPQ rotation applied on the device before the table build (rii/rii.py:305-306): R (D, D) row-major, or null
+    float *d_R = nullptr;
+    DevBuf qrot;
 
     DevBuf dbg;               // optional phase clocks of the v2 scan kernel ("debug_clocks" option)
     int opt_debug_clocks = 0;
     int opt_stream_ctas = 0;  // v4 engine: 1 = always one CTA per SM; otherwise per-query IVF batches run two CTAs per SM
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
+    int opt_zero_copy = 1;      // small host calls go through mapped pinned memory (no cudaMemcpy)
     int opt_persist = 1;        // 0 = never, 1 = auto (batches of >= 296 queries), 2 = whenever the shape fits (tests)
     int opt_assign_kernel = 0;  // 0 auto (streaming engine, two CTAs per SM), 1 natural-layout k_assign, 3 streaming engine with one CTA per SM
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
@@ -1089,6 +1098,13 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
     if ((long long)topk > (S ? S : Ntot)) return fail(RII_ERR_ARG, "need topk <= N (and topk <= len(target_ids))");  // :200,:219
     if (S > 0 && !d_tids) return fail(RII_ERR_ARG, "target_ids is null but S > 0");
     const int D = h->M * h->Ds;
+    if (h->d_R) {  // OPQ: rotate the queries first (rii/rii.py:305-306, fine_quantizer.rotate)
+        CKR(h->qrot.ensure((size_t)B * D * 4));
+        k_rotate<<<dim3((D + 127) / 128, B), 128, 0, st>>>(d_Q, h->d_R, D, h->qrot.as<float>());
+        LAUNCHED();
+        CK(cudaGetLastError());
+        d_Q = h->qrot.as<float>();
+    }
     if (method == RII_METHOD_LINEAR) {
         if (h->N <= 0) {  // an empty shard of a larger index
             CK(cudaMemsetAsync(d_out_counts, 0, (size_t)B * 4, st));
@@ -1133,6 +1149,27 @@ int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tid
     CK(cudaSetDevice(h->device));
     const int D = h->M * h->Ds;
     cudaStream_t st = h->stream;
+    if (B <= 16 && S == 0 && topk <= 1024 && h->opt_zero_copy) {  // low-latency path: zero-copy through mapped pinned memory
+        const size_t oq = 0, oi = ((size_t)B * D * 4 + 15) & ~(size_t)15, od = oi + (size_t)B * topk * 8, oc = od + (size_t)B * topk * 4;
+        const size_t need = oc + (size_t)B * 4;
+        if (need > h->pin_cap) {
+            if (h->pin) cudaFreeHost(h->pin);
+            h->pin = nullptr;
+            h->pin_cap = 0;
+            CK(cudaHostAlloc(&h->pin, need + 4096, cudaHostAllocMapped));
+            h->pin_cap = need + 4096;
+        }
+        char *hp = (char *)h->pin, *dp = nullptr;
+        CK(cudaHostGetDevicePointer((void **)&dp, h->pin, 0));
+        std::memcpy(hp + oq, Q, (size_t)B * D * 4);
+        std::memset(hp + oc, 0, (size_t)B * 4);
+        CKR(query_dev(h, (const float *)(dp + oq), B, topk, nullptr, 0, L, method, (long long *)(dp + oi), (float *)(dp + od), (int *)(dp + oc), st, -1));
+        CK(cudaStreamSynchronize(st));
+        std::memcpy(out_ids, hp + oi, (size_t)B * topk * 8);
+        std::memcpy(out_dists, hp + od, (size_t)B * topk * 4);
+        std::memcpy(out_counts, hp + oc, (size_t)B * 4);
+        return 0;
+    }
     CKR(h->q.ensure((size_t)B * D * 4));
     CKR(h->o_ids.ensure((size_t)B * topk * 8));
     CKR(h->o_dists.ensure((size_t)B * topk * 4));
@@ -1217,6 +1254,9 @@ int rii_destroy(rii_index_t *h)
                       &h->redo_ids, &h->redo_d, &h->redo_c})
         b->release();
     if (h->sort_tmp.p) cudaFree(h->sort_tmp.p);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->d_R) cudaFree(h->d_R);
+    h->qrot.release();
     if (h->d_cw) cudaFree(h->d_cw);
     if (h->d_cw_t) cudaFree(h->d_cw_t);
     if (h->d_Dm) cudaFree(h->d_Dm);
@@ -1374,6 +1414,10 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
         if (value != 0 && value != 1 && value != 4)
             return fail(RII_ERR_ARG, "scan_kernel must be 0 (auto), 1 (natural-layout kernels) or 4 (skew64 streaming engine)");
         h->opt_scan_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "zero_copy")) {
+        h->opt_zero_copy = value != 0;
         return 0;
     }
     if (!strcmp(name, "persist")) {
@@ -1761,6 +1805,20 @@ int rii_encode(rii_index_t *h, const float *vecs, int64_t n, uint8_t *out_codes)
     dx.release();
     dc.release();
     return rc;
+}
+
+int rii_set_rotation(rii_index_t *h, const float *R)
+{
+    if (!h) return fail(RII_ERR_ARG, "null index");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_R) cudaFree(h->d_R);
+    h->d_R = nullptr;
+    if (!R) return 0;
+    const size_t D = (size_t)h->M * h->Ds;
+    CK(cudaMalloc(&h->d_R, D * D * 4));
+    CK(cudaMemcpy(h->d_R, R, D * D * 4, cudaMemcpyHostToDevice));
+    return 0;
 }
 
 int rii_set_shard(rii_index_t *h, int64_t id_base, int64_t N_total)

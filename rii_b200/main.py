@@ -233,6 +233,17 @@ class RiiCpp(object):
         check(_capi.lib().rii_encode(self._h, _ptr(X, C.c_float), X.shape[0], _ptr(out, C.c_uint8)))
         return out
 
+    def set_rotation(self, R):
+        """OPQ rotation applied on the device to every query (q @ R); None switches it off."""
+        if R is None:
+            check(_capi.lib().rii_set_rotation(self._h, None))
+            return
+        R = np.ascontiguousarray(R, np.float32)
+        D = self.M * self.Ds
+        if R.shape != (D, D):
+            raise ValueError("R must have shape (D, D)")
+        check(_capi.lib().rii_set_rotation(self._h, _ptr(R, C.c_float)))
+
     def set_option(self, name, value):
         check(_capi.lib().rii_set_option(self._h, name.encode(), int(value)))
 

@@ -20,13 +20,23 @@ class Rii(object):
         device (int): CUDA device ordinal of the index.
     """
 
-    def __init__(self, fine_quantizer, device=0):
+    def __init__(self, fine_quantizer, device=0, rotate_on_device=False):
         assert _pq.is_quantizer(fine_quantizer)
         assert fine_quantizer.codewords is not None, "Please fit the PQ/OPQ instance first"
         assert fine_quantizer.Ks <= 256, "Ks must be less than 256 so that each code must be uint8"
         self.fine_quantizer = copy.deepcopy(fine_quantizer)
         self.impl_cpp = main.RiiCpp(fine_quantizer.codewords, fine_quantizer.verbose, device=device)
         self.threshold = None
+        # OPQ (rii/rii.py:305-306 rotates every query on the host): optionally folded into the engine, ahead of the table build
+        self._device_rotation = bool(rotate_on_device) and _pq.is_opq(fine_quantizer)
+        if self._device_rotation:
+            self.impl_cpp.set_rotation(fine_quantizer.R)
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._device_rotation = bool(state.get("_device_rotation", False))
+        if self._device_rotation:  # the engine's pickle state is the reference's (src/main.cpp:35-54): the rotation is ours to restore
+            self.impl_cpp.set_rotation(self.fine_quantizer.R)
 
     # ---- properties, rii/rii.py:40-121 ------------------------------------------------------
     @property
@@ -143,7 +153,7 @@ class Rii(object):
         """ids (topk,) int64 and distances (topk,) float64 of the nearest PQ codes; rii/rii.py:235-320."""
         assert method in ["auto", "linear", "ivf"]
         topk, L, tids, len_target_ids = self._prepare(topk, L, target_ids, sort_target_ids)
-        q_ = self.fine_quantizer.rotate(q) if _pq.is_opq(self.fine_quantizer) else q
+        q_ = self.fine_quantizer.rotate(q) if _pq.is_opq(self.fine_quantizer) and not self._device_rotation else q
         if method == "auto":
             method = "linear" if self._use_linear(len_target_ids, L, subset=target_ids is not None) else "ivf"
         if method == "linear":
@@ -158,7 +168,7 @@ class Rii(object):
         assert method in ["auto", "linear", "ivf"]
         assert Q.ndim == 2 and Q.dtype == np.float32
         topk, L, tids, _ = self._prepare(topk, L, target_ids, sort_target_ids)
-        Q_ = self.fine_quantizer.rotate(Q) if _pq.is_opq(self.fine_quantizer) else Q
+        Q_ = self.fine_quantizer.rotate(Q) if _pq.is_opq(self.fine_quantizer) and not self._device_rotation else Q
         if method == "auto":
             method = "linear" if self._use_linear(len(tids) if target_ids is not None else self.N, L,
                                                    subset=target_ids is not None, batch=Q.shape[0]) else "ivf"

@@ -995,3 +995,39 @@ def test_persistent_batch_kernel(M, D):
                 exp = O.query_ivf(O.dtable(Qd[b].cpu().numpy(), cw, 16), codes, centers, offsets, ids, topk, L)
                 n = int(gc[b])
                 assert_same_result(gi[b, :n], gd[b, :n], exp[0], exp[1], "persist shards k=%d L=%d b=%d" % (topk, L, b))
+
+
+def test_opq_rotation_on_the_device_and_small_call_path():
+    """(1) rii/rii.py:305-306: the OPQ rotation of the query folded into the engine (k_rotate, fp32 FMA chain) returns the
+    ids of the host rotation and distances within the 1e-5 relative contract; it survives pickling.  (2) single calls
+    (zero-copy through mapped pinned memory) == the staged-copy path."""
+    import copy
+    from rii_b200 import Rii, pq
+    rng = np.random.default_rng(9)
+    D, M, N = 64, 16, 20000
+    X = rng.random((N, D), dtype=np.float32)
+    codec = pq.OPQ(M=M, Ks=256, verbose=False).fit(X[:2000], pq_iter=3, rotation_iter=2, seed=123)
+    e_host = Rii(codec).add_configure(X, nlist=50, iter=2)
+    e_dev = Rii(codec, rotate_on_device=True).add_configure(X, nlist=50, iter=2)
+    e_dev2 = copy.deepcopy(e_dev)
+    Q = rng.random((20, D), dtype=np.float32)
+    for q in Q:
+        for method in ("linear", "ivf"):
+            ih, dh = e_host.query(q, topk=5, L=2000, method=method)
+            for e in (e_dev, e_dev2):
+                i2, d2 = e.query(q, topk=5, L=2000, method=method)
+                assert np.allclose(d2, dh, rtol=1e-5, atol=0), (method, d2, dh)   # tolerance: north_star's 1e-5 relative
+                assert np.array_equal(i2, ih) or np.allclose(np.sort(d2), np.sort(dh), rtol=1e-5)
+    bi, bd, bc = e_dev.query_batch(Q, topk=5, L=2000, method="ivf")
+    hi, hd, hc = e_host.query_batch(Q, topk=5, L=2000, method="ivf")
+    assert np.allclose(bd, hd, rtol=1e-5) and (bi == hi).mean() > 0.95
+    # zero-copy small calls == staged copies, bit for bit
+    imp = e_host.impl_cpp
+    qr = codec.rotate(Q)
+    for q in qr[:8]:
+        imp.set_option("zero_copy", 1)
+        a = (imp.query_linear(q, 7, EMPTY), imp.query_ivf(q, 7, EMPTY, 1500))
+        imp.set_option("zero_copy", 0)
+        b = (imp.query_linear(q, 7, EMPTY), imp.query_ivf(q, 7, EMPTY, 1500))
+        assert a == b
+    imp.set_option("zero_copy", 1)
