@@ -18,6 +18,19 @@ __device__ __forceinline__ float sqdiff(float a, float b)
     return __fmul_rn(t, t);
 }
 
+// One table entry for Ds <= 4 from the zero-padded float4 copies of the query sub-vector and the codeword:
+// (s0 + s1) + (s2 + s3), s_i = (q_i - c_i)^2, absent lanes contribute +0 (src/distance.h:148-169).  The subtracts and the
+// multiplies are packed (FADD2 / FMUL2: two lanes per instruction, each rounded like the scalar op); the adds stay scalar --
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the explicit rounding modifiers, which would change
+// the bits.
+__device__ __forceinline__ float sqdist4(float2 qa, float2 qb, float4 c)
+{
+    float2 ta = __fadd2_rn(qa, make_float2(-c.x, -c.y)), tb = __fadd2_rn(qb, make_float2(-c.z, -c.w));
+    ta = __fmul2_rn(ta, ta);
+    tb = __fmul2_rn(tb, tb);
+    return __fadd_rn(__fadd_rn(ta.x, ta.y), __fadd_rn(tb.x, tb.y));
+}
+
 static __device__ __noinline__ float l2sqr_lanes(const float *__restrict__ x, const float *__restrict__ y, int d, int variant)
 {
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -196,6 +209,7 @@ struct SkewArgs {
     int coarse_mode;           // IVF: 0 = one launch does everything; 1 = coarse pass only (write plan.ranked, no scan);
                                //      2 = no coarse pass: the ranking is read from plan.ranked, the plan is made in-kernel
     int coarse_lists;          // v4 fused: rank the centers with the warps' top-k lists (nlist > 1024) instead of keeping every distance
+    int l2_prefetch;           // posting lists that do not fit the L2: bulk L2 prefetches run ahead of the cp.async front
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)

@@ -163,6 +163,8 @@ struct rii_index {
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
     int opt_zero_copy = 1;      // small host calls go through mapped pinned memory (no cudaMemcpy)
     int opt_persist = 1;        // 0 = never, 1 = auto (batches of >= 296 queries), 2 = whenever the shape fits (tests)
+    int opt_l2_prefetch = -1;   // persistent kernel: bulk L2 prefetches (UBLKPF) ahead of the copy front; 0 / 1, -1 = auto = off: measured neutral on
+                                // HBM-resident lists (C5 shape 0.463 vs 0.465 ms, profiles/r02_phase_clocks.jsonl) -- the scan is bound on the SM side
     int opt_assign_kernel = 0;  // 0 auto (streaming engine, two CTAs per SM), 1 natural-layout k_assign, 3 streaming engine with one CTA per SM
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
                               // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
@@ -581,6 +583,7 @@ struct ListsView {
     const uint8_t *skew = nullptr;       // skew64 segment per list (streaming engine), or null
     const long long *skew_off = nullptr;
     long long cap_local = 0;             // upper bound of the ids listed locally
+    long long skew_bytes = 0;            // size of the skew64 table (decides whether it can be L2-resident)
 };
 
 int make_tables(rii_index *h, const float *d_Q, int B, cudaStream_t st)  // K1 for the natural-layout / general kernels
@@ -779,6 +782,7 @@ int main_view(rii_index *h, cudaStream_t st, ListsView *v)
         CKR(ensure_skew_lists(h, st));
         v->skew = h->skew_lists.as<uint8_t>();
         v->skew_off = h->skew_off.as<long long>();
+        v->skew_bytes = (h->h_offsets.back() + 64ll * h->nlist) * h->rb;
     }
     v->offsets = h->offsets.as<long long>();
     v->ids = h->ids.as<int>();
@@ -827,6 +831,7 @@ int build_subview(rii_index *h, const long long *d_tids, long long S, cudaStream
         CKR(skew_build(h->d_codes, v->ids, v->offsets, h->sub_off.as<long long>(), nlist, 0, cap_rows, h->sub_skew.as<uint8_t>(), h->M, h->rb, st));
         v->skew = h->sub_skew.as<uint8_t>();
         v->skew_off = h->sub_off.as<long long>();
+        v->skew_bytes = cap_rows * 32;
     }
     return 0;
 }
@@ -953,6 +958,7 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
             sp_.centers = mode == 0 ? h->centers_skew.as<uint8_t>() : nullptr;
             sp_.coarse_mode = mode == 0 ? 0 : 2;
             sp_.cap = PS_CAPW_HOST;
+            sp_.l2_prefetch = h->opt_l2_prefetch > 0 ? 1 : 0;
             out.final = 1;
             sp_.out = out;
             Prof pr(h, st, PK_SCAN_IVF);
@@ -1423,6 +1429,11 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
     if (!strcmp(name, "persist")) {
         if (value < 0 || value > 2) return fail(RII_ERR_ARG, "persist must be 0 (off), 1 (auto) or 2 (whenever the shape fits)");
         h->opt_persist = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "l2_prefetch")) {
+        if (value < -1 || value > 1) return fail(RII_ERR_ARG, "l2_prefetch must be -1 (auto), 0 or 1");
+        h->opt_l2_prefetch = (int)value;
         return 0;
     }
     if (!strcmp(name, "assign_kernel")) {

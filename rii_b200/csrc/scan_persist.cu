@@ -26,13 +26,16 @@ int launch_persist(const SkewArgs &a, int B, cudaStream_t st)
     CK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return rii_fail(RII_ERR_LIMIT, "device ordinal >= 64");
     if (!configured[dev]) {
-        CK(cudaFuncSetAttribute(k_scan_persist32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k_scan_persist32, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_scan_persist32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_scan_persist32<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_scan_persist32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_scan_persist32<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = true;
     }
     const int grid = std::min(B, sms[dev]);
-    k_scan_persist32<<<grid, (PS_NC + 1) * 32, PS_SMEM_BYTES, st>>>(a, B);
+    if (a.k == 1) k_scan_persist32<true><<<grid, (PS_NC + 1) * 32, PS_SMEM_BYTES, st>>>(a, B);
+    else k_scan_persist32<false><<<grid, (PS_NC + 1) * 32, PS_SMEM_BYTES, st>>>(a, B);
     rii_count_launch();
     CK(cudaGetLastError());
     return 0;

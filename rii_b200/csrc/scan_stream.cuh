@@ -437,8 +437,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 #pragma unroll 16
                     for (int i = wid; i < 256; i += NW) {
                         const int ks = (i + rot) & 255;
-                        const float4 c4 = __ldg(cw4 + ks * Mr);
-                        float v = __fadd_rn(__fadd_rn(sqdiff(q4.x, c4.x), sqdiff(q4.y, c4.y)), __fadd_rn(sqdiff(q4.z, c4.z), sqdiff(q4.w, c4.w)));
+                        float v = sqdist4(make_float2(q4.x, q4.y), make_float2(q4.z, q4.w), __ldg(cw4 + ks * Mr));
                         v = ks < a.Ks ? v : 0.f;
                         bad |= !(v <= ST_TABLE_LIMIT);
                         lut2[ks * 64 + ((m + 32) & 63)] = v;

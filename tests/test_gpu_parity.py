@@ -997,6 +997,39 @@ def test_persistent_batch_kernel(M, D):
                 assert_same_result(gi[b, :n], gd[b, :n], exp[0], exp[1], "persist shards k=%d L=%d b=%d" % (topk, L, b))
 
 
+def test_persistent_batch_kernel_exact_ties_across_lists():
+    """topk = 1 on k_scan_persist32<K1> keeps one (distance, position) per warp; exact distance ties between candidates of
+    DIFFERENT posting lists must still be decided by id (the reference ranks by distance only; we pin (distance, id)).
+    Codes with 8 live sub-spaces over 4 codewords: 65536 distinct codes for 60000 rows -> duplicates and massive ties."""
+    D, M, Ks, N, nlist = 64, 32, 4, 60000, 64
+    cw, codes, Q = synth(D, M, Ks, N, 12, seed=77)
+    codes[:, 8:] = 0
+    e = engine(cw, codes)
+    e.reconfigure(nlist, 1)
+    centers = e.coarse_centers_array()
+    offsets, ids = e.posting_lists_csr()
+    B = 333
+    Qb = np.ascontiguousarray(np.tile(Q, (B // len(Q) + 1, 1))[:B])
+    for topk, L in [(1, 20000), (1, 900), (4, 20000)]:
+        e.set_option("persist", 2)
+        f = e.query_batch(Qb, topk, L=L, method="ivf")
+        e.set_option("persist", 0)
+        u = e.query_batch(Qb, topk, L=L, method="ivf")
+        assert np.array_equal(f[2], u[2]) and np.array_equal(f[0], u[0]) and np.array_equal(bits(f[1]), bits(u[1])), (topk, L)
+        for b in range(0, B, 29):
+            exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
+            n = int(f[2][b])
+            assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "persist ties k=%d L=%d b=%d" % (topk, L, b))
+    # the L2-prefetch variant of the walk returns the same results
+    e.set_option("persist", 2)
+    e.set_option("l2_prefetch", 1)
+    g = e.query_batch(Qb, 1, L=20000, method="ivf")
+    e.set_option("l2_prefetch", 0)
+    h = e.query_batch(Qb, 1, L=20000, method="ivf")
+    e.set_option("l2_prefetch", -1)
+    assert np.array_equal(g[0], h[0]) and np.array_equal(bits(g[1]), bits(h[1])) and np.array_equal(g[2], h[2])
+
+
 def test_opq_rotation_on_the_device_and_small_call_path():
     """(1) rii/rii.py:305-306: the OPQ rotation of the query folded into the engine (k_rotate, fp32 FMA chain) returns the
     ids of the host rotation and distances within the 1e-5 relative contract; it survives pickling.  (2) single calls
