@@ -209,7 +209,6 @@ struct SkewArgs {
     int coarse_mode;           // IVF: 0 = one launch does everything; 1 = coarse pass only (write plan.ranked, no scan);
                                //      2 = no coarse pass: the ranking is read from plan.ranked, the plan is made in-kernel
     int coarse_lists;          // v4 fused: rank the centers with the warps' top-k lists (nlist > 1024) instead of keeping every distance
-    int l2_prefetch;           // posting lists that do not fit the L2: bulk L2 prefetches run ahead of the cp.async front
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)

@@ -163,8 +163,6 @@ struct rii_index {
     int opt_fuse_coarse = 1;  // fuse coarse ranking + plan into the v2 posting-list scan when one CTA serves a query
     int opt_zero_copy = 1;      // small host calls go through mapped pinned memory (no cudaMemcpy)
     int opt_persist = 1;        // 0 = never, 1 = auto (batches of >= 296 queries), 2 = whenever the shape fits (tests)
-    int opt_l2_prefetch = -1;   // persistent kernel: bulk L2 prefetches (UBLKPF) ahead of the copy front; 0 / 1, -1 = auto = off: measured neutral on
-                                // HBM-resident lists (C5 shape 0.463 vs 0.465 ms, profiles/r02_phase_clocks.jsonl) -- the scan is bound on the SM side
     int opt_assign_kernel = 0;  // 0 auto (streaming engine, two CTAs per SM), 1 natural-layout k_assign, 3 streaming engine with one CTA per SM
     int opt_scan_kernel = 0;  // 0 auto, 1 natural-layout kernels (v1), 2 skewed conflict-free kernel (v2), 3 dual-stream FFMA2
                               // skewed kernel (v3), 4 register-streaming kernel over the skew64 layout (v4; what auto picks
@@ -958,7 +956,6 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
             sp_.centers = mode == 0 ? h->centers_skew.as<uint8_t>() : nullptr;
             sp_.coarse_mode = mode == 0 ? 0 : 2;
             sp_.cap = PS_CAPW_HOST;
-            sp_.l2_prefetch = h->opt_l2_prefetch > 0 ? 1 : 0;
             out.final = 1;
             sp_.out = out;
             Prof pr(h, st, PK_SCAN_IVF);
@@ -1429,11 +1426,6 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value)
     if (!strcmp(name, "persist")) {
         if (value < 0 || value > 2) return fail(RII_ERR_ARG, "persist must be 0 (off), 1 (auto) or 2 (whenever the shape fits)");
         h->opt_persist = (int)value;
-        return 0;
-    }
-    if (!strcmp(name, "l2_prefetch")) {
-        if (value < -1 || value > 1) return fail(RII_ERR_ARG, "l2_prefetch must be -1 (auto), 0 or 1");
-        h->opt_l2_prefetch = (int)value;
         return 0;
     }
     if (!strcmp(name, "assign_kernel")) {

@@ -21,7 +21,9 @@
 //
 // The walk of a warp is a list of RUNS: consecutive 2 KB blocks of one posting list (its groups inside the warp's slice
 // plus the drain block behind them, which is simply the next block in memory).  Inside a run the issue logic is a pointer
-// increment and a counter; segment tables are only read when a run starts (~5 times per query and warp).
+// increment and a counter; segment tables are only read when a run starts (~5 times per query and warp).  (Bulk L2 prefetches
+// -- cp.async.bulk.prefetch.L2, UBLKPF -- running 8 blocks ahead of the cp.async front were measured on HBM-resident lists:
+// 0.463 vs 0.465 ms for the C5-shaped batch, i.e. nothing: the scan is bound on the SM side, not by memory latency.  Removed.)
 //
 // topk == 1 (the recall@1 operating point of every BASELINE config) has its own instantiation: a warp keeps its best
 // (distance, position) in two warp-uniform registers -- no key buffers, no compaction, no shared-memory traffic; a group
@@ -119,12 +121,6 @@ __device__ __forceinline__ long long ps_mbar_wait(uint32_t bar, uint32_t parity,
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1536), "l"(bp + 1536));     \
             bp += ST_BLOCK_BYTES;                                                                             \
             --run_left;                                                                                       \
-            if (pf_on && (run_left & 3) == 0 && run_left > PS_PF_AHEAD) {                                      \
-                /* HBM-resident lists: pull the 4 blocks PS_PF_AHEAD ahead of the copy front into the L2 (one TMA-unit */ \
-                /* instruction per 8 KB, no registers, no shared memory) */                                   \
-                const uint8_t *pf_ = bp - lane * 16 + PS_PF_AHEAD * ST_BLOCK_BYTES;                           \
-                if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_), "r"(4 * ST_BLOCK_BYTES) : "memory"); \
-            }                                                                                                 \
         }                                                                                                     \
         asm volatile("cp.async.commit_group;");                                                               \
     }
@@ -146,7 +142,6 @@ __device__ __forceinline__ long long ps_mbar_wait(uint32_t bar, uint32_t parity,
         out2 = 0ull;                                                                                          \
         emit2(dx_, dy_, dsel_);                                                                               \
     }
-#define PS_PF_AHEAD 8
 
 // the w smallest of np (distance bits, index) pairs by ONE warp: 256-bin histogram over [mn, mx], the bin holding the
 // w-th smallest, gather of everything up to that bin as (dist, index) keys, register sort.  Returns the number of keys in
@@ -242,7 +237,6 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         const uint32_t ring = smem_base + (wid < PS_RINGS_A ? PS_OFF_RINGS_A + wid * PS_RING_BYTES : PS_OFF_RINGS_B + (wid - PS_RINGS_A) * PS_RING_BYTES) +
                               lane * 16;
         const uint8_t *pc = a.codes;
-        const bool pf_on = a.l2_prefetch != 0;
 #pragma unroll 1
         for (int qi = 0; qi < n_my; ++qi) {
             const int p = qi & 1;
@@ -287,10 +281,6 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
                 int tail = 64;
                 if (end == seg_gend) tail = s_take[seg] - (seg_gend - seg_g0 - 1) * 64;  // rows of the list's last group
                 last_bits = (lane < tail ? 1u : 0u) | (lane + 32 < tail ? 2u : 0u);
-                if (pf_on && lane == 0) {
-                    const uint32_t nb = (uint32_t)(run_left < PS_PF_AHEAD + 4 ? run_left : PS_PF_AHEAD + 4) * ST_BLOCK_BYTES;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(bp), "r"(nb) : "memory");
-                }
             };
             {
                 const int G = J ? s_gcum[J - 1] : 0;
@@ -427,7 +417,6 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         u64 *selk = reinterpret_cast<u64 *>(smem_raw + PS_OFF_SELK);
         const uint32_t ring = smem_base + PS_OFF_PRING + lane * 16;
         const bool fused = a.coarse_mode == 0;
-        const bool pf_on = false;
         long long p_wait = 0, p_merge = 0, p_table = 0, p_coarse = 0, p_select = 0, p_plan = 0;
 
         // final merge of the consumers' results of query qi -> output

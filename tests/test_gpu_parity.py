@@ -1020,15 +1020,6 @@ def test_persistent_batch_kernel_exact_ties_across_lists():
             exp = O.query_ivf(O.dtable(Qb[b], cw, 16), codes, centers, offsets, ids, topk, L)
             n = int(f[2][b])
             assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "persist ties k=%d L=%d b=%d" % (topk, L, b))
-    # the L2-prefetch variant of the walk returns the same results
-    e.set_option("persist", 2)
-    e.set_option("l2_prefetch", 1)
-    g = e.query_batch(Qb, 1, L=20000, method="ivf")
-    e.set_option("l2_prefetch", 0)
-    h = e.query_batch(Qb, 1, L=20000, method="ivf")
-    e.set_option("l2_prefetch", -1)
-    assert np.array_equal(g[0], h[0]) and np.array_equal(bits(g[1]), bits(h[1])) and np.array_equal(g[2], h[2])
-
 
 def test_opq_rotation_on_the_device_and_small_call_path():
     """(1) rii/rii.py:305-306: the OPQ rotation of the query folded into the engine (k_rotate, fp32 FMA chain) returns the

@@ -30,7 +30,6 @@ def run():
     ap.add_argument("--split", type=int, default=1)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--persist", type=int, default=1)
-    ap.add_argument("--l2pf", type=int, default=-1)
     ap.add_argument("--shards", type=int, default=1, help="pretend this GPU holds 1/shards of every list (global lengths = shards x local)")
     a = ap.parse_args()
     lib = _capi.lib()
@@ -55,7 +54,6 @@ def run():
     Q = torch.rand((B, a.d), device=dev)
     e.set_option("stream_ctas", a.ctas)
     e.set_option("persist", a.persist)
-    e.set_option("l2_prefetch", a.l2pf)
     e.set_option("debug_clocks", 1)
     lib.rii_profile_enable(e._h, 1)
     w = _capi.check(lib.rii_coarse_width(e._h, L))
