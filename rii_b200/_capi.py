@@ -21,8 +21,9 @@ SYMBOLS = {
     "rii_add_codes_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
     "rii_reconfigure": (C.c_int, [_vp, C.c_int, C.c_int]),
     "rii_clear": (C.c_int, [_vp]),
-    "rii_query_linear": (C.c_int64, [_vp, _f32p, C.c_int, _i64p, C.c_int64, _i64p, _f32p]),
-    "rii_query_ivf": (C.c_int64, [_vp, _f32p, C.c_int, _i64p, C.c_int64, C.c_int64, _i64p, _f32p]),
+    # (void pointers: the single-query wrappers pass raw addresses -- building typed ctypes pointers costs microseconds)
+    "rii_query_linear": (C.c_int64, [_vp, _vp, C.c_int, _vp, C.c_int64, _vp, _vp]),
+    "rii_query_ivf": (C.c_int64, [_vp, _vp, C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "rii_query_batch": (C.c_int, [_vp, _f32p, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int64, C.c_int, _i64p, _f32p,
                                   _i32p]),
     "rii_query_batch_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp,

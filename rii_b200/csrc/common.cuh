@@ -104,6 +104,8 @@ struct TopkOut {
     long long id_base;
     const long long *id_map;  // when set: key id -> global id (subset scans over a compact copy of the target rows)
     int final;
+    int *merge_cnt;      // (B) zero on entry, when !final: the LAST CTA of a query to deliver its partial list merges all of
+                         // them into out_ids / out_dists / out_counts itself (and resets the counter) -- no separate k_merge launch
 };
 __device__ __forceinline__ void emit_topk(BlockTopk &tk, const TopkOut &o, int b, int part, int parts)
 {

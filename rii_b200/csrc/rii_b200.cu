@@ -139,6 +139,7 @@ struct rii_index {
     std::vector<long long> len_sorted_prefix;  // prefix sums of ascending *global* list lengths
 
     // scratch (grow only)
+    DevBuf merge_cnt;   // (B) per-query arrival counters of the in-kernel merge (zero between launches)
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
         tmp2, tmp3;
     // sub-index of a subset search (target_ids): (list, row) pairs, their sorted form = CSR of the members, skew64 copy
@@ -596,6 +597,24 @@ int make_tables(rii_index *h, const float *d_Q, int B, cudaStream_t st)  // K1 f
     return 0;
 }
 
+// Partial lists of `parts` CTAs per query: merged by the last CTA itself when parts * topk keys fit one warp sort (returns
+// true: no merge launch needed), else by k_merge.
+int prepare_partial(rii_index *h, int B, int parts, int topk, TopkOut *out, cudaStream_t st, bool *in_kernel)
+{
+    CKR(h->partial.ensure((size_t)B * parts * topk * 8));
+    out->partial = h->partial.as<u64>();
+    out->merge_cnt = nullptr;
+    *in_kernel = (long long)parts * topk <= 256;
+    if (*in_kernel) {
+        if ((size_t)B * 4 > h->merge_cnt.cap) {
+            CKR(h->merge_cnt.ensure((size_t)std::max(B, 4096) * 4));
+            CK(cudaMemsetAsync(h->merge_cnt.p, 0, h->merge_cnt.cap, st));  // (the kernels leave the counters at zero)
+        }
+        out->merge_cnt = h->merge_cnt.as<int>();
+    }
+    return 0;
+}
+
 int launch_merge(rii_index *h, int B, int parts, int topk, TopkOut out, cudaStream_t st)
 {
     const int mcap = next_pow2(topk + RII_THREADS);
@@ -680,7 +699,7 @@ int run_linear(rii_index *h, const float *d_Q, int B, int topk, const long long 
     int nw = 0, shape = 0;
     size_t smem4 = 0;
     if (h->rb && topk <= SK_MAX_K && h->opt_scan_kernel != 1) shape = stream_pick(h->rb, false, false, capw, 0, 0, &nw, &smem4);
-    bool use4 = shape > 0 && (h->opt_scan_kernel == 4 || (S == 0 ? (h->N >= (1ll << 21) || (B >= 16 && h->N >= 65536)) : ncand * B >= (1ll << 22)));
+    bool use4 = shape > 0 && (h->opt_scan_kernel == 4 || (S == 0 ? h->N >= 32768 : ncand * B >= (1ll << 22)));
     long long i0 = 0, cnt = S;
     if (use4 && S) {
         if (tids_state < 0 || h->N_total >= 0) {  // ascending?  which run of it lies in this shard?
@@ -729,17 +748,15 @@ int run_linear(rii_index *h, const float *d_Q, int B, int topk, const long long 
         }
         const int parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)), std::max<long long>(1, sa.N / (nw * SK_TILE_ROWS * 4)));
         out.final = parts == 1;
-        if (!out.final) {
-            CKR(h->partial.ensure((size_t)B * parts * topk * 8));
-            out.partial = h->partial.as<u64>();
-        }
+        bool in_kernel = false;
+        if (!out.final) CKR(prepare_partial(h, B, parts, topk, &out, st, &in_kernel));
         sa.out = out;
         if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         {
             Prof pr(h, st, PK_SCAN_LINEAR);
             CKR(launch_stream(shape, false, sa, parts, B, smem4, st));
         }
-        if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+        if (!out.final && !in_kernel) CKR(launch_merge(h, B, parts, topk, out, st));
         return 0;
     }
     // ---- natural-layout kernel: keys of the CTA in shared memory ----
@@ -942,7 +959,10 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
     if (use4) {
         int parts = mode == 1 ? 1 : (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)),
                                                             std::max<long long>(1, (L + nw * SK_TILE_ROWS - 1) / (nw * SK_TILE_ROWS)));
-        const bool fuse = mode == 0 && parts == 1 && h->opt_fuse_coarse;
+        // one launch does everything when a CTA serves a whole query -- or, with nlist <= 1024 (every CTA of a query repeats the
+        // cheap coarse pass + selection + plan and scans its share), for any number of CTAs per query: a single query is then
+        // ONE kernel launch (table, ranking, plan, scan, merge by the last CTA)
+        const bool fuse = mode == 0 && h->opt_fuse_coarse && (parts == 1 || (!big_nlist && (long long)parts * topk <= 256));
         SkewArgs sa{};
         sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
         sa.codes = v.skew; sa.offsets = v.offsets; sa.ids = v.ids; sa.skew_off = v.skew_off;
@@ -963,10 +983,13 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
         }
         if (fuse) {
             sa.centers = h->centers_skew.as<uint8_t>(); sa.coarse_lists = big_nlist ? 1 : 0; sa.coarse_mode = 0;
-            sa.cap = capw; out.final = 1; sa.out = out;
-            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)B * 64)); sa.dbg = h->dbg.as<long long>(); }
+            sa.cap = capw; out.final = parts == 1;
+            bool in_kernel = true;
+            if (!out.final) CKR(prepare_partial(h, B, parts, topk, &out, st, &in_kernel));
+            sa.out = out;
+            if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)B * parts * 64)); sa.dbg = h->dbg.as<long long>(); }
             Prof pr(h, st, PK_SCAN_IVF);
-            return launch_stream(shape_c, true, sa, 1, B, smem_c, st);
+            return launch_stream(shape_c, true, sa, parts, B, smem_c, st);
         }
         if (mode != 2) {  // coarse pass on its own: one CTA per query ranks the lists
             SkewArgs sc = sa;
@@ -977,17 +1000,15 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
         }
         sa.centers = nullptr; sa.coarse_mode = 2; sa.cap = std::max(64, next_pow2(topk + 32));
         out.final = parts == 1;
-        if (!out.final) {
-            CKR(h->partial.ensure((size_t)B * parts * topk * 8));
-            out.partial = h->partial.as<u64>();
-        }
+        bool in_kernel = false;
+        if (!out.final) CKR(prepare_partial(h, B, parts, topk, &out, st, &in_kernel));
         sa.out = out;
         if (h->opt_debug_clocks) { CKR(h->dbg.ensure((size_t)parts * B * 64)); sa.dbg = h->dbg.as<long long>(); }
         {
             Prof pr(h, st, PK_SCAN_IVF);
             CKR(launch_stream(shape, true, sa, parts, B, smem4, st));
         }
-        if (!out.final) CKR(launch_merge(h, B, parts, topk, out, st));
+        if (!out.final && !in_kernel) CKR(launch_merge(h, B, parts, topk, out, st));
         return 0;
     }
     // ---- natural-layout kernels: coarse keys and candidate keys of a CTA in shared memory ----
@@ -1250,7 +1271,7 @@ int rii_destroy(rii_index_t *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->skew_lin, &h->skew_lists, &h->skew_off, &h->centers_skew, &h->skew_misc_off, &h->dbg, &h->centers, &h->offsets, &h->ids, &h->loc_len, &h->glob_len, &h->pre_len, &h->T, &h->partial, &h->ranked,
-                      &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
+                      &h->merge_cnt, &h->cum, &h->take_last, &h->J, &h->flags, &h->filt, &h->bitmap, &h->q, &h->tids, &h->o_ids, &h->o_dists,
                       &h->o_counts, &h->tmp0, &h->tmp1, &h->tmp2, &h->tmp3, &h->assign, &h->ws_best, &h->ws_arg, &h->d_flag,
                       &h->sub_keys, &h->sub_rows, &h->sub_keys_s, &h->sub_rows_s, &h->sub_bounds, &h->sub_len, &h->sub_off, &h->sub_skew,
                       &h->sub_glob, &h->sub_pre, &h->gen_keys, &h->gen_sorted, &h->gen_seg, &h->gen_cnt, &h->redo_idx, &h->redo_q,

@@ -230,7 +230,38 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
         ps_mbar_init(bar_done, PS_NC);
         ps_mbar_init(bar_done + 8, PS_NC);
     }
-    __syncthreads();  // (the only CTA-wide barrier of the kernel)
+    // The table of the CTA's FIRST query is built by all 12 warps (rows ks = wid, wid + 12, ...: 22 rows per warp instead
+    // of 256 for the producer alone) -- otherwise the consumers idle for a whole single-warp table build (~25 K cycles) at
+    // the start, 4 % of a batch of 1024 queries (7 per CTA).  Ds <= 4 only; other shapes leave it to the producer.
+    const bool first_coop = n_my > 0 && a.Ds <= 4;
+    int bad0 = 0;
+    if (first_coop) {
+        float *lut2 = reinterpret_cast<float *>(smem_raw + (PS_T0 - 0x400u));
+        const int m = lane;
+        if (m < Mr) {
+            const float *qm = a.Q + (size_t)blockIdx.x * Mr * a.Ds + (size_t)m * a.Ds;
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            q4.x = __ldg(qm);
+            if (a.Ds > 1) q4.y = __ldg(qm + 1);
+            if (a.Ds > 2) q4.z = __ldg(qm + 2);
+            if (a.Ds > 3) q4.w = __ldg(qm + 3);
+            const float2 qa = make_float2(q4.x, q4.y), qb = make_float2(q4.z, q4.w);
+            const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
+#pragma unroll 8
+            for (int ks = wid; ks < a.Ks; ks += PS_NC + 1) {
+                const float v = sqdist4(qa, qb, __ldg(cw4 + ks * Mr));
+                bad0 |= !(v <= ST_TABLE_LIMIT);
+                lut2[ks * 64 + m + 32] = v;
+                lut2[ks * 64 + m] = v;
+            }
+        } else {
+            for (int ks = wid; ks < a.Ks; ks += PS_NC + 1) {
+                lut2[ks * 64 + m + 32] = 0.f;
+                lut2[ks * 64 + m] = 0.f;
+            }
+        }
+    }
+    bad0 = __syncthreads_or(bad0);  // (the only CTA-wide barrier of the kernel; also publishes the mbarrier inits)
 
     if (wid < PS_NC) {
         // =========================================== consumers ===========================================
@@ -479,8 +510,8 @@ __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs
             PsKeys &kb = keyb[p];
             float *lut2 = reinterpret_cast<float *>(smem_raw + (PS_T0 - 0x400u) + p * SK_LUT_BYTES);
             // ---- K1 (src/rii.h:361-373): lane = sub-space, every ks; column c of the table holds sub-space c mod 32 ----
-            int bad = 0;
-            {
+            int bad = qi == 0 && first_coop ? bad0 : 0;
+            if (!(qi == 0 && first_coop)) {
                 const int m = lane;
                 const float *qm = a.Q + (size_t)b * Mr * a.Ds + (size_t)m * a.Ds;
                 if (m >= Mr) {

@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 int *ranked_g = a.plan.ranked + (size_t)b * a.w_eff;
                 for (int j = lane; j < a.w_eff; j += 32) {  // w_eff <= nlist, np >= w_eff
                     const int no = (int)key_id(selk[j]);
-                    ranked_g[j] = no;
+                    if (blockIdx.x == 0) ranked_g[j] = no;  // (every CTA of the query computes the same ranking)
                     s_f[j] = a.plan.glob_len[no];
                     s_pre[j] = a.plan.pre_len ? a.plan.pre_len[no] : 0;
                     s_loc[j] = a.plan.loc_len[no];
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                     s_prow[j] = a.skew_off[no];
                 }
                 __syncwarp();
-                const int jc = a.coarse_mode == 1 ? 0 : plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take);
+                const int jc = a.coarse_mode == 1 ? 0 : plan_warp(a.plan, b, lane, s_f, s_pre, s_loc, s_off, s_prow, s_gcum, s_take, blockIdx.x == 0);
                 if (lane == 0) {
                     s_plan[0] = jc;
                     *cta_thr = RII_KEY_MAX;
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             wt.ids = a.ids;
             wt.J = J;
             thr_hi = 0xffffffffu;
-            set_range(1, 0);  // (also resets the walk state: hb, drain_left, d_last0)
+            set_range(gridDim.x, blockIdx.x);  // this CTA's share of the planned groups (also resets the walk state: hb, drain_left, d_last0)
 #pragma unroll
             for (int s = 0; s < ST_R; ++s) dsc[s] = 0u;
             ST_ISSUE(0, dsc[0], 0 < nblk)
@@ -680,6 +680,37 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             for (int w2 = 0; w2 < NW; ++w2)
                 for (int i = threadIdx.x; i < s_cnt[w2]; i += blockDim.x) tk.push(allkeys[(size_t)w2 * capw + i]);
             emit_topk(tk, a.out, b, blockIdx.x, gridDim.x);
+        }
+    }
+    if (!a.out.final && a.out.merge_cnt) {
+        // several CTAs served this query: the last one to deliver its partial list merges them all (gridDim.x * k <= 256 keys;
+        // the host falls back to k_merge otherwise).  Classic last-block pattern: fence, count, the last arriver reads.
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(a.out.merge_cnt + b, 1) == (int)gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (s_last && wid == 0) {
+            __threadfence();
+            u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
+            const int tot = (int)gridDim.x * a.k;
+            const u64 *src = a.out.partial + (size_t)b * gridDim.x * a.k;
+            for (int i = lane; i < tot; i += 32) mk[i] = __ldcg(src + i);
+            warp_sort_any(mk, tot, lane);
+            int n = 0;
+            for (int i = lane; i < a.k; i += 32) {
+                const u64 key = mk[i];
+                if (key != RII_KEY_MAX) {
+                    a.out.out_ids[(size_t)b * a.k + i] = a.out.id_map ? a.out.id_map[key_id(key)] : a.out.id_base + (long long)key_id(key);
+                    a.out.out_dists[(size_t)b * a.k + i] = key_dist(key);
+                    ++n;
+                }
+            }
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (lane == 0) {
+                a.out.out_counts[b] = n;
+                a.out.merge_cnt[b] = 0;
+            }
         }
     }
     if (dbg && threadIdx.x == 0) dbg[3] = clock64();

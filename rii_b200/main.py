@@ -26,6 +26,8 @@ def _strict(a, dtype, ndim, name):
 class RiiCpp(object):
     def __init__(self, codewords=None, verbose=False, device=0, l2_variant=0):
         self._h = None
+        self._outs = {}
+        self._lib = _capi.lib()
         self._codewords = None
         self._device = device
         self._l2_variant = l2_variant
@@ -62,27 +64,37 @@ class RiiCpp(object):
             raise ValueError("codes must have shape (N, M)")
         check(_capi.lib().rii_add_codes(self._h, _ptr(codes, C.c_uint8), codes.shape[0], int(bool(update_flag))))
 
-    def query_linear(self, query, topk, target_ids):
+    def _out(self, topk):
+        """Result buffers of a single-query call, kept per topk with their ctypes pointers: a call is a few microseconds of
+        device work, so the wrapper must not spend more than that on allocations and pointer conversions."""
+        o = self._outs.get(topk)
+        if o is None:
+            ids, dists = np.empty(topk, np.int64), np.empty(topk, np.float32)
+            o = self._outs[topk] = (ids, dists, ids.ctypes.data, dists.ctypes.data)
+        return o
+
+    def _single(self, query, topk, target_ids, L, ivf):
         q = _strict(query, np.float32, 1, "query")
         t = _strict(target_ids, np.int64, 1, "target_ids")
         if q.shape[0] != self.M * self.Ds:
             raise ValueError("query must have M * Ds = %d elements" % (self.M * self.Ds))
-        ids = np.empty(int(topk), np.int64)
-        dists = np.empty(int(topk), np.float32)
-        n = check(_capi.lib().rii_query_linear(self._h, _ptr(q, C.c_float), int(topk), _ptr(t, C.c_int64), t.size,
-                                               _ptr(ids, C.c_int64), _ptr(dists, C.c_float)))
+        topk = int(topk)
+        ids, dists, pi, pd = self._out(topk)
+        pq, pt = q.ctypes.data, (t.ctypes.data if t.size else None)
+        lib = self._lib
+        if ivf:
+            n = lib.rii_query_ivf(self._h, pq, topk, pt, t.size, int(L), pi, pd)
+        else:
+            n = lib.rii_query_linear(self._h, pq, topk, pt, t.size, pi, pd)
+        if n < 0:
+            check(n)
         return ids[:n].tolist(), dists[:n].tolist()
 
+    def query_linear(self, query, topk, target_ids):
+        return self._single(query, topk, target_ids, 0, False)
+
     def query_ivf(self, query, topk, target_ids, L):
-        q = _strict(query, np.float32, 1, "query")
-        t = _strict(target_ids, np.int64, 1, "target_ids")
-        if q.shape[0] != self.M * self.Ds:
-            raise ValueError("query must have M * Ds = %d elements" % (self.M * self.Ds))
-        ids = np.empty(int(topk), np.int64)
-        dists = np.empty(int(topk), np.float32)
-        n = check(_capi.lib().rii_query_ivf(self._h, _ptr(q, C.c_float), int(topk), _ptr(t, C.c_int64), t.size, int(L),
-                                            _ptr(ids, C.c_int64), _ptr(dists, C.c_float)))
-        return ids[:n].tolist(), dists[:n].tolist()
+        return self._single(query, topk, target_ids, L, True)
 
     def clear(self):
         check(_capi.lib().rii_clear(self._h))
@@ -161,6 +173,8 @@ class RiiCpp(object):
         if len(t) not in (5, 7):
             raise RuntimeError("Invalid state when reading pickled item")
         self._h = None
+        self._outs = {}
+        self._lib = _capi.lib()
         self._device, self._l2_variant = (t[5], t[6]) if len(t) == 7 else (0, 0)
         self._create(np.asarray(t[0], np.float32), bool(t[1]))
         centers = np.ascontiguousarray(t[2], np.uint8).reshape(-1, self.M)

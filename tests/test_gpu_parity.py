@@ -368,6 +368,24 @@ def test_skew_kernel_small_ks_and_ties(sk):
             assert_same_result(r2[0], np.array(r2[1], np.float32), *O.query_linear(T, codes, topk), "ties")
 
 
+@pytest.mark.parametrize("N", [32767, 32768, 40000])
+def test_linear_auto_dispatch_boundary(N):
+    """The automatic choice between the natural-layout kernels (N < 32768) and the streaming engine (one launch: table, scan
+    and the merge by the last CTA) must not change a bit of the result on either side of the boundary."""
+    cw, codes, Q = synth(128, 32, 256, N, 3, seed=N)
+    e, e1 = engine(cw, codes), engine(cw, codes)
+    e1.set_option("scan_kernel", 1)
+    for q in Q:
+        T = O.dtable(q, cw, 16)
+        for topk in (1, 10, 100):
+            r, r1 = e.query_linear(q, topk, EMPTY), e1.query_linear(q, topk, EMPTY)
+            assert r == r1
+            assert_same_result(r[0], np.array(r[1], np.float32), *O.query_linear(T, codes, topk), "boundary N=%d k=%d" % (N, topk))
+    bi, bd, bc = e.query_batch(Q, 7, method="linear")
+    for b, q in enumerate(Q):
+        assert_same_result(bi[b], bd[b], *O.query_linear(O.dtable(q, cw, 16), codes, 7), "boundary batch")
+
+
 def test_skew_kernel_large_n_vs_v1():
     N = 5000000
     cw, codes, Q = synth(128, 32, 256, N, 3, seed=77)
