@@ -31,10 +31,10 @@ int stream_pick(int row_bytes, bool ivf, bool two_ctas, int capw, int w_eff, siz
     return 0;
 }
 
-template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H>
-static int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
+template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H, bool K1>
+static int launch_stream_k(SkewArgs a, int parts, int B, size_t smem, cudaStream_t st)
 {
-    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB, H>;
+    auto kern = k_scan_stream32<NW, IVF, R, MINB, TB, H, K1>;
     static bool configured[64] = {false};  // function attributes are per device: once per (instantiation, device)
     int dev = 0;
     CK(cudaGetDevice(&dev));
@@ -48,6 +48,14 @@ static int launch_stream_t(SkewArgs a, int parts, int B, size_t smem, cudaStream
     rii_count_launch();
     CK(cudaGetLastError());
     return 0;
+}
+
+template <int NW, bool IVF, int R, int MINB, uint32_t TB, int H>
+static int launch_stream_t(const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)
+{
+    // topk == 1 in a launch that produces results (not the coarse-only ranking launch, whose lists hold w_eff keys)
+    if (a.k == 1 && !(IVF && a.coarse_mode == 1)) return launch_stream_k<NW, IVF, R, MINB, TB, H, true>(a, parts, B, smem, st);
+    return launch_stream_k<NW, IVF, R, MINB, TB, H, false>(a, parts, B, smem, st);
 }
 
 int launch_stream(int shape, bool ivf, const SkewArgs &a, int parts, int B, size_t smem, cudaStream_t st)

@@ -228,7 +228,10 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
 
 // Args: SkewArgs (kernels.cuh) with `codes` = skew64 table of the pass-1 rows (linear: the codes by id, one segment;
 // IVF: every local posting list, segment i at physical row skew_off[i]) and `centers` = skew64 of the coarse centers.
-template <int NW, bool IVF, int ST_R, int MINB, uint32_t TB, int H>
+// K1: the topk == 1 instantiation -- in the final pass a warp keeps its best (distance, position) in warp-uniform registers
+// instead of pushing keys into its shared-memory list (no pushes, no compaction, ids looked up for the winner and for exact
+// cross-list ties only; same scheme as k_scan_persist32<true>).
+template <int NW, bool IVF, int ST_R, int MINB, uint32_t TB, int H, bool K1>
 __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 {
     static_assert(H == 1 || H == 2, "M = 32 or 64");
@@ -471,8 +474,42 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
     // position of the row `half` (0: x, 1: y) of flattened group f in this lane: the center's index (coarse pass), the id
     // (linear scan), or what warp_compact turns into an id (posting lists: WarpTopk lazy ids)
     auto row_id = [&](int f, int half) -> uint32_t { return (uint32_t)(f * 64 + half * 32 + lane); };
+    // K1: the warp's best so far (warp-uniform): distance bits, position, id (-1: not looked up yet), segment
+    uint32_t b_thr = 0xffffffffu, b_pos = 0u;
+    int b_id = -1, b_seg = -1;
+    bool b_have = false;
+    auto id_of = [&](uint32_t pos) -> uint32_t {  // position (flattened group << 6 | row) -> key id
+        if (!IVF) return pos;                      // linear scans: rows are ids
+        const int f = (int)(pos >> 6), j = seg_of(f);
+        const int r = (f - (j ? s_gcum[j - 1] : 0)) * 64 + (int)(pos & 63u);
+        return (uint32_t)__ldg(a.ids + s_off[j] + r);
+    };
     auto emit2 = [&](float dx, float dy, uint32_t d) {
         const int f = (int)(d >> 2);
+        if constexpr (K1) {
+            if (!pass0) {
+                const uint32_t ux = __float_as_uint(dx), uy = __float_as_uint(dy);
+                const bool px = (d & 1u) && ux <= b_thr, py = (d & 2u) && uy <= b_thr;
+                if (__any_sync(0xffffffffu, px || py)) {
+                    const uint32_t mine = umin(px ? ux : 0xffffffffu, py ? uy : 0xffffffffu);
+                    const uint32_t mn = __reduce_min_sync(0xffffffffu, mine);
+                    // the lowest position at that distance: x rows (row = lane) lie before y rows (row = 32 + lane)
+                    const unsigned bx = __ballot_sync(0xffffffffu, px && ux == mn), by = __ballot_sync(0xffffffffu, py && uy == mn);
+                    const uint32_t pos = ((uint32_t)f << 6) | (bx ? (uint32_t)(__ffs(bx) - 1) : 32u + (uint32_t)(__ffs(by) - 1));
+                    if (!b_have || mn < b_thr) {
+                        b_thr = mn; b_pos = pos; b_id = -1; b_seg = IVF ? seg_of(f) : 0; b_have = true;
+                    } else if (IVF) {  // an exact tie with the best so far (at a lower position): ids decide across posting lists
+                        const int sn = seg_of(f);
+                        if (sn != b_seg) {
+                            const int idn = (int)id_of(pos);
+                            if (b_id < 0) b_id = (int)id_of(b_pos);
+                            if (idn < b_id) { b_pos = pos; b_id = idn; b_seg = sn; }
+                        }
+                    }
+                }
+                return;
+            }
+        }
         if (IVF && direct) {  // coarse pass of the fused kernel: keep every distance (and their range, for the selection)
             const uint32_t ux = __float_as_uint(dx), uy = __float_as_uint(dy);
             if (d & 1u) { pool_d[f * 64 + lane] = ux; d_lo = ux < d_lo ? ux : d_lo; d_hi = ux > d_hi ? ux : d_hi; }
@@ -634,6 +671,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 atomicMin(reinterpret_cast<uint32_t *>(hist) + 256, d_lo);
                 atomicMax(reinterpret_cast<uint32_t *>(hist) + 257, d_hi);
             }
+        } else if (K1 && !pass0) {
+            if (b_have && b_id < 0) b_id = (int)id_of(b_pos);
+            if (lane == 0) wkeys[0] = ((u64)b_thr << 32) | (u64)(uint32_t)b_id;
+            wt.count = b_have ? 1 : 0;
+            __syncwarp();
         } else {
             warp_compact(wt, cta_thr, lane);
         }
