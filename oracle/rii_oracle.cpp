@@ -6,8 +6,8 @@
 //
 // Parity status: PINNED.  Every function below is checked bit-for-bit against the UNMODIFIED reference
 // compiled from /root/reference/src with "-O2 -ffp-contract=off" (oracle/_ref/strict_*; see
-// oracle/Makefile, tests/test_oracle_vs_ref.py) and against golden vectors generated from that build
-// (tests/golden/, generator: tests/golden/make_golden.py).
+// oracle/Makefile; tests/golden/make_golden.py drives it) and against golden vectors generated from that build
+// (tests/golden/*.npz, checked by tests/test_oracle_golden.py).
 //
 // All file:line citations are into /root/reference/ (matsui528/rii v0.2.12).  The arithmetic is the
 // reference's arithmetic *as written*: fp32, separate sub/mul/add (no FMA contraction, no

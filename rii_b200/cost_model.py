@@ -21,7 +21,7 @@ The constants are measurements on B200 (profiles/r02_*): see DESIGN.md section 4
 
 T_LAUNCH = 4.0e-6            # s per kernel launch on an idle stream (launch + drain)
 T_TABLE = 5.0e-6             # s: distance table build + merge of a query (K1, ~10 K cycles)
-LOOKUP_RATE = 4.0e12         # table lookups / s of the streaming engine (3.4 T fused IVF .. 5.5 T long linear scans)
+LOOKUP_RATE = 4.5e12         # table lookups / s of the streaming engine (4.7 T persistent IVF batches .. 5.1 T long linear scans)
 BUILD_BW = 2.5e12            # bytes / s of the gather / sort passes that build sub-indexes
 SUB_BYTES_PER_TARGET = 104   # keys 8 + 3 radix passes x 16 + row gather 32 + skew write 32 (M = 32)
 SUB_LAUNCHES = 10
@@ -42,14 +42,15 @@ class CostModel(object):
 
     def linear(self, S, subset, batch=1):
         """seconds per query of a linear scan over S candidates (S = N without target_ids)."""
-        t = 2 * T_LAUNCH + T_TABLE + S * self.rb / LOOKUP_RATE
+        t = T_LAUNCH + T_TABLE + S * self.rb / LOOKUP_RATE  # one launch: table + scan + merge by the last CTA
         if subset:
             t += (LIN_SUB_LAUNCHES * T_LAUNCH + S * (8 + 2 * self.rb) / BUILD_BW) / batch
         return t
 
     def ivf(self, L, S, subset, batch=1):
         """seconds per query of an inverted-index search that evaluates L candidates."""
-        t = (1 if batch >= 148 else 3) * T_LAUNCH + T_TABLE + (self.nlist + L) * self.rb / LOOKUP_RATE
+        # one fused launch (table, coarse pass, selection, plan, scan, merge) while every coarse distance fits shared memory
+        t = (1 if (batch >= 148 or self.nlist <= 1024) else 3) * T_LAUNCH + T_TABLE + (self.nlist + L) * self.rb / LOOKUP_RATE
         if subset:
             t += (SUB_LAUNCHES * T_LAUNCH + S * (SUB_BYTES_PER_TARGET - 64 + 2 * self.rb) / BUILD_BW) / batch
         return t

@@ -154,6 +154,9 @@ struct rii_index {
     // is launches + one stream synchronisation, no cudaMemcpy
     void *pin = nullptr;
     size_t pin_cap = 0;
+    // large host batches: chunked H2D copies on their own stream, overlapped with the search of the previous chunk
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     // OPQ rotation applied on the device before the table build (rii/rii.py:305-306): R (D, D) row-major, or null
     float *d_R = nullptr;
     DevBuf qrot;
@@ -1198,6 +1201,42 @@ int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tid
     CKR(h->o_ids.ensure((size_t)B * topk * 8));
     CKR(h->o_dists.ensure((size_t)B * topk * 4));
     CKR(h->o_counts.ensure((size_t)B * 4));
+    const int HC = 8192;  // queries per pipelined chunk of a large batch
+    if (S == 0 && B >= 2 * HC) {
+        // large batch: the queries travel in chunks on a copy stream while the previous chunk is searched (the H2D copy of a
+        // 32768-query step is 4.5 % of its search time when it is not overlapped); results come back in one copy at the end
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        // a small first chunk so that the search starts early, the rest in one piece (copied while the first chunk is searched)
+        const int c0 = 2048;
+        const int nch = 2;
+        while ((int)h->copy_events.size() < nch) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->copy_events.push_back(ev);
+        }
+        for (int c = 0; c < nch; ++c) {
+            const size_t o = c ? (size_t)c0 : 0, n = c ? (size_t)(B - c0) : (size_t)c0;
+            CK(cudaMemcpyAsync(h->q.as<float>() + o * D, Q + o * D, n * D * 4, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->copy_events[c], h->copy_stream));
+        }
+        int rc = 0;
+        for (int c = 0; c < nch && rc == 0; ++c) {
+            const size_t o = c ? (size_t)c0 : 0;
+            const int n = c ? B - c0 : c0;
+            if (cudaStreamWaitEvent(st, h->copy_events[c], 0) != cudaSuccess) { rc = fail(RII_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+            rc = query_dev(h, h->q.as<float>() + o * D, n, topk, nullptr, 0, L, method, h->o_ids.as<long long>() + o * topk,
+                           h->o_dists.as<float>() + o * topk, h->o_counts.as<int>() + o, st, -1);
+        }
+        if (rc < 0) {  // the copy stream may still be writing h->q: drain it before anyone reuses the buffer
+            cudaStreamSynchronize(h->copy_stream);
+            return rc;
+        }
+        CK(cudaMemcpyAsync(out_ids, h->o_ids.p, (size_t)B * topk * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_dists, h->o_dists.p, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_counts, h->o_counts.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
     CK(cudaMemcpyAsync(h->q.p, Q, (size_t)B * D * 4, cudaMemcpyHostToDevice, st));
     int tids_state = -1;
     if (S > 0) {
@@ -1279,6 +1318,8 @@ int rii_destroy(rii_index_t *h)
         b->release();
     if (h->sort_tmp.p) cudaFree(h->sort_tmp.p);
     if (h->pin) cudaFreeHost(h->pin);
+    for (cudaEvent_t ev : h->copy_events) cudaEventDestroy(ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d_R) cudaFree(h->d_R);
     h->qrot.release();
     if (h->d_cw) cudaFree(h->d_cw);

@@ -23,7 +23,11 @@
 // plus the drain block behind them, which is simply the next block in memory).  Inside a run the issue logic is a pointer
 // increment and a counter; segment tables are only read when a run starts (~5 times per query and warp).  (Bulk L2 prefetches
 // -- cp.async.bulk.prefetch.L2, UBLKPF -- running 8 blocks ahead of the cp.async front were measured on HBM-resident lists:
-// 0.463 vs 0.465 ms for the C5-shaped batch, i.e. nothing: the scan is bound on the SM side, not by memory latency.  Removed.)
+// 0.463 vs 0.465 ms for the C5-shaped batch, i.e. nothing: the scan is bound on the SM side, not by memory latency.  Removed.
+// Also measured and removed: OR-merging the drain block of a list with the first block of the next one (complementary zero
+// padding; consumed together, the second block's pipeline instance only refills the ring).  It saves 34 of a C2 query's 606
+// blocks, but the two extra warp-uniform branches per block and the shorter prefetch distance of merged blocks cost more:
+// 4.42 -> 4.24 M queries/s (tools/gpu_r2_x.sh).)
 //
 // topk == 1 (the recall@1 operating point of every BASELINE config) has its own instantiation: a warp keeps its best
 // (distance, position) in two warp-uniform registers -- no key buffers, no compaction, no shared-memory traffic; a group

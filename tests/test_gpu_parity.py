@@ -1039,6 +1039,23 @@ def test_persistent_batch_kernel_exact_ties_across_lists():
             n = int(f[2][b])
             assert_same_result(f[0][b][:n], f[1][b][:n], exp[0], exp[1], "persist ties k=%d L=%d b=%d" % (topk, L, b))
 
+def test_large_host_batch_is_pipelined_in_chunks():
+    """rii_query_batch with >= 16384 host queries copies them in chunks on a second stream while the previous chunk is
+    searched: the results must equal those of separate smaller calls, bit for bit (also across the chunk boundaries)."""
+    cw, codes, Q = synth(128, 32, 256, 60000, 50, seed=5)
+    e = engine(cw, codes)
+    e.reconfigure(100, 1)
+    B = 8192 * 2 + 1234
+    Qb = np.ascontiguousarray(np.tile(Q, (B // len(Q) + 1, 1))[:B] + np.float32(1e-4) * (np.arange(B, dtype=np.float32) % 977)[:, None])
+    for topk, L, method in [(1, 3000, "ivf"), (3, 3000, "ivf")]:
+        big = e.query_batch(Qb, topk, L=L, method=method)
+        for s0 in (0, 8192 - 100, 16384 - 50, B - 300):
+            small = e.query_batch(np.ascontiguousarray(Qb[s0:s0 + 300]), topk, L=L, method=method)
+            n = min(300, B - s0)
+            assert np.array_equal(big[0][s0:s0 + n], small[0][:n]) and np.array_equal(bits(big[1][s0:s0 + n]), bits(small[1][:n]))
+            assert np.array_equal(big[2][s0:s0 + n], small[2][:n])
+
+
 def test_opq_rotation_on_the_device_and_small_call_path():
     """(1) rii/rii.py:305-306: the OPQ rotation of the query folded into the engine (k_rotate, fp32 FMA chain) returns the
     ids of the host rotation and distances within the 1e-5 relative contract; it survives pickling.  (2) single calls
