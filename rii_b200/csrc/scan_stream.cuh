@@ -132,36 +132,30 @@ __device__ __forceinline__ int plan_warp(const PlanArgs &p, int b, int lane, con
 
 #define ST_LDS128(W, A)                                                                                       \
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"((W)[0]), "=r"((W)[1]), "=r"((W)[2]), "=r"((W)[3]) : "r"(A))
-// issue the copy of the next block of this warp's walk (data block or drain block) into ring stage S and describe
-// it: D = flattened group << 2 | y row valid << 1 | x row valid   (0 for a drain block).  Past the end of the walk
-// only an (empty) group is committed, so that "wait_group ST_D" always means "the block of this stage has landed".
+// issue the copy of the next block of this warp's walk into ring stage S and describe it: D = flattened group << 2 | y row
+// valid << 1 | x row valid for the first block of a group, 0 for its other half (H = 2) and for drain blocks.  The walk is a
+// list of RUNS -- the consecutive blocks of one segment inside the warp's slice plus the H drain blocks behind them (the next
+// blocks in memory): inside a run the logic is a pointer increment and a counter, segment tables are read by next_run() only.
+// Warp-uniform state: run_left (blocks left in the run, drain blocks included), bp (this lane's 16-byte column of the next
+// block), cur_f, hb, last_bits (valid bits of the run's last group).  Past the end of the walk only an (empty) group is
+// committed, so that "wait_group ST_D" always means "the block of this stage has landed".
 #define ST_ISSUE(S, D, ACTIVE)                                                                                \
     {                                                                                                         \
         if (ACTIVE) {                                                                                         \
-            const int g_ = cur_f - seg_g0;                                                                    \
-            const long long prow_ = seg_prow; /* (load_seg below may move on to the next segment) */          \
-            int blk_;                                                                                         \
-            if (drain_left == 0) { /* block hb of group cur_f; the group's descriptor travels with its first block */ \
-                const int hb_ = H == 1 ? 0 : hb;                                                              \
-                blk_ = g_ * H + hb_;                                                                          \
-                const int r_ = g_ * 64 + lane;                                                                \
-                D = hb_ ? 0u : (((uint32_t)cur_f << 2) | (r_ < seg_take ? 1u : 0u) | (r_ + 32 < seg_take ? 2u : 0u)); \
-                if (H == 1 || ++hb == H) {                                                                    \
-                    hb = 0;                                                                                   \
-                    ++cur_f;                                                                                  \
-                    if (cur_f == f_end || cur_f == seg_gend) drain_left = H;                                  \
-                }                                                                                             \
-            } else { /* the H blocks after the segment's (or the range's) last group: only the lagging bytes of the first matter */ \
-                blk_ = g_ * H + (H - drain_left);                                                             \
-                D = 0u;                                                                                       \
-                if (--drain_left == 0 && cur_f < f_end) load_seg(seg + 1);                                    \
+            if (run_left == 0) next_run();                                                                    \
+            if (run_left <= H) D = 0u; /* drain */                                                            \
+            else if (H == 2 && hb) { D = 0u; hb = 0; ++cur_f; }                                               \
+            else {                                                                                            \
+                D = ((uint32_t)cur_f << 2) | (run_left <= 2 * H ? last_bits : 3u);                            \
+                if (H == 1) ++cur_f; else hb = 1;                                                             \
             }                                                                                                 \
-            const uint8_t *p_ = pc + (size_t)prow_ * 32 + (size_t)blk_ * ST_BLOCK_BYTES + lane * 16;          \
             const uint32_t dst_ = ring + (S) * ST_BLOCK_BYTES;                                                \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_), "l"(p_));                   \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 512), "l"(p_ + 512));       \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1024), "l"(p_ + 1024));     \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1536), "l"(p_ + 1536));     \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_), "l"(bp));                   \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 512), "l"(bp + 512));       \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1024), "l"(bp + 1024));     \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_ + 1536), "l"(bp + 1536));     \
+            bp += ST_BLOCK_BYTES;                                                                             \
+            --run_left;                                                                                       \
         }                                                                                                     \
         asm volatile("cp.async.commit_group;");                                                               \
     }
@@ -322,10 +316,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
 
     // per-pass state (warp-uniform)
     const uint8_t *pc = fused ? a.centers : a.codes;  // skew64 table of the pass
-    int f0 = 0, f_end = 0, cur_f = 0, nblk = 0, hb = 0, drain_left = 0;
+    int f0 = 0, f_end = 0, cur_f = 0, nblk = 0, hb = 0, run_left = 0;
+    uint32_t last_bits = 3u;
+    const uint8_t *bp = pc;
     uint32_t d_last0 = 0u;  // descriptor of the group whose rows complete in the next first-half block
-    int seg = 0, seg_g0 = 0, seg_gend = 0, seg_take = 0;
-    long long seg_prow = 0;
+    int seg = 0, seg_g0 = 0, seg_gend = 0;
     WarpTopk wt;
     wt.keys = wkeys;
     wt.cap = next_pow2(a.k + 32) < 64 ? 64 : next_pow2(a.k + 32);
@@ -358,8 +353,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         seg = j;
         seg_g0 = j ? s_gcum[j - 1] : 0;
         seg_gend = s_gcum[j];
-        seg_take = s_take[j];
-        seg_prow = s_prow[j];
+    };
+    auto next_run = [&]() {  // (warp-uniform; cur_f < f_end)
+        if (cur_f == seg_gend) load_seg(seg + 1);
+        const int end = seg_gend < f_end ? seg_gend : f_end;
+        run_left = (end - cur_f + 1) * H;  // + the drain blocks: the next blocks in memory
+        bp = pc + (size_t)s_prow[seg] * 32 + (size_t)(cur_f - seg_g0) * H * ST_BLOCK_BYTES + lane * 16;
+        int tail = 64;
+        if (end == seg_gend) tail = s_take[seg] - (seg_gend - seg_g0 - 1) * 64;  // rows of the segment's last group
+        last_bits = (lane < tail ? 1u : 0u) | (lane + 32 < tail ? 2u : 0u);
     };
     auto set_range = [&](int nsplit, int split) {  // this warp's slice [f0, f_end) of the pass's groups
         const int G = J ? s_gcum[J - 1] : 0;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         f_end = f0 + per < G ? f0 + per : G;
         cur_f = f0;
         hb = 0;
-        drain_left = 0;
+        run_left = 0;
         d_last0 = 0u;
         nblk = 0;
         if (f_end > f0) {
