@@ -214,4 +214,6 @@ struct SkewArgs {
     PlanArgs plan;             // IVF fused: plan inputs (lengths, L, topk, w) and its global outputs (ranked, J, flags)
     TopkOut out;
     long long *dbg;            // optional: per-CTA clock64() at [start, table ready, scan done, end] (tools/microbench.py)
+    int q_inline;              // single host call with D <= 128, Ds <= 4: the query vector travels in the kernel parameters (qv) --
+    float qv[128];             //   the launch carries it, no read of the pinned host buffer over PCIe before the table build can start
 };

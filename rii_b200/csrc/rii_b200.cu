@@ -139,6 +139,7 @@ struct rii_index {
     std::vector<long long> len_sorted_prefix;  // prefix sums of ascending *global* list lengths
 
     // scratch (grow only)
+    const float *q_host = nullptr;  // set by query_host around a single zero-copy call: the query also travels in the kernel parameters
     DevBuf merge_cnt;   // (B) per-query arrival counters of the in-kernel merge (zero between launches)
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
         tmp2, tmp3;
@@ -725,6 +726,10 @@ int run_linear(rii_index *h, const float *d_Q, int B, int topk, const long long 
         SkewArgs sa{};
         sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
         sa.Ks = Ks; sa.k = topk; sa.cap = capw;
+        if (h->q_host && B == 1 && M * h->Ds <= 128 && h->Ds <= 4 && !h->d_R) {
+            sa.q_inline = 1;
+            std::memcpy(sa.qv, h->q_host, (size_t)M * h->Ds * 4);
+        }
         if (S) {  // compact skew64 copy of the target rows (in the given order; repeated ids stay repeated, src/rii.h:222-227)
             if (cnt <= 0) {  // nothing of the subset lives in this shard
                 CK(cudaMemsetAsync(d_out_counts, 0, (size_t)B * 4, st));
@@ -970,6 +975,10 @@ int run_ivf(rii_index *h, const float *d_Q, int B, int topk, long long L, const 
         sa.Q = d_Q; sa.cw = h->d_cw; sa.cw_t = h->d_cw_t; sa.Ds = h->Ds; sa.variant = h->variant; sa.M = M;
         sa.codes = v.skew; sa.offsets = v.offsets; sa.ids = v.ids; sa.skew_off = v.skew_off;
         sa.w_eff = w_eff; sa.Ks = Ks; sa.k = topk; sa.nlist = nlist; sa.plan = p;
+        if (h->q_host && B == 1 && M * h->Ds <= 128 && h->Ds <= 4 && !h->d_R) {
+            sa.q_inline = 1;
+            std::memcpy(sa.qv, h->q_host, (size_t)M * h->Ds * 4);
+        }
         if (fuse || mode == 1 || mode == 0) CKR(ensure_centers_skew(h, st));
         // batches of independent queries: the persistent warp-specialised kernel (scan_persist.cuh) when the shape fits
         const bool pers_shape = persist_fits(h->rb, topk, w_eff, nlist, mode == 0) && (mode == 2 || (mode == 0 && h->opt_fuse_coarse));
@@ -1190,7 +1199,10 @@ int query_host(rii_index *h, const float *Q, int B, int topk, const int64_t *tid
         CK(cudaHostGetDevicePointer((void **)&dp, h->pin, 0));
         std::memcpy(hp + oq, Q, (size_t)B * D * 4);
         std::memset(hp + oc, 0, (size_t)B * 4);
-        CKR(query_dev(h, (const float *)(dp + oq), B, topk, nullptr, 0, L, method, (long long *)(dp + oi), (float *)(dp + od), (int *)(dp + oc), st, -1));
+        h->q_host = B == 1 ? Q : nullptr;
+        const int rc_ = query_dev(h, (const float *)(dp + oq), B, topk, nullptr, 0, L, method, (long long *)(dp + oi), (float *)(dp + od), (int *)(dp + oc), st, -1);
+        h->q_host = nullptr;
+        CKR(rc_);
         CK(cudaStreamSynchronize(st));
         std::memcpy(out_ids, hp + oi, (size_t)B * topk * 8);
         std::memcpy(out_dists, hp + od, (size_t)B * topk * 4);

@@ -434,10 +434,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
                 } else if (a.Ds <= 4) {  // every BASELINE shape: the codeword copy is padded to 4 floats (zeros add +0: same sum), 16
                                          // independent 16-byte loads in flight per lane
                     float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    q4.x = __ldg(qm);
-                    if (a.Ds > 1) q4.y = __ldg(qm + 1);
-                    if (a.Ds > 2) q4.z = __ldg(qm + 2);
-                    if (a.Ds > 3) q4.w = __ldg(qm + 3);
+                    if (a.q_inline) {  // (one query, b == 0)
+                        q4.x = a.qv[m * a.Ds];
+                        if (a.Ds > 1) q4.y = a.qv[m * a.Ds + 1];
+                        if (a.Ds > 2) q4.z = a.qv[m * a.Ds + 2];
+                        if (a.Ds > 3) q4.w = a.qv[m * a.Ds + 3];
+                    } else {
+                        q4.x = __ldg(qm);
+                        if (a.Ds > 1) q4.y = __ldg(qm + 1);
+                        if (a.Ds > 2) q4.z = __ldg(qm + 2);
+                        if (a.Ds > 3) q4.w = __ldg(qm + 3);
+                    }
                     const float4 *cw4 = reinterpret_cast<const float4 *>(a.cw_t) + m;
 #pragma unroll 16
                     for (int i = wid; i < 256; i += NW) {
@@ -690,7 +697,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
         int tot = 0;
         for (int w2 = 0; w2 < NW; ++w2) tot += s_cnt[w2];
         const u64 *allkeys = reinterpret_cast<const u64 *>(smem_raw);
-        if (tot <= 256) {
+        if (K1 && NW <= 32) {
+            // topk == 1: every warp holds at most one key -- a warp minimum under (distance, id), no sort
+            if (wid == 0) {
+                u64 key = lane < NW && s_cnt[lane] ? allkeys[(size_t)lane * capw] : RII_KEY_MAX;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const u64 y = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = y < key ? y : key;
+                }
+                if (lane == 0) {
+                    if (a.out.final) {
+                        if (key != RII_KEY_MAX) {
+                            a.out.out_ids[b] = a.out.id_map ? a.out.id_map[key_id(key)] : a.out.id_base + (long long)key_id(key);
+                            a.out.out_dists[b] = key_dist(key);
+                        }
+                        a.out.out_counts[b] = key != RII_KEY_MAX ? 1 : 0;
+                    } else {
+                        a.out.partial[(size_t)b * gridDim.x + blockIdx.x] = key;
+                    }
+                }
+            }
+        } else if (tot <= 256) {
             // small (the usual topk <= 16 case): one warp gathers and bitonic-sorts <= 256 keys with warp barriers only
             if (wid == 0) {
                 u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
@@ -739,8 +767,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_scan_stream32(SkewArgs a)
             u64 *mk = reinterpret_cast<u64 *>(smem_raw + lut_off);
             const int tot = (int)gridDim.x * a.k;
             const u64 *src = a.out.partial + (size_t)b * gridDim.x * a.k;
-            for (int i = lane; i < tot; i += 32) mk[i] = __ldcg(src + i);
-            warp_sort_any(mk, tot, lane);
+            if (K1) {  // one key per CTA: a warp minimum
+                u64 key = RII_KEY_MAX;
+                for (int i = lane; i < tot; i += 32) {
+                    const u64 y = __ldcg(src + i);
+                    key = y < key ? y : key;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const u64 y = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = y < key ? y : key;
+                }
+                if (lane == 0) mk[0] = key;
+                __syncwarp();
+            } else {
+                for (int i = lane; i < tot; i += 32) mk[i] = __ldcg(src + i);
+                warp_sort_any(mk, tot, lane);
+            }
             int n = 0;
             for (int i = lane; i < a.k; i += 32) {
                 const u64 key = mk[i];

@@ -87,6 +87,7 @@ static __device__ __noinline__ void warp_sort_any(u64 *keys, int n, int lane)  /
 static __device__ __noinline__ void warp_compact(WarpTopk &w, u64 *cta_thr, int lane)
 {
     const int n = w.count;  // <= cap <= 256
+    __syncwarp();  // the keys were written by other lanes of this warp (warp_push): order them before the reads below
     if (w.ids) {  // positions -> ids for everything pushed since the last compaction
         for (int e = w.nres + lane; e < n; e += 32) {
             const u64 key = w.keys[e];

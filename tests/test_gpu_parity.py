@@ -1056,6 +1056,42 @@ def test_large_host_batch_is_pipelined_in_chunks():
             assert np.array_equal(big[2][s0:s0 + n], small[2][:n])
 
 
+def test_randomised_shapes_against_the_oracle():
+    """40 random (M, Ks, N, nlist, batch, topk, L) draws through the automatic dispatch: every combination of engine
+    (persistent / fused multi-CTA with the merge by the last CTA / k_merge / natural layout / general path), batch size and
+    top-k mode (topk = 1 instantiations, warp lists) must agree with the oracle bit for bit."""
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        M = int(rng.choice([8, 16, 20, 32, 32, 32, 48, 64]))
+        Ds = int(rng.choice([1, 2, 4]))
+        Ks = int(rng.choice([16, 64, 256, 256]))
+        N = int(rng.choice([3000, 40000, 90000]))
+        nlist = int(rng.choice([7, 60, 300]))
+        B = int(rng.choice([1, 2, 5, 40, 150, 310]))
+        topk = int(rng.choice([1, 1, 1, 2, 9, 33]))
+        L = int(rng.choice([topk, 500, 5000, N]))
+        L = max(topk, min(L, N))
+        cw, codes, Q = synth(M * Ds, M, Ks, N, 16, seed=1000 + trial)
+        if trial % 5 == 0:
+            codes[:, 3:] = 0  # exact ties
+        e = engine(cw, codes)
+        e.reconfigure(nlist, 1)
+        centers = e.coarse_centers_array()
+        offsets, ids = e.posting_lists_csr()
+        Qb = np.ascontiguousarray(np.tile(Q, (B // len(Q) + 1, 1))[:B])
+        what = "trial %d: M=%d Ds=%d Ks=%d N=%d nlist=%d B=%d topk=%d L=%d" % (trial, M, Ds, Ks, N, nlist, B, topk, L)
+        gi, gd, gc = e.query_batch(Qb, topk, L=L, method="ivf")
+        li, ld, lc = e.query_batch(Qb, topk, method="linear")
+        for b in sorted(set([0, B // 2, B - 1])):
+            T = O.dtable(Qb[b], cw, 16)
+            exp = O.query_ivf(T, codes, centers, offsets, ids, topk, L)
+            n = int(gc[b])
+            assert_same_result(gi[b][:n], gd[b][:n], exp[0], exp[1], what + " ivf b=%d" % b)
+            exp = O.query_linear(T, codes, topk)
+            assert int(lc[b]) == topk
+            assert_same_result(li[b], ld[b], exp[0], exp[1], what + " linear b=%d" % b)
+
+
 def test_opq_rotation_on_the_device_and_small_call_path():
     """(1) rii/rii.py:305-306: the OPQ rotation of the query folded into the engine (k_rotate, fp32 FMA chain) returns the
     ids of the host rotation and distances within the 1e-5 relative contract; it survives pickling.  (2) single calls
