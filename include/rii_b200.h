@@ -73,7 +73,8 @@ int rii_query_batch(rii_index_t *h, const float *queries, int B, int topk, const
                     int64_t L, int method, int64_t *out_ids, float *out_dists, int32_t *out_counts);
 /* Same with DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = the CUDA default stream) and not
  * synchronised unless the rare full-ranking re-run (walk beyond w) is needed.  The handle's scratch
- * buffers are shared: one call in flight per handle.
+ * buffers are shared: one call in flight per handle (calls on different streams must be ordered by the caller; the
+ * derived code layouts a call builds lazily are guarded by an event, so a later call on another stream waits for them).
  * d_target_ids: device int64 (S) or NULL. */
 int rii_query_batch_dev(rii_index_t *h, const float *d_queries, int B, int topk, const int64_t *d_target_ids,
                         int64_t S, int64_t L, int method, int64_t *d_out_ids, float *d_out_dists,

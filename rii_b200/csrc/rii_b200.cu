@@ -139,6 +139,11 @@ struct rii_index {
     std::vector<long long> len_sorted_prefix;  // prefix sums of ascending *global* list lengths
 
     // scratch (grow only)
+    // derived layouts (skew64 copies) are built lazily on the stream of the query that first needs them; a later query on
+    // ANOTHER stream must not read them before that build has finished: the build records this event, other streams wait on it
+    cudaEvent_t built_ev = nullptr;
+    cudaStream_t built_on = nullptr;
+    bool built_pending = false;
     const float *q_host = nullptr;  // set by query_host around a single zero-copy call: the query also travels in the kernel parameters
     DevBuf merge_cnt;   // (B) per-query arrival counters of the in-kernel merge (zero between launches)
     DevBuf T, partial, ranked, cum, take_last, J, flags, filt, bitmap, q, tids, o_ids, o_dists, o_counts, tmp0, tmp1,
@@ -260,6 +265,15 @@ struct AssignSrc {
     const uint8_t *skew = nullptr;  // null: natural-layout kernel only
     long long n = 0;
 };
+
+int note_build(rii_index *h, cudaStream_t st)  // a derived layout was (re)built on `st`
+{
+    if (!h->built_ev) CK(cudaEventCreateWithFlags(&h->built_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->built_ev, st));
+    h->built_on = st;
+    h->built_pending = true;
+    return 0;
+}
 
 int ensure_skew_lin(rii_index *h, cudaStream_t st);
 int skew_build(const uint8_t *codes, const int *ids, const long long *offsets, const long long *d_skew_off, int nseg, long long n_single,
@@ -545,7 +559,7 @@ int ensure_skew_lin(rii_index *h, cudaStream_t st)  // skew64 of the codes by id
     LAUNCHED();
     CK(cudaGetLastError());
     h->skew_lin_rows = h->N;
-    return 0;
+    return note_build(h, st);
 }
 
 int ensure_centers_skew(rii_index *h, cudaStream_t st)  // skew64 of the coarse centers (fused coarse pass)
@@ -559,7 +573,7 @@ int ensure_centers_skew(rii_index *h, cudaStream_t st)  // skew64 of the coarse 
     CKR(skew_build(h->centers.as<uint8_t>(), nullptr, nullptr, h->skew_misc_off.as<long long>() + 2, 1, h->nlist, prows,
                    h->centers_skew.as<uint8_t>(), h->M, h->rb, st));
     h->centers_skew_valid = true;
-    return 0;
+    return note_build(h, st);
 }
 
 int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local posting list
@@ -574,7 +588,7 @@ int ensure_skew_lists(rii_index *h, cudaStream_t st)  // skew64 of every local p
     CKR(skew_build(h->d_codes, h->ids.as<int>(), h->offsets.as<long long>(), h->skew_off.as<long long>(), nlist, 0, off[nlist],
                    h->skew_lists.as<uint8_t>(), h->M, h->rb, st));
     h->skew_lists_valid = true;
-    return 0;
+    return note_build(h, st);
 }
 
 // ---- the query pipeline on device buffers -----------------------------------------------------------
@@ -1129,6 +1143,7 @@ int query_dev(rii_index *h, const float *d_Q, int B, int topk, const long long *
     if (h->N <= 0 && h->n_total() <= 0) return fail(RII_ERR_STATE, "query on an empty index");
     if (topk < 1) return fail(RII_ERR_ARG, "topk must be >= 1");
     if (h->shard_stale) return fail(RII_ERR_STATE, "codes were added to / cleared from this shard: call rii_set_shard (and rii_set_global_lengths) again");
+    if (h->built_pending && h->built_on != st) CK(cudaStreamWaitEvent(st, h->built_ev, 0));  // (lazy builds of an earlier query on another stream)
     const long long Ntot = h->n_total();
     if (S < 0 || S > Ntot) return fail(RII_ERR_ARG, "need 0 <= len(target_ids) <= N");            // src/rii.h:220
     if ((long long)topk > (S ? S : Ntot)) return fail(RII_ERR_ARG, "need topk <= N (and topk <= len(target_ids))");  // :200,:219
@@ -1331,6 +1346,7 @@ int rii_destroy(rii_index_t *h)
     if (h->sort_tmp.p) cudaFree(h->sort_tmp.p);
     if (h->pin) cudaFreeHost(h->pin);
     for (cudaEvent_t ev : h->copy_events) cudaEventDestroy(ev);
+    if (h->built_ev) cudaEventDestroy(h->built_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d_R) cudaFree(h->d_R);
     h->qrot.release();
