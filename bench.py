@@ -16,7 +16,9 @@ scan -> top-k).
 
 Multi-GPU (torchrun, one rank per GPU), total work per step fixed -> "strong":
   default  : N = 1M fits every GPU many times over, so the index is REPLICATED and each rank answers B/G of the step's
-             queries; the per-rank results are all-gathered over NCCL so that every rank holds the whole batch.
+             queries and returns their results (independent units: no exchange step, no collective).  The same steps with
+             one packed NCCL all-gather (every rank holds the whole batch; --gather) are measured beside the headline.
+             The sharded C5 / C4 legs (`sharded_large`) are where the path has real exchange steps.
   --shard  : the index is partitioned by contiguous id range (what C4/C5-sized indexes need): every rank
              scans its shard for every query, per-shard top-k are all-gathered and merged (k_merge_shards).  At
              N = 1M this divides only the scan, not the per-query table / coarse work: measured in profiles/.
@@ -400,27 +402,26 @@ def run_ours(args):
     f_c = torch.empty((B,), dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def finish_step():
-        """After this rank's results are in po.buf: the one collective of the step, and what the caller reads."""
-        if world == 1:
+    # Replicas (the default for the metric's N = 1M): every rank answers ITS B / world queries and keeps the results -- the
+    # queries are independent units, there is no exchange step on this path, so no collective is timed (--gather adds the
+    # packed all-gather that makes every rank hold the whole batch; it is also measured once, beside the headline).
+    # Shards: the per-shard top-k MUST be exchanged: one packed all-gather + merge.
+    def finish_step(gather):
+        """After this rank's results are in po.buf: the collective of the step (if any), and what the caller reads."""
+        if world == 1 or (not shard and not gather):
             return po.ids
         dist.all_gather_into_tensor(po.gathered.view(-1), po.buf)
         if not shard:  # replicas: rank r answered queries [r * Bl, (r + 1) * Bl): every rank now holds all of them
-            return None
+            return po.ids
         _capi.check(lib.rii_merge_shards_packed_dev(e._h, _ptr(po.gathered), po.nbytes, world, B, k, _ptr(f_ids), _ptr(f_d), _ptr(f_c), sp))
         return f_ids
 
-    def step_dev(i):
+    def step_dev(i, gather=None):
         q = dQ[(i % (nq // B)) * B:(i % (nq // B) + 1) * B]
         if world > 1 and not shard:
             q = q[rank * Bl:(rank + 1) * Bl]
         _capi.check(lib.rii_query_batch_dev(e._h, _ptr(q), Bl, k, None, 0, L, 1, _ptr(po.ids), _ptr(po.d), _ptr(po.c), sp))
-        return finish_step()
-
-    def all_ids(ret):
-        if ret is not None:
-            return ret.clone()
-        return torch.cat([po.rank_ids(torch, r) for r in range(world)]).clone()
+        return finish_step(bool(args.gather) if gather is None else gather)
 
     def barrier():
         if world > 1:
@@ -446,7 +447,7 @@ def run_ours(args):
         b.record(st)
         evs.append((a, b))
         if i < nq // B:
-            got.append((W + i, all_ids(ret)))
+            got.append((W + i, ret.clone()))  # this rank's answers (replicas: its slice of the step; shards / 1 GPU: the whole step)
     barrier()
     launches = lib.rii_launch_count() - launches0
     sampler.stop_flag = True
@@ -455,7 +456,27 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # replicas: the same K steps once more WITH (default run) / WITHOUT (--gather run) the packed all-gather of the results
+    no_gather = None
+    if world > 1 and not shard:
+        other = not bool(args.gather)
+        evs2 = []
+        for i in range(K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            step_dev(W + i, gather=other)
+            b.record(st)
+            evs2.append((a, b))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        no_gather = {"all_gather": other, "queries_per_s": round(K * B / (float(t.item()) * 1e-3), 1), "ms_per_step": round(float(t.item()) / K, 4),
+                     "note": ("the same steps with one packed NCCL all-gather (ids | dists | counts) after the search, so that every rank holds "
+                              "the whole batch's results" if other else "the same steps without the all-gather") + "; max over ranks"}
     scan_ms, scan_n = kernel_ms(lib, e, "scan_ivf")
+    scan_n = scan_n if no_gather is None else scan_n // 2  # (the profile saw both loops; per-launch time is the same)
+    scan_ms = scan_ms if no_gather is None else scan_ms / 2
     prof = {}
     for name in ("dtable", "coarse_rank", "scan_ivf", "merge"):
         m_, n_ = kernel_ms(lib, e, name)
@@ -466,9 +487,14 @@ def run_ours(args):
     # recall@1 (examples/benchmark/util.py:35-58) of what the timed steps returned
     hit = tot = 0
     for i, ids in got:
-        s = (i % (nq // B)) * B
-        hit += int((ids[:, 0].cpu().numpy() == gt[s:s + B]).sum())
-        tot += B
+        s = (i % (nq // B)) * B + (rank * Bl if (world > 1 and not shard) else 0)
+        n_ = ids.shape[0]
+        hit += int((ids[:, 0].cpu().numpy() == gt[s:s + n_]).sum())
+        tot += n_
+    if world > 1 and not shard:
+        t = torch.tensor([hit, tot], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        hit, tot = float(t[0].item()), float(t[1].item())
     recall = hit / max(tot, 1)
 
     # ---- end-to-end arm: host (pinned) buffers.  1 GPU: the reference-facing C-ABI call rii_query_batch (H2D of the queries
@@ -490,23 +516,38 @@ def run_ours(args):
     else:
         dq_l = torch.empty((Bl, D), dtype=torch.float32, device=dev)
         h_all = torch.empty((world, po.nbytes), dtype=torch.uint8).pin_memory()
+        h_own = torch.empty((po.nbytes,), dtype=torch.uint8).pin_memory()
         h_fin = torch.empty((B * k * 12 + B * 4,), dtype=torch.uint8).pin_memory()
+
+        hl_ids = torch.empty((Bl, k), dtype=torch.int64).pin_memory()
+        hl_d = torch.empty((Bl, k), dtype=torch.float32).pin_memory()
+        hl_c = torch.empty((Bl,), dtype=torch.int32).pin_memory()
 
         def step_host(i):
             q = hQ[(i % (nq // B)) * B:(i % (nq // B) + 1) * B]
             if not shard:
                 q = q[rank * Bl:(rank + 1) * Bl]
+            if not shard and not args.gather:
+                # replicas without a collective: exactly the 1-GPU end-to-end path, per rank -- the reference-facing C-ABI call with
+                # host buffers (H2D of this rank's queries, chunk-pipelined inside the call, and D2H of their results)
+                _capi.check(lib.rii_query_batch(e._h, C.cast(q.data_ptr(), C.POINTER(C.c_float)), Bl, k, None, 0, L, 1,
+                                                C.cast(hl_ids.data_ptr(), C.POINTER(C.c_int64)),
+                                                C.cast(hl_d.data_ptr(), C.POINTER(C.c_float)),
+                                                C.cast(hl_c.data_ptr(), C.POINTER(C.c_int32))))
+                return
             dq_l.copy_(q, non_blocking=True)
             _capi.check(lib.rii_query_batch_dev(e._h, _ptr(dq_l), Bl, k, None, 0, L, 1, _ptr(po.ids), _ptr(po.d), _ptr(po.c), sp))
-            ret = finish_step()
-            if ret is None:
+            ret = finish_step(bool(args.gather))
+            if not shard and args.gather:
                 h_all.copy_(po.gathered, non_blocking=True)
+            elif not shard:
+                h_own.copy_(po.buf, non_blocking=True)  # this rank's results
             else:
                 h_fin[:B * k * 8].copy_(f_ids.view(-1).view(torch.uint8), non_blocking=True)
                 h_fin[B * k * 8:B * k * 12].copy_(f_d.view(-1).view(torch.uint8), non_blocking=True)
                 h_fin[B * k * 12:].copy_(f_c.view(torch.uint8), non_blocking=True)
             st.synchronize()
-        h2d, d2h = Bl * D * 4, (world * po.nbytes if not shard else B * k * 12 + B * 4)
+        h2d, d2h = Bl * D * 4, ((world * po.nbytes if args.gather else Bl * k * 12 + Bl * 4) if not shard else B * k * 12 + B * 4)
     for i in range(W):
         step_host(i)
     barrier()
@@ -520,7 +561,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e = {"value": round(K * B / dt, 1), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "note": "per rank" if world > 1 else "rii_query_batch (C ABI, host buffers)"}
+           "note": ("per rank; rii_query_batch (C ABI, host buffers) on every rank" if (world > 1 and not shard and not args.gather) else
+                    "per rank") if world > 1 else "rii_query_batch (C ABI, host buffers)"}
     if world == 1:
         # single-query latency through the reference's own call shape (query_ivf, one query per call)
         qs = Q[:200]
@@ -686,7 +728,8 @@ def run_ours(args):
                    "batch_queries_per_step": B, "l2": "flushed between steps (256 MB write)",
                    "parallelism": "1 GPU" if world == 1 else
                    ("id-range shards x%d + one packed NCCL all-gather of per-shard top-k + merge" % world if shard else
-                    "index replicated x%d, queries split, one packed NCCL all-gather of the results" % world),
+                    "index replicated x%d, queries split%s" % (world, ", one packed NCCL all-gather of the results" if args.gather else
+                                                                  "; no collective on this path (each rank returns the results of its own queries)")),
                    "index_build_s": round(t_build, 2)},
         "recall_at_1": round(recall, 4),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -703,6 +746,8 @@ def run_ours(args):
                                      "roofline_linear_scan and the sharded C4/C5 legs"}},
         "kernel_ms": prof,
     }
+    if no_gather is not None:
+        line["replicas_with_all_gather" if no_gather["all_gather"] else "replicas_without_all_gather"] = no_gather
     if lin is not None:
         line["roofline_linear_scan"] = lin
     if subset is not None:
@@ -827,6 +872,8 @@ if __name__ == "__main__":
                          "the GPU cannot hold it); 1 GPU only")
     ap.add_argument("--no-large", action="store_true", help="skip the C4 / C5 sharded legs (weak scaling, 12.5M / 125M codes per GPU)")
     ap.add_argument("--quick", action="store_true", help="skip the C3 subset leg")
+    ap.add_argument("--gather", action="store_true", help="multi-GPU replicas: also all-gather the results so that every rank holds the whole batch "
+                                                          "(one packed NCCL collective per step inside the timed region)")
     ap.add_argument("--shard", action="store_true", help="multi-GPU: partition the index by id range instead of replicating it")
     a = ap.parse_args()
     if a.warmup < 3:
