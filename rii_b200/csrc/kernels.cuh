@@ -745,17 +745,6 @@ __global__ void k_gather_rows(const uint8_t *__restrict__ codes, const long long
     out[i] = codes[pick[r] * M + m];
 }
 
-// list-ordered copy of the codes: out[p] = codes[ids[p]] (32-byte rows, 16 bytes per thread)
-__global__ void k_gather_rows32_by_list(const uint8_t *__restrict__ codes, const int *__restrict__ ids, long long n,
-                                        uint8_t *__restrict__ out)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
-    if (i >= n * 2) return;
-    const long long p = i >> 1;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(codes + (size_t)ids[p] * 32) + (i & 1));
-    reinterpret_cast<uint4 *>(out)[i] = v;
-}
-
 // histogram of code bytes per (cluster, subspace): hist[k][m][ks].  src/pqkmeans.cpp:229-233
 __global__ void k_vote_hist(const uint8_t *__restrict__ codes, const int *__restrict__ assign, long long n, int M,
                             int Ks, int *hist)

@@ -212,7 +212,7 @@ __device__ __forceinline__ int warp_select_smallest(const uint32_t *d, int np, i
 template <bool K1>
 __global__ void __launch_bounds__((PS_NC + 1) * 32, 1) k_scan_persist32(SkewArgs a, int nq)
 {
-    constexpr int H = 1, ST_R = PS_R, ST_D = PS_R - 1;
+    constexpr int ST_R = PS_R, ST_D = PS_R - 1;  // (rows of 32 bytes: H = 1)
     constexpr uint32_t TB = 0;  // the table base is in colreg
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
