@@ -768,17 +768,10 @@ int run_linear(rii_index *h, const float *d_Q, int B, int topk, const long long 
             sa.codes = h->skew_lin.as<uint8_t>();
             sa.N = h->N;
         }
-        // CTAs per query.  Fewer queries than SMs: spread each over 148 / B CTAs.  More: B CTAs of one query each leave the last
-        // wave partly empty (256 queries on 148 SMs: 2 waves for 1.73 waves of work), so split every query into the `parts`
-        // that minimise waves x (table build + rows per CTA) -- the table build costs about as much as scanning 1800 rows.
-        int parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)), std::max<long long>(1, sa.N / (nw * SK_TILE_ROWS * 4)));
-        if (B > 148 && sa.N >= 32768) {
-            double best = 0;
-            for (int p_ = 1; p_ <= 8 && (long long)p_ * topk <= 256; ++p_) {
-                const double waves = std::ceil((double)B * p_ / 148.0), cost = waves * (1800.0 + (double)sa.N / p_);
-                if (p_ == 1 || cost < best * 0.97) { best = cost; parts = p_; }
-            }
-        }
+        // CTAs per query: fewer queries than SMs -> each is spread over 148 / B CTAs.  (For B > 148 a wave-aware split -- 256 queries
+        // on 148 SMs are 2 waves for 1.73 waves of work -- was measured: 4 CTAs per query made the C3 linear leg 9 % SLOWER, the
+        // per-CTA table build, pipeline fill and partial-list merge cost more than the emptier last wave.)
+        const int parts = (int)std::min<long long>(std::max(1, 148 / std::min(B, 148)), std::max<long long>(1, sa.N / (nw * SK_TILE_ROWS * 4)));
         out.final = parts == 1;
         bool in_kernel = false;
         if (!out.final) CKR(prepare_partial(h, B, parts, topk, &out, st, &in_kernel));
