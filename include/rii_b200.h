@@ -176,9 +176,12 @@ int rii_query_ranked_dev(rii_index_t *h, const float *d_queries, int B, int topk
                          float *d_out_dists, int32_t *d_out_counts, int32_t *d_flags, void *stream);
 
 /* Tuning knobs.  "scan_kernel": 0 = auto, 1 = natural-layout kernels only, 4 = the skew64 streaming engine or fail
- * (what auto picks for 12 <= M <= 64, topk <= 224, ascending target_ids).  "stream_ctas": 1 = always one CTA per SM.
- * "fuse_coarse": 0 = coarse ranking in its own launch.  "assign_kernel": 0 = auto, 1 = natural-layout k_assign, 3 =
- * streaming assignment engine with one CTA per SM.  Results are identical for every setting. */
+ * (what auto picks for 12 <= M <= 64, topk <= 224, ascending target_ids, N >= 32768).  "persist": 0 = never use the persistent
+ * warp-specialised batch kernel, 1 = auto (batches of >= 296 queries), 2 = whenever the shape fits.  "stream_ctas": 1 = always
+ * one CTA per SM.  "fuse_coarse": 0 = coarse ranking in its own launch.  "zero_copy": 0 = small host calls use staged copies
+ * instead of the pinned, device-mapped buffer.  "assign_kernel": 0 = auto, 1 = natural-layout k_assign, 3 = streaming
+ * assignment engine with one CTA per SM.  "debug_clocks": 1 = record per-CTA phase clocks (rii_debug_clocks).
+ * Results are identical for every setting. */
 int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
@@ -187,9 +190,11 @@ int rii_set_option(rii_index_t *h, const char *name, int64_t value);
 int rii_profile_enable(rii_index_t *h, int on);
 int rii_profile_reset(rii_index_t *h);
 int rii_profile_get(rii_index_t *h, const char *kernel, double *ms_total, int64_t *launches);
-/* With option "debug_clocks" = 1 the v2 scan kernel records clock64() per CTA: [0] start, [1] ready to scan (table,
- * and for the fused kernel coarse ranking + plan), [2] scan done, [3] end, [4] table built, [5] coarse pass done,
- * [6] coarse pool sorted, [7] = pool size; this copies the (n_ctas, 8) values of the last launch to the host. */
+/* With option "debug_clocks" = 1 the scan kernels record clock64() values per CTA; this copies (n_ctas, 8) int64 of the last
+ * launch to the host.  k_scan_stream32: [0] start, [1] ready to scan (table, and for the fused kernel coarse ranking + plan),
+ * [2] scan done, [3] end, [4] table built, [5] coarse pass done, [6] coarse pool sorted, [7] = pool size.  k_scan_persist32:
+ * 16 counters per CTA (two rows): cycles waiting / scanning of consumer warps 0 and 10, producer cycles waiting / merging /
+ * table / coarse pass / selection / plan, queries of the CTA (tools/phase_clocks.py). */
 int rii_debug_clocks(rii_index_t *h, int64_t n_ctas, int64_t *out);
 
 #ifdef __cplusplus
