@@ -199,3 +199,125 @@ def test_segment_walk_emits_every_candidate_once_with_the_exact_distance(M, nwar
         exp = O.adist_all(T, c[:take])
         g = np.array([got[(s, r)] for r in range(take)], np.float32)
         assert np.array_equal(bits(g), bits(exp)), "segment %d" % s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: the same walk as a list of RUNS (ST_ISSUE of scan_stream.cuh / PS_ISSUE of scan_persist.cuh): inside a run the
+# issue logic is a pointer increment and a counter (run_left), the segment tables are read by next_run() only, and the
+# row-valid bits are 3 except for the last group of a run that ends with its segment (last_bits from the take count).
+def issue_blocks_runs(segs_groups, takes, f0, f_end, H):
+    """Block sequence of one warp from the run-based logic: list of (segment, block in segment, descriptor or None) with
+    descriptor = (flattened group, segment, group in segment, valid-bits function of the lane)."""
+    gcum = np.cumsum(segs_groups)
+    out = []
+    if f_end <= f0:
+        return out
+    seg = int(np.searchsorted(gcum, f0, side="right"))
+    seg_g0, seg_gend = (int(gcum[seg - 1]) if seg else 0), int(gcum[seg])
+    cur_f, hb, run_left, bp, tail = f0, 0, 0, None, 64
+    sb = int(np.searchsorted(gcum, f_end - 1, side="right"))
+    nblk = ((f_end - f0) + (sb - seg + 1)) * H
+    for _ in range(nblk):
+        if run_left == 0:  # next_run()
+            if cur_f == seg_gend:
+                seg += 1
+                seg_g0, seg_gend = seg_gend, int(gcum[seg])
+            end = min(seg_gend, f_end)
+            run_left = (end - cur_f + 1) * H
+            bp = (cur_f - seg_g0) * H
+            tail = takes[seg] - (seg_gend - seg_g0 - 1) * 64 if end == seg_gend else 64
+        if run_left <= H:
+            d = None
+        elif H == 2 and hb:
+            d, hb = None, 0
+            cur_f += 1
+        else:
+            g = cur_f - seg_g0
+            last = run_left <= 2 * H
+            d = (cur_f, seg, g, (tail if last else 64))
+            if H == 1:
+                cur_f += 1
+            else:
+                hb = 1
+        out.append((seg, bp, d))
+        bp += 1
+        run_left -= 1
+    return out
+
+
+@pytest.mark.parametrize("H", [1, 2])
+def test_run_based_walk_issues_the_same_blocks_and_valid_rows(H):
+    rng = np.random.default_rng(40 + H)
+    for trial in range(300):
+        nseg = int(rng.integers(1, 9))
+        lens = [int(rng.integers(1, 400)) for _ in range(nseg)]
+        takes = list(lens)
+        if rng.random() < 0.5:
+            takes[-1] = int(rng.integers(1, lens[-1] + 1))      # the plan's last segment may be cut mid-way
+        groups = [(t + 63) // 64 for t in takes]
+        G = sum(groups)
+        nw = int(rng.choice([1, 3, 6, 11, 12]))
+        per = (G + nw - 1) // nw
+        for w in range(nw):
+            f0, f_end = min(w * per, G), min((w + 1) * per, G)
+            old = issue_blocks(groups, takes, f0, f_end, H) if f_end > f0 else []
+            new = issue_blocks_runs(groups, takes, f0, f_end, H)
+            assert [(s, b) for s, b, _ in old] == [(s, b) for s, b, _ in new], (trial, w)
+            for (s, b, d0), (_, _, d1) in zip(old, new):
+                assert (d0 is None) == (d1 is None)
+                if d0 is not None:
+                    f, s2, g2 = d0
+                    assert (f, s2, g2) == d1[:3]
+                    for y in range(2):                           # valid bits == "row < take" of the per-block logic
+                        for l in (0, 1, 31):
+                            r = 64 * g2 + 32 * y + l
+                            assert (r < takes[s2]) == (32 * y + l < d1[3]), (trial, w, f, y, l)
+
+
+def test_top1_selection_rule_equals_the_global_minimum_under_dist_id():
+    """The topk = 1 instantiations keep, per warp, the best (distance, position) of the groups they walk: a later candidate
+    replaces it only with a strictly smaller distance -- or, on an exact tie in ANOTHER segment, with a smaller id (ids ascend
+    with the position inside a segment, not across segments).  The merge takes the minimum (distance, id) over the warps.
+    Model of that rule against the brute-force minimum, with heavy ties."""
+    rng = np.random.default_rng(7)
+    for trial in range(400):
+        nseg = int(rng.integers(1, 7))
+        lens = [int(rng.integers(1, 150)) for _ in range(nseg)]
+        total = sum(lens)
+        ids = [np.sort(rng.choice(10 * total, n, replace=False)) for n in lens]       # ascending inside a segment
+        all_ids = np.concatenate(ids)
+        if len(set(all_ids.tolist())) != total:
+            continue
+        dist = [rng.integers(0, 4, n).astype(np.float32) for n in lens]               # 4 distinct values: ties everywhere
+        groups = [(n + 63) // 64 for n in lens]
+        G = sum(groups)
+        gcum = np.cumsum(groups)
+        nw = int(rng.choice([1, 2, 5, 11]))
+        per = (G + nw - 1) // nw
+        finals = []
+        for w in range(nw):
+            f0, f_end = min(w * per, G), min((w + 1) * per, G)
+            best = None  # (dist, pos, seg, id)
+            for f in range(f0, f_end):
+                s = int(np.searchsorted(gcum, f, side="right"))
+                g = f - (int(gcum[s - 1]) if s else 0)
+                rows = [r for r in range(64 * g, min(64 * g + 64, lens[s]))]
+                if best is not None:
+                    rows_pass = [r for r in rows if dist[s][r] <= best[0]]
+                else:
+                    rows_pass = rows
+                if not rows_pass:
+                    continue
+                mn = min(dist[s][r] for r in rows_pass)
+                # lowest position at that distance: x rows (lane) before y rows (32 + lane) == ascending row inside the group
+                r = min(r for r in rows_pass if dist[s][r] == mn)
+                if best is None or mn < best[0]:
+                    best = (mn, (f, r), s, int(ids[s][r]))
+                elif s != best[2] and int(ids[s][r]) < best[3]:
+                    best = (mn, (f, r), s, int(ids[s][r]))
+            if best is not None:
+                finals.append((best[0], best[3]))
+        got = min(finals)
+        flat_d = np.concatenate(dist)
+        o = np.lexsort((all_ids, flat_d))[0]
+        assert got == (flat_d[o], int(all_ids[o])), trial
