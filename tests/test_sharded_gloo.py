@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the id-range sharding host logic of rii_b200/sharded.py (sample assembly, list
+"""CPU, world_size 2 and 3 over gloo: the id-range sharding host logic of rii_b200/sharded.py (sample assembly, list
 length exchange, per-shard IVF cut, all-gather + (distance, id) merge) reproduces the unsharded oracle."""
 import os
 import subprocess
@@ -19,11 +19,15 @@ def test_shard_bounds_and_sample_ids():
     assert sorted(sharded.reference_sample_ids(30, 20).tolist()) == list(range(30))
 
 
-def test_world2_gloo_matches_unsharded_oracle():
-    port = 29500 + os.getpid() % 2000
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_shards_match_unsharded_oracle(world):
+    port = 29500 + (os.getpid() + 7 * world) % 2000
     procs = []
-    for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    OMP_NUM_THREADS="2")
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_shard_worker.py")], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
